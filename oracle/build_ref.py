@@ -1,0 +1,57 @@
+"""oracle/build_ref.py -- compile the reference's own CPU ops in place.  TEST INFRASTRUCTURE.
+
+Builds oracle/_ref/detmatch_ref_cpu.so from
+  /root/reference/mmdet3d/ops/voxel/src/voxelization_cpu.cpp
+  /root/reference/mmdet3d/ops/roiaware_pool3d/src/points_in_boxes_cpu.cpp
+plus oracle/ref_shim.cpp (ours).  Nothing from /root/reference is copied into the repo;
+oracle/_ref/ is git-ignored but travels to the GPU box with the gpurun snapshot.
+
+The reference's setup.py cannot build these two extensions without CUDA sources
+(setup.py:199-219 lists the .cu files unconditionally), so the translation units are
+compiled directly.  Flags: -O2 (what torch's cpp_extension / the reference's setup.py use,
+setup.py:41-47 adds no -O flag so distutils' default -O2/-O3 applies) and
+-ffp-contract=off (a no-op on baseline x86-64, pinned so that -march changes or an aarch64
+host cannot silently fuse the rotation).
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("DETMATCH_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+NAME = "detmatch_ref_cpu"
+
+SOURCES = [
+    os.path.join(HERE, "ref_shim.cpp"),
+    os.path.join(REF, "mmdet3d/ops/voxel/src/voxelization_cpu.cpp"),
+    os.path.join(REF, "mmdet3d/ops/roiaware_pool3d/src/points_in_boxes_cpu.cpp"),
+]
+
+
+def built_path():
+    return os.path.join(OUT, NAME + ".so")
+
+
+def build(verbose=False):
+    """Returns the path of the built module, or None when /root/reference is absent."""
+    if not all(os.path.exists(s) for s in SOURCES):
+        return built_path() if os.path.exists(built_path()) else None
+    if os.path.exists(built_path()) and all(
+            os.path.getmtime(built_path()) >= os.path.getmtime(s) for s in SOURCES):
+        return built_path()
+    os.makedirs(OUT, exist_ok=True)
+    from torch.utils import cpp_extension
+    cpp_extension.load(
+        name=NAME,
+        sources=SOURCES,
+        extra_cflags=["-O2", "-ffp-contract=off", "-fno-fast-math"],
+        build_directory=OUT,
+        verbose=verbose,
+        is_python_module=False,  # only build; oracle/ref.py loads it by path
+    )
+    return built_path()
+
+
+if __name__ == "__main__":
+    p = build(verbose="-v" in sys.argv)
+    print(p if p else "reference tree not found; nothing built")

@@ -1,0 +1,386 @@
+/*
+ * oracle/pcfe_oracle.c -- CPU restatement of the reference's point-to-cell and
+ * point-to-box ops in plain C.  TEST INFRASTRUCTURE ONLY (see pcfe_oracle.h).
+ *
+ * Parity status: PINNED against the reference's known-answer tests and against
+ * the reference's own .cpp files compiled in place (oracle/_ref), see
+ * tests/test_oracle.py.
+ *
+ * Build: gcc -O2 -fPIC -shared -ffp-contract=off -fno-fast-math (oracle/Makefile).
+ * -ffp-contract=off matters: the reference's rotation `sx*cosa + sy*(-sina)` is
+ * evaluated with two roundings on baseline x86-64; a fused multiply-add would
+ * change mask bits for points within ~1 ulp of a box face.
+ */
+#define _GNU_SOURCE /* M_PI, sincosf */
+#include "pcfe_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------- */
+/* helpers                                                                   */
+/* ------------------------------------------------------------------------- */
+
+/* (int)floor(v) as x86-64 evaluates it: cvttsd2si returns INT_MIN ("integer
+ * indefinite") for NaN and for anything outside int32.  The reference relies
+ * on this (voxelization_cpu.cpp:23 assigns floor() to an int), so NaN/Inf/huge
+ * coordinates fail the `c < 0` test at :25. */
+static int floor_to_int_x86(double v) {
+  double f = floor(v);
+  if (!(f >= -2147483648.0 && f < 2147483648.0)) return INT_MIN;
+  return (int)f;
+}
+
+void pcfe_oracle_grid_size(const float vs[3], const float range[6], int grid[3]) {
+  for (int j = 0; j < 3; ++j) {
+    /* float32 subtract, float32 divide, round half away from zero
+     * (voxelization_cpu.cpp:119-122). */
+    float q = (range[3 + j] - range[j]) / vs[j];
+    grid[j] = (int)roundf(q);
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* dynamic voxelization  (voxelization_cpu.cpp:7-41)                          */
+/* ------------------------------------------------------------------------- */
+
+int pcfe_oracle_dynamic_voxelize_f32(const float* points, int64_t n, int c,
+                                     const float vs[3], const float range[6],
+                                     int32_t* coors) {
+  if (n < 0 || c < 3) return -1;
+  int grid[3];
+  pcfe_oracle_grid_size(vs, range, grid);
+  for (int64_t i = 0; i < n; ++i) {
+    const float* p = points + i * c;
+    int coor[3];
+    int failed = 0;
+    for (int j = 0; j < 3; ++j) {
+      /* T = float: float - float -> float, / float -> float (:23) */
+      float q = (p[j] - range[j]) / vs[j];
+      int cj = floor_to_int_x86((double)q);
+      if (cj < 0 || cj >= grid[j]) { /* :25 */
+        failed = 1;
+        break;
+      }
+      coor[2 - j] = cj; /* :29, (z,y,x) order */
+    }
+    for (int k = 0; k < 3; ++k) coors[i * 3 + k] = failed ? -1 : coor[k]; /* :32-37 */
+  }
+  return 0;
+}
+
+int pcfe_oracle_dynamic_voxelize_f64(const double* points, int64_t n, int c,
+                                     const float vs[3], const float range[6],
+                                     int32_t* coors) {
+  if (n < 0 || c < 3) return -1;
+  int grid[3];
+  pcfe_oracle_grid_size(vs, range, grid);
+  for (int64_t i = 0; i < n; ++i) {
+    const double* p = points + i * c;
+    int coor[3];
+    int failed = 0;
+    for (int j = 0; j < 3; ++j) {
+      /* T = double: double - (double)float, / (double)float (:23) */
+      double q = (p[j] - (double)range[j]) / (double)vs[j];
+      int cj = floor_to_int_x86(q);
+      if (cj < 0 || cj >= grid[j]) {
+        failed = 1;
+        break;
+      }
+      coor[2 - j] = cj;
+    }
+    for (int k = 0; k < 3; ++k) coors[i * 3 + k] = failed ? -1 : coor[k];
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* hard voxelization  (voxelization_cpu.cpp:43-99, :105-142)                  */
+/* ------------------------------------------------------------------------- */
+
+/* The reference allocates a dense (gz,gy,gx) int32 grid filled with -1 on every
+ * call (:127-128).  The oracle keeps one such grid cached between calls and
+ * restores the cells it touched, which is observably identical and lets the
+ * CPU test-suite run in seconds.  (bench.py times oracle/_ref, i.e. the real
+ * reference including its per-call grid init, when it is available.) */
+static int32_t* g_grid = NULL;
+static size_t g_grid_cells = 0;
+
+static int32_t* acquire_grid(size_t cells) {
+  if (cells > g_grid_cells) {
+    free(g_grid);
+    g_grid = (int32_t*)malloc(cells * sizeof(int32_t));
+    if (!g_grid) {
+      g_grid_cells = 0;
+      return NULL;
+    }
+    memset(g_grid, 0xff, cells * sizeof(int32_t)); /* all -1 */
+    g_grid_cells = cells;
+  }
+  return g_grid;
+}
+
+#define HARD_VOXELIZE_BODY(T, DYNAMIC)                                              \
+  if (n < 0 || c < 3) return -1;                                                    \
+  int grid[3];                                                                      \
+  pcfe_oracle_grid_size(vs, range, grid);                                           \
+  if (grid[0] <= 0 || grid[1] <= 0 || grid[2] <= 0) return -2;                      \
+  size_t cells = (size_t)grid[0] * (size_t)grid[1] * (size_t)grid[2];               \
+  int32_t* g = acquire_grid(cells);                                                 \
+  if (!g) return -3;                                                                \
+  int32_t* temp = (int32_t*)malloc((size_t)(n > 0 ? n : 1) * 3 * sizeof(int32_t));  \
+  if (!temp) return -3;                                                             \
+  DYNAMIC(points, n, c, vs, range, temp); /* :56-63 */                              \
+  int voxel_num = 0;                                                                \
+  for (int64_t i = 0; i < n; ++i) { /* :68-96 */                                    \
+    const int32_t* co = temp + i * 3;                                               \
+    if (co[0] == -1) continue; /* :71 */                                            \
+    size_t cell = ((size_t)co[0] * grid[1] + co[1]) * grid[0] + co[2];              \
+    int voxelidx = g[cell]; /* :73 */                                               \
+    if (voxelidx == -1) {   /* :76 */                                               \
+      voxelidx = voxel_num;                                                         \
+      if (max_voxels != -1 && voxel_num >= max_voxels) continue; /* :78 */          \
+      voxel_num += 1;                                                               \
+      g[cell] = voxelidx;                                                           \
+      for (int k = 0; k < 3; ++k) coors[(size_t)voxelidx * 3 + k] = co[k]; /* :83 */\
+    }                                                                               \
+    int num = num_out[voxelidx]; /* :89 */                                          \
+    if (max_points == -1 || num < max_points) {                                     \
+      T* dst = voxels + ((size_t)voxelidx * (size_t)pstride + (size_t)num) * c;     \
+      const T* src = points + i * c;                                                \
+      for (int k = 0; k < c; ++k) dst[k] = src[k]; /* :91-93 */                     \
+      num_out[voxelidx] += 1;                                                       \
+    }                                                                               \
+  }                                                                                 \
+  /* restore the cached grid to all -1 */                                           \
+  for (int64_t i = 0; i < n; ++i) {                                                 \
+    const int32_t* co = temp + i * 3;                                               \
+    if (co[0] == -1) continue;                                                      \
+    g[((size_t)co[0] * grid[1] + co[1]) * grid[0] + co[2]] = -1;                    \
+  }                                                                                 \
+  free(temp);                                                                       \
+  return voxel_num;
+
+int pcfe_oracle_hard_voxelize_f32(const float* points, int64_t n, int c,
+                                  const float vs[3], const float range[6],
+                                  int max_points, int max_voxels,
+                                  float* voxels, int32_t* coors, int32_t* num_out) {
+  /* slot stride of the voxels buffer: (max_voxels, max_points, c) */
+  const int pstride = max_points;
+  HARD_VOXELIZE_BODY(float, pcfe_oracle_dynamic_voxelize_f32)
+}
+
+int pcfe_oracle_hard_voxelize_f64(const double* points, int64_t n, int c,
+                                  const float vs[3], const float range[6],
+                                  int max_points, int max_voxels,
+                                  double* voxels, int32_t* coors, int32_t* num_out) {
+  const int pstride = max_points;
+  HARD_VOXELIZE_BODY(double, pcfe_oracle_dynamic_voxelize_f64)
+}
+
+/* ------------------------------------------------------------------------- */
+/* glibc sinf / cosf restated                                                */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+  double sign[4];
+  double hpi_inv; /* 2/pi * 2^24 */
+  double hpi;     /* pi/2 */
+  double c0, c1, c2, c3, c4;
+  double s1, s2, s3;
+} sincos_tab_t;
+
+static const sincos_tab_t k_tab[2] = {
+    {{1.0, -1.0, -1.0, 1.0},
+     0x1.45F306DC9C883p+23,
+     0x1.921FB54442D18p0,
+     0x1p0,
+     -0x1.ffffffd0c621cp-2,
+     0x1.55553e1068f19p-5,
+     -0x1.6c087e89a359dp-10,
+     0x1.99343027bf8c3p-16,
+     -0x1.555545995a603p-3,
+     0x1.1107605230bc4p-7,
+     -0x1.994eb3774cf24p-13},
+    {{1.0, -1.0, -1.0, 1.0},
+     0x1.45F306DC9C883p+23,
+     0x1.921FB54442D18p0,
+     -0x1p0,
+     0x1.ffffffd0c621cp-2,
+     -0x1.55553e1068f19p-5,
+     0x1.6c087e89a359dp-10,
+     -0x1.99343027bf8c3p-16,
+     -0x1.555545995a603p-3,
+     0x1.1107605230bc4p-7,
+     -0x1.994eb3774cf24p-13}};
+
+/* 4/pi to 192 bits, 8 new bits per entry. */
+static const uint32_t k_inv_pio4[24] = {
+    0xa2,       0xa2f9,     0xa2f983,   0xa2f9836e, 0xf9836e4e, 0x836e4e44,
+    0x6e4e4415, 0x4e441529, 0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1,
+    0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, 0x34ddc0db, 0xddc0db62,
+    0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
+
+static inline uint32_t f2u(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+static inline uint32_t abstop12(float f) { return (f2u(f) >> 20) & 0x7ff; }
+
+/* n even -> sine polynomial, n odd -> cosine polynomial.
+ * x86-64 glibc selects its FMA build of sinf/cosf (sysdeps/x86_64/fpu/multiarch/s_sinf-fma.c,
+ * compiled -mfma -mavx2) on every FMA-capable CPU, so each `a + b*c` below is ONE fused
+ * operation there.  The fma() calls are written out so that this file gives the same bits
+ * whatever -ffp-contract / -march it is compiled with.  (Un-fused evaluation differs from the
+ * host libm for 17 of the 24.1 M floats in [16,120) and for none below 16 -- measured.) */
+static inline float sc_poly(double x, double x2, const sincos_tab_t* p, int n) {
+  if ((n & 1) == 0) {
+    double x3 = x * x2;
+    double s1 = fma(x2, p->s3, p->s2);
+    double x7 = x3 * x2;
+    double s = fma(x3, p->s1, x);
+    return (float)fma(x7, s1, s);
+  } else {
+    double x4 = x2 * x2;
+    double c2 = fma(x2, p->c4, p->c3);
+    double c1 = fma(x2, p->c1, p->c0);
+    double x6 = x4 * x2;
+    double c = fma(x4, p->c2, c1);
+    return (float)fma(x6, c2, c);
+  }
+}
+
+static inline double reduce_fast(double x, const sincos_tab_t* p, int* np) {
+  double r = x * p->hpi_inv;
+  int n = ((int32_t)r + 0x800000) >> 24;
+  *np = n;
+  return fma(-(double)n, p->hpi, x); /* x - n*hpi, fused */
+}
+
+static inline double reduce_large(uint32_t xi, int* np) {
+  const uint32_t* arr = &k_inv_pio4[(xi >> 26) & 15];
+  int shift = (xi >> 23) & 7;
+  uint64_t n, res0, res1, res2;
+  xi = (xi & 0xffffff) | 0x800000;
+  xi <<= shift;
+  res0 = xi * arr[0]; /* 32-bit wrap-around multiply, as in glibc */
+  res1 = (uint64_t)xi * arr[4];
+  res2 = (uint64_t)xi * arr[8];
+  res0 = (res2 >> 32) | (res0 << 32);
+  res0 += res1;
+  n = (res0 + (1ULL << 61)) >> 62;
+  res0 -= n << 62;
+  double x = (double)(int64_t)res0;
+  *np = (int)n;
+  return x * 0x1.921FB54442D18p-62;
+}
+
+static float restated_sin_or_cos(float y, int want_cos) {
+  double x = (double)y;
+  const sincos_tab_t* p = &k_tab[0];
+  int n;
+  if (abstop12(y) < abstop12(0x1.921FB6p-1f)) {
+    double x2 = x * x;
+    if (abstop12(y) < abstop12(0x1p-12f)) return want_cos ? 1.0f : y;
+    return sc_poly(x, x2, p, want_cos);
+  } else if (abstop12(y) < abstop12(120.0f)) {
+    x = reduce_fast(x, p, &n);
+    double s = p->sign[n & 3];
+    if (n & 2) p = &k_tab[1];
+    return sc_poly(x * s, x * x, p, n ^ want_cos);
+  } else if (abstop12(y) < abstop12(INFINITY)) {
+    uint32_t xi = f2u(y);
+    int sign = (int)(xi >> 31);
+    x = reduce_large(xi, &n);
+    double s = p->sign[(n + sign) & 3];
+    if ((n + sign) & 2) p = &k_tab[1];
+    return sc_poly(x * s, x * x, p, n ^ want_cos);
+  }
+  return y - y; /* Inf/NaN -> NaN (glibc __math_invalidf) */
+}
+
+void pcfe_oracle_sincosf(float x, float* sinp, float* cosp) {
+  *sinp = restated_sin_or_cos(x, 0);
+  *cosp = restated_sin_or_cos(x, 1);
+}
+
+void pcfe_oracle_host_sincosf(float x, float* sinp, float* cosp) {
+  /* two separate libm calls behind volatile so gcc cannot merge them into
+   * sincosf; the sweep below checks sincosf too. */
+  volatile float vx = x;
+  *sinp = sinf(vx);
+  *cosp = cosf(vx);
+}
+
+int64_t pcfe_oracle_sincosf_sweep(uint32_t lo_bits, uint32_t hi_bits,
+                                  uint32_t stride, uint32_t* first_bad) {
+  int64_t bad = 0;
+  if (first_bad) *first_bad = 0;
+  if (stride == 0) stride = 1;
+  for (uint64_t b = lo_bits; b < hi_bits; b += stride) {
+    uint32_t u = (uint32_t)b;
+    float x;
+    memcpy(&x, &u, 4);
+    float rs, rc, hs, hc, ss, sc;
+    pcfe_oracle_sincosf(x, &rs, &rc);
+    pcfe_oracle_host_sincosf(x, &hs, &hc);
+    sincosf(x, &ss, &sc);
+    int mism = (f2u(rs) != f2u(hs)) || (f2u(rc) != f2u(hc)) ||
+               (f2u(ss) != f2u(hs)) || (f2u(sc) != f2u(hc));
+    /* NaN payloads are not part of the contract */
+    if (mism && isnan(rs) && isnan(hs) && isnan(rc) && isnan(hc)) mism = 0;
+    if (mism) {
+      if (bad == 0 && first_bad) *first_bad = u;
+      ++bad;
+    }
+  }
+  return bad;
+}
+
+/* ------------------------------------------------------------------------- */
+/* points in boxes  (points_in_boxes_cpu.cpp:16-69)                           */
+/* ------------------------------------------------------------------------- */
+
+static inline int check_pt_in_box3d(const float* pt, const float* box3d, int restated) {
+  float x = pt[0], y = pt[1], z = pt[2];
+  float cx = box3d[0], cy = box3d[1], cz = box3d[2];
+  float w = box3d[3], l = box3d[4], h = box3d[5], rz = box3d[6];
+  cz += h / 2.0; /* double add, rounded back to float (:33) */
+  if (fabsf(z - cz) > h / 2.0) return 0; /* float |dz| vs double h/2 (:35) */
+  float shift_x = x - cx, shift_y = y - cy; /* :36 */
+  float rot_angle = rz + M_PI / 2;          /* double add -> float (:19) */
+  float cosa, sina;
+  if (restated) {
+    pcfe_oracle_sincosf(rot_angle, &sina, &cosa);
+  } else {
+    cosa = cosf(rot_angle); /* :20 (cos/sin on a float resolve to cosf/sinf) */
+    sina = sinf(rot_angle);
+  }
+  float local_x = shift_x * cosa + shift_y * (-sina); /* :21 (no FMA) */
+  float local_y = shift_x * sina + shift_y * cosa;    /* :22 */
+  float in_flag = (local_x > -l / 2.0) & (local_x < l / 2.0) &
+                  (local_y > -w / 2.0) & (local_y < w / 2.0); /* :37-38 */
+  return (int)in_flag;
+}
+
+static int pib_impl(const float* boxes, int t, const float* points, int64_t n,
+                    int32_t* out, int restated) {
+  if (t < 0 || n < 0) return -1;
+  for (int i = 0; i < t; ++i)
+    for (int64_t j = 0; j < n; ++j) /* box-major (:60-66) */
+      out[(int64_t)i * n + j] = check_pt_in_box3d(points + j * 3, boxes + i * 7, restated);
+  return 1;
+}
+
+int pcfe_oracle_points_in_boxes_cpu(const float* boxes, int t,
+                                    const float* points, int64_t n, int32_t* out) {
+  return pib_impl(boxes, t, points, n, out, 0);
+}
+
+int pcfe_oracle_points_in_boxes_restated(const float* boxes, int t,
+                                         const float* points, int64_t n, int32_t* out) {
+  return pib_impl(boxes, t, points, n, out, 1);
+}

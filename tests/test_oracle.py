@@ -1,0 +1,134 @@
+"""CPU tests that pin the oracle (oracle/pcfe_oracle.c) before anything trusts it:
+
+1. against the golden vectors the reference itself produced (tests/golden/make_golden.py),
+   including the literals of the reference's own known-answer tests;
+2. against oracle/_ref (the reference's unmodified .cpp files compiled in place) on fresh
+   random inputs, when that build is present;
+3. the restated glibc sinf/cosf against the host libm.
+"""
+import struct
+
+import numpy as np
+import pytest
+
+from detmatch_b200 import synth
+from oracle import oracle, ref
+from tests.helpers import assert_same_bits, golden, golden_names
+
+
+def _bits(f):
+    return struct.unpack("<I", struct.pack("<f", f))[0]
+
+
+@pytest.mark.parametrize("name", golden_names("voxel_"))
+def test_oracle_voxel_golden(name):
+    g = golden(name)
+    if name == "voxel_generator_kat":
+        # tests/test_models/test_voxel_encoder/test_voxel_generator.py:6-22 literal
+        for pts, vox in ((g["points64"], g["voxels64"]), (g["points64"].astype(np.float32), g["voxels32"])):
+            v, c, n = oracle.hard_voxelize(pts, g["voxel_size"], g["range"], int(g["max_points"]), int(g["max_voxels"]))
+            assert_same_bits(c, g["coors"], "coors")
+            assert_same_bits(n, g["num"], "num")
+            assert_same_bits(v, vox, "voxels")
+        return
+    v, c, n = oracle.hard_voxelize(g["points"], g["voxel_size"], g["range"], int(g["max_points"]), int(g["max_voxels"]))
+    assert_same_bits(v, g["voxels"], "voxels")
+    assert_same_bits(c, g["coors"], "coors")
+    assert_same_bits(n, g["num"], "num")
+    if "dyn_coors" in g:
+        assert_same_bits(oracle.dynamic_voxelize(g["points"], g["voxel_size"], g["range"]), g["dyn_coors"], "dyn")
+
+
+def test_oracle_dynamic_matches_hard_content():
+    """tests/test_models/test_voxel_encoder/test_voxelize.py:49-59: points grouped by dynamic
+    coors, in order, equal the hard-voxelize content."""
+    g = golden("voxel_kitti_fixture")
+    coors = oracle.dynamic_voxelize(g["points"], g["voxel_size"], g["range"])
+    for i in range(g["coors"].shape[0]):
+        idx = np.all(coors == g["coors"][i], axis=1)
+        k = int(idx.sum())
+        assert k > 0 and k == g["num"][i]
+        assert np.array_equal(g["points"][idx], g["voxels"][i][:k])
+
+
+@pytest.mark.parametrize("name", golden_names("pib_"))
+def test_oracle_pib_golden(name):
+    g = golden(name)
+    for restated in (False, True):
+        out = oracle.points_in_boxes_cpu(g["points"], g["boxes"], restated_trig=restated)
+        assert_same_bits(out, g["expected_cpu"], f"{name} restated={restated}")
+    if name == "pib_kat":
+        assert_same_bits(oracle.points_in_boxes_gpu(g["gpu_points"], g["gpu_boxes"]), g["expected_gpu"], "gpu literal")
+        assert_same_bits(oracle.points_in_boxes_batch(g["batch_points"], g["batch_boxes"]), g["expected_batch"], "batch literal")
+
+
+def test_oracle_empty_inputs():
+    """the CPU ops accept N=0 / T=0."""
+    vs, rg = [0.5] * 3, [0, -40, -3, 70.4, 40, 1]
+    v, c, n = oracle.hard_voxelize(np.zeros((0, 4), np.float32), vs, rg, 5, 10)
+    assert v.shape == (0, 5, 4) and c.shape == (0, 3) and n.shape == (0,)
+    assert oracle.dynamic_voxelize(np.zeros((0, 4), np.float32), vs, rg).shape == (0, 3)
+    assert oracle.points_in_boxes_cpu(np.zeros((0, 3), np.float32), np.zeros((2, 7), np.float32)).shape == (2, 0)
+    assert oracle.points_in_boxes_cpu(np.zeros((5, 3), np.float32), np.zeros((0, 7), np.float32)).shape == (0, 5)
+
+
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg_name,ci", [("C1", 1), ("C4", 4), ("C5", 5)])
+def test_oracle_vs_reference_voxelize(cfg_name, ci):
+    import torch
+    cfg = synth.CONFIGS[cfg_name]
+    n = 30000
+    for k, pts in enumerate((synth.lidar_frame(n, cfg["c"], synth.seed_for(ci, 10), cfg["r_max"]),
+                             synth.uniform_frame(n, cfg["c"], synth.seed_for(ci, 11), cfg["point_cloud_range"]))):
+        mv = cfg["max_voxels"] // (8 if k == 0 else 20)
+        rv, rc, rn = ref.voxelization(pts, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], mv)
+        v, c, m = oracle.hard_voxelize(pts.numpy(), cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], mv)
+        assert_same_bits(v, rv.numpy(), "voxels")
+        assert_same_bits(c, rc.numpy(), "coors")
+        assert_same_bits(m, rn.numpy(), "num")
+        rd = ref.voxelization(pts, cfg["voxel_size"], cfg["point_cloud_range"], -1, -1)
+        assert_same_bits(oracle.dynamic_voxelize(pts.numpy(), cfg["voxel_size"], cfg["point_cloud_range"]), rd.numpy(), "dyn")
+        assert isinstance(rd, torch.Tensor)
+
+
+@needs_ref
+def test_oracle_vs_reference_pib():
+    import torch
+    c3 = synth.CONFIGS["C3"]
+    pts = synth.lidar_frame(20000, 3, synth.seed_for(3, 20), c3["r_max"])
+    bxs = synth.random_boxes(100, synth.seed_for(3, 21), c3["point_cloud_range"])
+    bxs[:30, 0:2] = pts[:30, 0:2]
+    bxs[:30, 2] = pts[:30, 2] - 0.4
+    fp = synth.face_points(bxs, 5, per_box=32)
+    pts = torch.cat([pts, fp])
+    exp = ref.points_in_boxes_cpu(pts, bxs).numpy()
+    assert exp.sum() > 200
+    assert_same_bits(oracle.points_in_boxes_cpu(pts.numpy(), bxs.numpy()), exp, "host trig")
+    assert_same_bits(oracle.points_in_boxes_cpu(pts.numpy(), bxs.numpy(), restated_trig=True), exp, "restated trig")
+
+
+def test_restated_sincosf_matches_host_libm():
+    """The device computes cosa/sina with this algorithm; it must equal the host libm the
+    reference calls (points_in_boxes_cpu.cpp:20).  Exhaustive over [2^-14, 16) takes ~2 s; the
+    rest of the float line is strided."""
+    sweeps = [
+        (0x00000000, _bits(2.0 ** -14), 997),
+        (_bits(2.0 ** -14), _bits(16.0), 1),
+        (_bits(16.0), _bits(120.0), 3),
+        (_bits(120.0), 0x7F800010, 211),
+        (0x80000000, 0x80000000 + _bits(16.0), 13),
+        (0x80000000 + _bits(16.0), 0xFF800010, 223),
+    ]
+    for lo, hi, stride in sweeps:
+        bad, first = oracle.sincosf_sweep(lo, hi, stride)
+        assert bad == 0, f"{bad} mismatches in [{lo:#x},{hi:#x}), first at bits {first:#x}"
+
+
+def test_grid_size_float32_rounding():
+    # (75.2+75.2)/0.1 = 1503.9999 in float32 -> round -> 1504
+    assert oracle.grid_size([0.1, 0.1, 0.15], [-75.2, -75.2, -2, 75.2, 75.2, 4]).tolist() == [1504, 1504, 40]
+    assert oracle.grid_size([0.05, 0.05, 0.1], [0, -40, -3, 70.4, 40, 1]).tolist() == [1408, 1600, 40]
+    assert oracle.grid_size([0.25, 0.25, 8], [-50, -50, -5, 50, 50, 3]).tolist() == [400, 400, 1]
