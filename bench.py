@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric: M points/s of Waymo-shape hard voxelization
+(config C4: 64 frames x 180 000 points x 5 features per GPU, voxel [0.1,0.1,0.15], range
+[-75.2,-75.2,-2,75.2,75.2,4], max_points 5, max_voxels 150 000) on N B200s, next to the HBM
+roofline and the reference's CPU op timed on the same host.
+
+    python bench.py --gpus 1 --steps K --warmup W                 (our arm, one GPU)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N GPUs)
+    python bench.py --impl reference --gpus N --steps K --warmup W    (reference CPU arm)
+
+A step = one pass of the hot path over one batch of 64 synthetic frames per GPU.  Frames shard
+across GPUs with no collective (weak scaling: every rank voxelizes its own 64 frames); the only
+communication is a barrier and a MAX over the ranks' device times.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "C4"
+METRIC = "hard_voxelize_throughput"
+UNIT = "Mpoints/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the config's 64)")
+    ap.add_argument("--workload", default=WORKLOAD, choices=["C1", "C4", "C5"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--frames-in-flight", type=int, default=0)
+    ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (default: all cores, <= 64)")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    from detmatch_b200 import synth
+    cfg = dict(synth.CONFIGS[args.workload])
+    if args.frames > 0:
+        cfg["frames"] = args.frames
+    cfg["index"] = int(args.workload[1])
+    return cfg
+
+
+def algorithmic_bytes(n, c, p, m_list):
+    """every input row read once, every returned output element written once:
+    N*C*4 + M*(P*C*4 + 3*4 + 4) per frame, M = returned voxel_num."""
+    return sum(n * c * 4 + m * (p * c * 4 + 16) for m in m_list)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        return self
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU op (oracle/_ref) on the host cores
+# --------------------------------------------------------------------------------------------
+def _ref_worker(conn, cfg, frame_id, use_ref):
+    """One single-threaded worker: owns one frame, voxelizes it with the reference op on demand."""
+    import torch
+    torch.set_num_threads(1)
+    from detmatch_b200 import synth
+    if use_ref:
+        from oracle import ref
+        ref.module()
+    else:
+        from oracle import oracle
+        oracle.lib()
+    pts = synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(cfg["index"], frame_id), cfg["r_max"])
+    conn.send("ready")
+    while True:
+        cmd = conn.recv()
+        if cmd != "run":
+            break
+        if use_ref:
+            # voxelize.py:46-58 call pattern, including the three new_zeros
+            v, c, n = ref.voxelization(pts, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], cfg["max_voxels"])
+        else:
+            v, c, n = oracle.hard_voxelize(pts.numpy(), cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], cfg["max_voxels"])
+        conn.send(int(n.shape[0]))
+
+
+def run_reference(args, quiet=False):
+    """Times the reference's CPU hard_voxelize on this host: one single-threaded worker process
+    per core, one frame per worker per step (a bounded sample of the workload)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    import multiprocessing as mp
+    cfg = workload_config(args)
+    from oracle import ref
+    use_ref = ref.available()
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    procs = args.ref_procs if args.ref_procs > 0 else min(cores, 64)
+    procs = max(1, min(procs, cfg["frames"] * max(args.gpus, 1)))
+    ctx = mp.get_context("fork")
+    workers = []
+    for k in range(procs):
+        parent, child = ctx.Pipe()
+        p = ctx.Process(target=_ref_worker, args=(child, cfg, k, use_ref), daemon=True)
+        p.start()
+        workers.append((p, parent))
+    for _, conn in workers:
+        assert conn.recv() == "ready"
+
+    def step():
+        t0 = time.perf_counter()
+        for _, conn in workers:
+            conn.send("run")
+        ms = [conn.recv() for _, conn in workers]
+        return time.perf_counter() - t0, ms
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    times, ms = [], None
+    for _ in range(max(args.steps, 1)):
+        dt, ms = step()
+        times.append(dt)
+    for p, conn in workers:
+        conn.send("stop")
+        p.join(timeout=5)
+    t_step = sum(times) / len(times)
+    pts_per_step = procs * cfg["n"]
+    value = pts_per_step / t_step / 1e6
+    kind = "reference" if use_ref else "port"
+    sample = (f"{procs} frames/step ({cfg['n']} pts x {cfg['c']}), one single-threaded worker process per core, "
+              f"{len(times)} steps; {'oracle/_ref = reference voxelization_cpu.cpp compiled in place' if use_ref else 'oracle C port'}")
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": max(args.warmup, 1), "ms_per_step": round(t_step * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": _config_dict(cfg, args, frames_per_step=procs),
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": procs, "kind": kind, "sample": sample,
+                         "host_cores_visible": cores, "mean_voxels_per_frame": round(sum(ms) / len(ms), 1)},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    if not quiet:
+        print(json.dumps(line), flush=True)
+    return line
+
+
+def _config_dict(cfg, args, frames_per_step):
+    return {"workload": f"{args.workload}: Waymo-shape hard voxelization" if args.workload == "C4" else args.workload,
+            "frames_per_gpu_per_step": frames_per_step, "points_per_frame": cfg["n"], "features": cfg["c"],
+            "voxel_size": cfg["voxel_size"], "point_cloud_range": cfg["point_cloud_range"],
+            "max_num_points": cfg["max_num_points"], "max_voxels": cfg["max_voxels"],
+            "generator": "LiDAR-like (SURVEY 8(d)), seed = 1000*config + frame",
+            "l2": "inputs+outputs per step (~0.94 GB) exceed the 126 MB L2; no explicit flush",
+            "sharding": "frames, no collective"}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from detmatch_b200 import _cabi, synth
+    from detmatch_b200.ops.voxel import HardVoxelizeBatchPlan
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = workload_config(args)
+    F, N, C = cfg["frames"], cfg["n"], cfg["c"]
+    P, V = cfg["max_num_points"], cfg["max_voxels"]
+
+    # synthetic frames, generated on the host; each rank has its own 64 frames
+    host = [synth.lidar_frame(N, C, synth.seed_for(cfg["index"], rank * F + k), cfg["r_max"]).pin_memory() for k in range(F)]
+    pts = [h.to(dev, non_blocking=True) for h in host]
+    torch.cuda.synchronize(dev)
+    plan = HardVoxelizeBatchPlan([N] * F, C, cfg["voxel_size"], cfg["point_cloud_range"], P, V, dev,
+                                 frames_in_flight=args.frames_in_flight).bind(pts)
+    L = _cabi.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        plan.run()
+    barrier()
+    m_list = plan.voxel_num.cpu().tolist()
+
+    # ---- timed region: K steps, device time, inputs resident in HBM -------------------------
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = L.pcfe_launch_count()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        plan.run()
+    e1.record()
+    barrier()
+    launches = L.pcfe_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0 and clocks and clocks["samples"] < 3:
+        # timed region shorter than the sampling period: sample an identical untimed loop
+        sampler = ClockSampler(local_rank).start()
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            plan.run()
+        torch.cuda.synchronize(dev)
+        clocks = sampler.stop()
+        clocks["note"] = "timed region < sampling period; sampled during an identical untimed loop right after"
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    total_points = world * F * N
+    value = total_points / (ms_step * 1e-3) / 1e6
+
+    # ---- per-kernel attribution (separate, untimed pass) -------------------------------------
+    kernels = None
+    if rank == 0:
+        _cabi.profile(True)
+        for _ in range(3):
+            plan.run()
+        torch.cuda.synchronize(dev)
+        rep = _cabi.profile_report()
+        _cabi.profile(False)
+        tot = sum(v[0] for v in rep.values()) or 1.0
+        kernels = {k: {"ms_per_step": round(v[0] / 3, 4), "launches_per_step": v[1] // 3, "share": round(v[0] / tot, 3)}
+                   for k, v in rep.items()}
+
+    # ---- end to end through the public API with HOST buffers --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, cfg, plan, host, pts, dev, world, barrier)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline ----------------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    algo = algorithmic_bytes(N, C, P, m_list)  # one rank's step
+    achieved = algo / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None,
+                "kernel": "hard-voxelize launch sequence (memset + K1..K5 per wave), per GPU",
+                "algorithmic_bytes_per_step": algo, "peak_source": peak_src,
+                "mean_voxels_per_frame": round(sum(m_list) / len(m_list), 1)}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu_baseline = cpu_baseline_subprocess(args)
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+        "config": _config_dict(cfg, args, frames_per_step=F),
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "kernels": kernels,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, cfg, plan, host, pts, dev, world, barrier):
+    """Same metric through the public batched call with HOST buffers: every step copies the 64
+    frames from pinned host memory to the device, voxelizes, reads voxel_num back and copies the
+    returned rows (voxels[:M], coors[:M], num_points[:M] of every frame) into pinned host memory."""
+    import torch
+    import torch.distributed as dist
+    F, N, C = cfg["frames"], cfg["n"], cfg["c"]
+    P, V = cfg["max_num_points"], cfg["max_voxels"]
+    out_vox = torch.empty((F, V, P, C), dtype=torch.float32).pin_memory()
+    out_coors = torch.empty((F, V, 3), dtype=torch.int32).pin_memory()
+    out_num = torch.empty((F, V), dtype=torch.int32).pin_memory()
+    h2d = F * N * C * 4
+
+    def step():
+        for k in range(F):
+            pts[k].copy_(host[k], non_blocking=True)
+        voxels, coors, num, vnum = plan.run()
+        counts = vnum.cpu().tolist()  # sync: the caller needs M to size what it reads
+        d2h = F * 4
+        for k, m in enumerate(counts):
+            out_vox[k, :m].copy_(voxels[k, :m], non_blocking=True)
+            out_coors[k, :m].copy_(coors[k, :m], non_blocking=True)
+            out_num[k, :m].copy_(num[k, :m], non_blocking=True)
+            d2h += m * (P * C * 4 + 16)
+        torch.cuda.synchronize(dev)
+        return d2h
+
+    step()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.e2e_steps):
+        d2h = step()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / args.e2e_steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    return {"value": round(world * F * N / dt / 1e6, 1), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt * 1e3, 3), "steps": args.e2e_steps,
+            "api": "HardVoxelizeBatchPlan.run (pcfe_hard_voxelize_batch_f32) with pinned host in/out buffers"}
+
+
+def cpu_baseline_subprocess(args):
+    """The reference arm on a bounded sample, in a fresh process (fork-safe: no CUDA there)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+           "--workload", args.workload, "--gpus", "1"]
+    try:
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k, None)
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (out.stderr or "no output")[-300:]}
+    except Exception as e:
+        return {"error": str(e)[:300]}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

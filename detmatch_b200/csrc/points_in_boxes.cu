@@ -1,0 +1,461 @@
+// detmatch_b200/csrc/points_in_boxes.cu -- point-in-rotated-box assignment for sm_100a.
+//
+// Replaces roiaware_pool3d_ext.points_in_boxes_{gpu,batch,cpu}
+// (mmdet3d/ops/roiaware_pool3d/src/points_in_boxes_cuda.cu:51-203 are the kernels superseded;
+//  mmdet3d/ops/roiaware_pool3d/src/points_in_boxes_cpu.cpp:16-40 is the arithmetic reproduced
+//  bit for bit).  See include/pcfe.h for the contract.
+//
+// Structure: a prologue kernel turns every box into 8 floats {cx, cy, cz_centre, h/2, cos, sin,
+// l/2, w/2} -- the trigonometry is glibc's sinf/cosf algorithm evaluated in double with the same
+// fused operations the x86-64 FMA build of glibc uses, so cosa/sina equal the host's bit for
+// bit -- and the per-pair kernels stage the prepared boxes of one frame in shared memory with a
+// TMA bulk copy (cp.async.bulk + mbarrier) and evaluate the test with explicitly un-fused
+// float32 operations.
+#include <algorithm>
+
+#include "pcfe_common.cuh"
+
+namespace pcfe {
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// glibc >= 2.28 sinf/cosf (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, sincosf.h), restated.
+// oracle/pcfe_oracle.c carries the same restatement for the CPU and is checked against the
+// host libm exhaustively on [2^-14, 120) (tests/test_oracle.py).
+// ------------------------------------------------------------------------------------------
+struct SinCosTab {
+  double c0, c1, c2, c3, c4, s1, s2, s3;
+};
+__device__ __constant__ SinCosTab kTab[2] = {
+    {0x1p0, -0x1.ffffffd0c621cp-2, 0x1.55553e1068f19p-5, -0x1.6c087e89a359dp-10,
+     0x1.99343027bf8c3p-16, -0x1.555545995a603p-3, 0x1.1107605230bc4p-7, -0x1.994eb3774cf24p-13},
+    {-0x1p0, 0x1.ffffffd0c621cp-2, -0x1.55553e1068f19p-5, 0x1.6c087e89a359dp-10,
+     -0x1.99343027bf8c3p-16, -0x1.555545995a603p-3, 0x1.1107605230bc4p-7, -0x1.994eb3774cf24p-13}};
+__device__ __constant__ uint32_t kInvPio4[24] = {
+    0xa2,       0xa2f9,     0xa2f983,   0xa2f9836e, 0xf9836e4e, 0x836e4e44,
+    0x6e4e4415, 0x4e441529, 0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1,
+    0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, 0x34ddc0db, 0xddc0db62,
+    0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
+
+__device__ __forceinline__ uint32_t abstop12(float f) { return (__float_as_uint(f) >> 20) & 0x7ffu; }
+
+// n even: sine polynomial, n odd: cosine polynomial.  Multiplications are single-rounded
+// (__dmul_rn), every a + b*c is ONE fused operation (__fma_rn), matching glibc's FMA build.
+__device__ __forceinline__ float sc_poly(double x, double x2, const SinCosTab& p, int n) {
+  if ((n & 1) == 0) {
+    const double x3 = __dmul_rn(x, x2);
+    const double s1 = __fma_rn(x2, p.s3, p.s2);
+    const double x7 = __dmul_rn(x3, x2);
+    const double s = __fma_rn(x3, p.s1, x);
+    return __double2float_rn(__fma_rn(x7, s1, s));
+  } else {
+    const double x4 = __dmul_rn(x2, x2);
+    const double c2 = __fma_rn(x2, p.c4, p.c3);
+    const double c1 = __fma_rn(x2, p.c1, p.c0);
+    const double x6 = __dmul_rn(x4, x2);
+    const double c = __fma_rn(x4, p.c2, c1);
+    return __double2float_rn(__fma_rn(x6, c2, c));
+  }
+}
+
+__device__ float glibc_sin_or_cos(float y, int want_cos) {
+  double x = (double)y;
+  const double sign[4] = {1.0, -1.0, -1.0, 1.0};
+  int n;
+  int tab = 0;
+  if (abstop12(y) < abstop12(0x1.921FB6p-1f)) {
+    if (abstop12(y) < abstop12(0x1p-12f)) return want_cos ? 1.0f : y;
+    return sc_poly(x, __dmul_rn(x, x), kTab[0], want_cos);
+  } else if (abstop12(y) < abstop12(120.0f)) {
+    const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+    n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
+    const double s = sign[n & 3];
+    if (n & 2) tab = 1;
+    return sc_poly(__dmul_rn(x, s), __dmul_rn(x, x), kTab[tab], n ^ want_cos);
+  } else if (abstop12(y) < 0x7f8u) {
+    uint32_t xi = __float_as_uint(y);
+    const int sgn = (int)(xi >> 31);
+    const uint32_t* arr = &kInvPio4[(xi >> 26) & 15];
+    const int shift = (xi >> 23) & 7;
+    xi = (xi & 0xffffffu) | 0x800000u;
+    xi <<= shift;
+    uint64_t res0 = (uint64_t)(uint32_t)(xi * arr[0]);
+    const uint64_t res1 = (uint64_t)xi * arr[4];
+    const uint64_t res2 = (uint64_t)xi * arr[8];
+    res0 = (res2 >> 32) | (res0 << 32);
+    res0 += res1;
+    const uint64_t nn = (res0 + (1ULL << 61)) >> 62;
+    res0 -= nn << 62;
+    x = __dmul_rn((double)(int64_t)res0, 0x1.921FB54442D18p-62);
+    n = (int)nn;
+    const double s = sign[(n + sgn) & 3];
+    if ((n + sgn) & 2) tab = 1;
+    return sc_poly(__dmul_rn(x, s), __dmul_rn(x, x), kTab[tab], n ^ want_cos);
+  }
+  return __fsub_rn(y, y);  // Inf/NaN -> NaN
+}
+
+__global__ void debug_sincosf_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ s,
+                                     float* __restrict__ c) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    s[i] = glibc_sin_or_cos(x[i], 0);
+    c[i] = glibc_sin_or_cos(x[i], 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// prepared boxes
+// ------------------------------------------------------------------------------------------
+struct __align__(16) PBox {
+  float cx, cy, czc, hh;      // centre (z shifted to the box centre), half height
+  float cosa, sina, hl, hw;   // rotation by rz + pi/2, half length (local x), half width (local y)
+};
+static_assert(sizeof(PBox) == 32, "PBox must be 32 bytes");
+
+__global__ void pib_prepare_kernel(const float* __restrict__ boxes, int64_t nboxes,
+                                   PBox* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nboxes) return;
+  const float* b = boxes + i * 7;
+  const float cx = b[0], cy = b[1], cz = b[2], w = b[3], l = b[4], h = b[5], rz = b[6];
+  PBox p;
+  p.cx = cx;
+  p.cy = cy;
+  // cz += h / 2.0  (double add, rounded to float; points_in_boxes_cpu.cpp:33)
+  p.czc = __double2float_rn(__dadd_rn((double)cz, __dmul_rn((double)h, 0.5)));
+  // The reference compares float values against the DOUBLE h/2, l/2, w/2 (:35,:37-38).  x/2 is
+  // exact in float except for odd subnormals; directed rounding keeps the float comparison
+  // equivalent there too:  |dz| > h/2  <=>  |dz| > rd(h/2);   lx < l/2  <=>  lx < ru(l/2);
+  // lx > -l/2  <=>  lx > -ru(l/2).
+  p.hh = __double2float_rd(__dmul_rn((double)h, 0.5));
+  p.hl = __double2float_ru(__dmul_rn((double)l, 0.5));
+  p.hw = __double2float_ru(__dmul_rn((double)w, 0.5));
+  // rot_angle = rz + M_PI / 2  (double add, rounded to float; :19)
+  const float rot = __double2float_rn(__dadd_rn((double)rz, 0x1.921fb54442d18p+0));
+  p.cosa = glibc_sin_or_cos(rot, 1);
+  p.sina = glibc_sin_or_cos(rot, 0);
+  out[i] = p;
+}
+
+// points_in_boxes_cpu.cpp:25-40, float32, no contraction.
+__device__ __forceinline__ int in_box(float x, float y, float z, const PBox& b) {
+  const float dz = __fsub_rn(z, b.czc);
+  const bool z_out = fabsf(dz) > b.hh;  // reject-if-greater keeps the NaN-z asymmetry
+  const float sx = __fsub_rn(x, b.cx);
+  const float sy = __fsub_rn(y, b.cy);
+  const float lx = __fadd_rn(__fmul_rn(sx, b.cosa), __fmul_rn(sy, -b.sina));
+  const float ly = __fadd_rn(__fmul_rn(sx, b.sina), __fmul_rn(sy, b.cosa));
+  const bool in = (lx > -b.hl) & (lx < b.hl) & (ly > -b.hw) & (ly < b.hw);
+  return (in & !z_out) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA bulk copy of the prepared boxes of one frame into shared memory
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+// Loads `count` prepared boxes (32 B each, 16-B aligned source) into sboxes.  All threads call.
+__device__ __forceinline__ void stage_boxes(PBox* sboxes, const PBox* gboxes, int count,
+                                            uint64_t* bar, uint32_t parity) {
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)count * (uint32_t)sizeof(PBox);
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(sboxes, gboxes, bytes, bar);
+  }
+  mbar_wait(bar, parity);
+}
+
+constexpr int kBoxChunk = 1024;  // boxes staged per pass (32 KB of static shared memory)
+
+// ------------------------------------------------------------------------------------------
+// points_in_boxes_batch: out (b, m, t), point-major.  Thread = VEC consecutive boxes (kept in
+// registers) x a strided set of points; the T flags of one point are written by T/VEC
+// neighbouring threads as one contiguous run.
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(1024)
+pib_all_kernel(const PBox* __restrict__ pboxes, const float* __restrict__ points, int t,
+               long long m, int pts_per_cta, int32_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  PBox* sboxes = reinterpret_cast<PBox*>(smem_raw);
+  float* spts = reinterpret_cast<float*>(smem_raw + (size_t)t * sizeof(PBox));
+
+  const int b = blockIdx.y;
+  const long long m0 = (long long)blockIdx.x * pts_per_cta;
+  const int npts = (int)min((long long)pts_per_cta, m - m0);
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  stage_boxes(sboxes, pboxes + (size_t)b * t, t, &bar, 0);
+  const float* gp = points + ((size_t)b * m + m0) * 3;
+  for (int i = threadIdx.x; i < npts * 3; i += blockDim.x) spts[i] = __ldg(gp + i);
+  __syncthreads();
+
+  const int groups = t / VEC;                 // threads per point
+  const int q = threadIdx.x % groups;         // my box group
+  const int prow = threadIdx.x / groups;      // my first point
+  const int pstep = blockDim.x / groups;      // blockDim.x is a multiple of groups
+  PBox bx[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) bx[v] = sboxes[q * VEC + v];
+  int32_t* obase = out + ((size_t)b * m + m0) * t + (size_t)q * VEC;
+  for (int p = prow; p < npts; p += pstep) {
+    const float x = spts[p * 3], y = spts[p * 3 + 1], z = spts[p * 3 + 2];
+    int32_t r[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r[v] = in_box(x, y, z, bx[v]);
+    int32_t* o = obase + (size_t)p * t;
+    if (VEC == 4) {
+      __stcs(reinterpret_cast<int4*>(o), make_int4(r[0], r[1], r[2], r[3]));
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) __stcs(o + v, r[v]);
+    }
+  }
+}
+
+// Generic fallback for very large T (boxes do not fit one staging pass): thread per point,
+// boxes streamed through shared memory in chunks, strided stores.
+__global__ void __launch_bounds__(256)
+pib_all_generic_kernel(const PBox* __restrict__ pboxes, const float* __restrict__ points, int t,
+                       long long m, int32_t* __restrict__ out) {
+  __shared__ __align__(16) PBox sboxes[kBoxChunk / 8];
+  const int b = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (p < m) {
+    const float* gp = points + ((size_t)b * m + p) * 3;
+    x = __ldg(gp); y = __ldg(gp + 1); z = __ldg(gp + 2);
+  }
+  constexpr int chunk = kBoxChunk / 8;
+  for (int t0 = 0; t0 < t; t0 += chunk) {
+    const int cnt = min(chunk, t - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) sboxes[i] = pboxes[(size_t)b * t + t0 + i];
+    __syncthreads();
+    if (p < m) {
+      int32_t* o = out + ((size_t)b * m + p) * t + t0;
+      for (int k = 0; k < cnt; ++k) o[k] = in_box(x, y, z, sboxes[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// points_in_boxes_gpu: out (b, m) = lowest containing box index or -1
+// points_in_boxes_cpu layout: out (t, n) box-major 0/1   (BOXMAJOR = true, b == 1)
+// Thread = one point; boxes broadcast from shared memory, staged by TMA in chunks.
+// ------------------------------------------------------------------------------------------
+template <bool BOXMAJOR>
+__global__ void __launch_bounds__(256)
+pib_point_kernel(const PBox* __restrict__ pboxes, const float* __restrict__ points, int t,
+                 long long m, int32_t* __restrict__ out) {
+  __shared__ __align__(16) PBox sboxes[kBoxChunk];
+  __shared__ uint64_t bar;
+  const int b = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (p < m) {
+    const float* gp = points + ((size_t)b * m + p) * 3;
+    x = __ldg(gp); y = __ldg(gp + 1); z = __ldg(gp + 2);
+  }
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  int first = -1;
+  uint32_t parity = 0;
+  for (int t0 = 0; t0 < t; t0 += kBoxChunk) {
+    const int cnt = min(kBoxChunk, t - t0);
+    if (t0 > 0) __syncthreads();  // everyone is done with the previous chunk
+    stage_boxes(sboxes, pboxes + (size_t)b * t + t0, cnt, &bar, parity);
+    parity ^= 1u;
+    if (p < m) {
+      if (BOXMAJOR) {
+        for (int k = 0; k < cnt; ++k) __stcs(out + (size_t)(t0 + k) * m + p, in_box(x, y, z, sboxes[k]));
+      } else if (first < 0) {
+        for (int k = 0; k < cnt; ++k) {
+          if (in_box(x, y, z, sboxes[k])) {
+            first = t0 + k;  // points_in_boxes_cuda.cu:71-75: first hit wins
+            break;
+          }
+        }
+      }
+    }
+  }
+  if (!BOXMAJOR && p < m) out[(size_t)b * m + p] = first;
+}
+
+__global__ void fill_kernel(int32_t* out, long long n, int32_t v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int check_common(const float* boxes, const float* points, const int32_t* out, int b, int t,
+                 int64_t m, void* ws, size_t ws_bytes) {
+  if (b < 0 || t < 0 || m < 0) return PCFE_ERR_SHAPE;
+  if (b > 65535) return PCFE_ERR_TOO_LARGE;
+  if ((int64_t)b * (int64_t)t >= (1ll << 31) || m >= (1ll << 40)) return PCFE_ERR_TOO_LARGE;
+  if (b == 0 || m == 0) return 1;  // nothing to write
+  if (!points || !out) return PCFE_ERR_NULL;
+  if (t > 0 && (!boxes || !ws)) return PCFE_ERR_NULL;
+  if (((uintptr_t)boxes & 3) || ((uintptr_t)points & 3) || ((uintptr_t)out & 3)) return PCFE_ERR_ALIGN;
+  if (t > 0 && ((uintptr_t)ws & 255)) return PCFE_ERR_ALIGN;
+  if (t > 0 && ws_bytes < pcfe_points_in_boxes_workspace_bytes(b, t)) return PCFE_ERR_WORKSPACE;
+  return PCFE_OK;
+}
+
+int prepare(const float* boxes, int64_t nboxes, PBox* pb, cudaStream_t st) {
+  pib_prepare_kernel<<<(unsigned)((nboxes + 127) / 128), 128, 0, st>>>(boxes, nboxes, pb);
+  PCFE_LAUNCH_CHECK();
+  return PCFE_OK;
+}
+
+}  // namespace
+}  // namespace pcfe
+
+using namespace pcfe;
+
+extern "C" size_t pcfe_points_in_boxes_workspace_bytes(int b, int t) {
+  if (b <= 0 || t <= 0) return 256;
+  return align256((size_t)b * (size_t)t * sizeof(PBox));
+}
+
+extern "C" int pcfe_points_in_boxes_part_f32(const float* boxes, const float* points, int b, int t,
+                                             int64_t m, int32_t* out, void* ws, size_t ws_bytes,
+                                             int device, void* stream) {
+  int rc = check_common(boxes, points, out, b, t, m, ws, ws_bytes);
+  if (rc != PCFE_OK) return rc > 0 ? PCFE_OK : rc;
+  DeviceGuard guard(device);
+  PCFE_CUDA_TRY(guard.err);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (t == 0) {  // no boxes: everything is background
+    const long long total = (long long)b * m;
+    fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, total, -1);
+    PCFE_LAUNCH_CHECK();
+    return PCFE_OK;
+  }
+  PBox* pb = (PBox*)ws;
+  if ((rc = prepare(boxes, (int64_t)b * t, pb, st)) != PCFE_OK) return rc;
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)b);
+  pib_point_kernel<false><<<grid, 256, 0, st>>>(pb, points, t, (long long)m, out);
+  PCFE_LAUNCH_CHECK();
+  return PCFE_OK;
+}
+
+extern "C" int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float* points, int t,
+                                                 int64_t n, int32_t* out, void* ws, size_t ws_bytes,
+                                                 int device, void* stream) {
+  int rc = check_common(boxes, points, out, 1, t, n, ws, ws_bytes);
+  if (rc != PCFE_OK) return rc > 0 ? PCFE_OK : rc;
+  if (t == 0) return PCFE_OK;
+  DeviceGuard guard(device);
+  PCFE_CUDA_TRY(guard.err);
+  cudaStream_t st = (cudaStream_t)stream;
+  PBox* pb = (PBox*)ws;
+  if ((rc = prepare(boxes, t, pb, st)) != PCFE_OK) return rc;
+  dim3 grid((unsigned)((n + 255) / 256), 1);
+  pib_point_kernel<true><<<grid, 256, 0, st>>>(pb, points, t, (long long)n, out);
+  PCFE_LAUNCH_CHECK();
+  return PCFE_OK;
+}
+
+extern "C" int pcfe_points_in_boxes_all_f32(const float* boxes, const float* points, int b, int t,
+                                            int64_t m, int32_t* out, void* ws, size_t ws_bytes,
+                                            int device, void* stream) {
+  int rc = check_common(boxes, points, out, b, t, m, ws, ws_bytes);
+  if (rc != PCFE_OK) return rc > 0 ? PCFE_OK : rc;
+  if (t == 0) return PCFE_OK;
+  DeviceGuard guard(device);
+  PCFE_CUDA_TRY(guard.err);
+  cudaStream_t st = (cudaStream_t)stream;
+  PBox* pb = (PBox*)ws;
+  if ((rc = prepare(boxes, (int64_t)b * t, pb, st)) != PCFE_OK) return rc;
+
+  // fast path: all boxes of a frame in shared memory, VEC boxes per thread in registers
+  const bool vec4 = (t % 4 == 0) && (((uintptr_t)out & 15) == 0);
+  const int vec = vec4 ? 4 : 1;
+  const int groups = t / vec;
+  if (groups <= 1024 && t <= kBoxChunk) {
+    const int ppi = 1024 / groups;                         // points per block iteration
+    const int threads = ppi * groups;                      // <= 1024, multiple of groups
+    const int iters = 16;
+    const int pts_per_cta = ppi * iters;
+    const size_t smem = (size_t)t * sizeof(PBox) + (size_t)pts_per_cta * 3 * sizeof(float);
+    dim3 grid((unsigned)((m + pts_per_cta - 1) / pts_per_cta), (unsigned)b);
+    if (vec4) {
+      PCFE_CUDA_TRY(cudaFuncSetAttribute(pib_all_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pib_all_kernel<4><<<grid, threads, smem, st>>>(pb, points, t, (long long)m, pts_per_cta, out);
+    } else {
+      PCFE_CUDA_TRY(cudaFuncSetAttribute(pib_all_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pib_all_kernel<1><<<grid, threads, smem, st>>>(pb, points, t, (long long)m, pts_per_cta, out);
+    }
+    PCFE_LAUNCH_CHECK();
+  } else {
+    dim3 grid((unsigned)((m + 255) / 256), (unsigned)b);
+    pib_all_generic_kernel<<<grid, 256, 0, st>>>(pb, points, t, (long long)m, out);
+    PCFE_LAUNCH_CHECK();
+  }
+  return PCFE_OK;
+}
+
+extern "C" int pcfe_debug_sincosf(const float* x, int64_t n, float* s, float* c, int device,
+                                  void* stream) {
+  if (n < 0) return PCFE_ERR_SHAPE;
+  if (n == 0) return PCFE_OK;
+  if (!x || !s || !c) return PCFE_ERR_NULL;
+  DeviceGuard guard(device);
+  PCFE_CUDA_TRY(guard.err);
+  debug_sincosf_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, s, c);
+  PCFE_LAUNCH_CHECK();
+  return PCFE_OK;
+}
+
+extern "C" int pcfe_version(void) { return PCFE_VERSION; }
+
+extern "C" uint64_t pcfe_launch_count(void) { return g_launches.load(); }
+
+extern "C" const char* pcfe_error_string(int code) {
+  switch (code) {
+    case PCFE_OK: return "ok";
+    case PCFE_ERR_NULL: return "pcfe: required pointer is NULL";
+    case PCFE_ERR_SHAPE: return "pcfe: bad shape (negative size, c < 3, or wrong inner dimension)";
+    case PCFE_ERR_GRID: return "pcfe: voxel grid is empty or has >= 2^32-1 cells";
+    case PCFE_ERR_WORKSPACE: return "pcfe: workspace too small";
+    case PCFE_ERR_ALIGN: return "pcfe: pointer is not sufficiently aligned";
+    case PCFE_ERR_CAPS: return "pcfe: max_points / max_voxels must be >= 0";
+    case PCFE_ERR_TOO_LARGE: return "pcfe: input too large";
+    case PCFE_ERR_DEVICE: return "pcfe: no usable CUDA device";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "pcfe: unknown error";
+}

@@ -1,0 +1,177 @@
+"""Mirror of mmdet3d/ops/voxel/voxelize.py: ``Voxelization`` / ``voxelization`` with the
+reference's argument semantics and return values, executed by the sm_100a kernels.
+
+``voxelize_batch`` is the batched form of the detectors' per-frame loop
+(mmdet3d/models/detectors/openpcdet.py:59-76, voxelnet.py:50-67): all frames of a
+teacher/student batch in one launch sequence, one host synchronisation per batch.
+"""
+import ctypes
+
+import torch
+from torch import nn
+from torch.nn.modules.utils import _pair
+
+from ... import _cabi
+from ..._torch_glue import ptr, stream_ptr, to_device, workspace
+from . import voxel_layer
+
+
+def voxelization(points, voxel_size, coors_range, max_points=35, max_voxels=20000):
+    """voxelize.py:13-58 (_Voxelization.forward).  The reference registers no backward either.
+
+    Returns ``coors`` (N, 3) in dynamic mode (max_points == -1 or max_voxels == -1), else
+    ``(voxels[:M], coors[:M], num_points_per_voxel[:M])``.
+    """
+    if points.dtype != torch.float32:
+        raise TypeError(f"voxelization: points must be float32, got {points.dtype}")
+    dpoints, home = to_device(points.contiguous())
+    with torch.no_grad():
+        if max_points == -1 or max_voxels == -1:
+            coors = torch.empty((dpoints.size(0), 3), dtype=torch.int32, device=dpoints.device)
+            voxel_layer.dynamic_voxelize(dpoints, coors, voxel_size, coors_range, 3)
+            return coors.to(home)
+        # rows [0, voxel_num) are written completely by the kernels (data + zero padding), rows
+        # beyond are unobservable through the returned views, so no (max_voxels-sized) memset.
+        voxels = torch.empty((max_voxels, max_points, dpoints.size(1)), dtype=torch.float32, device=dpoints.device)
+        coors = torch.empty((max_voxels, 3), dtype=torch.int32, device=dpoints.device)
+        num_points_per_voxel = torch.empty((max_voxels,), dtype=torch.int32, device=dpoints.device)
+        voxel_num = voxel_layer.hard_voxelize(dpoints, voxels, coors, num_points_per_voxel, voxel_size,
+                                              coors_range, max_points, max_voxels, 3)
+        return (voxels[:voxel_num].to(home), coors[:voxel_num].to(home),
+                num_points_per_voxel[:voxel_num].to(home))
+
+
+def voxelize_batch(points, voxel_size, coors_range, max_points, max_voxels, sync=True):
+    """Hard-voxelizes a list of (N_i, C) CUDA frames in one launch sequence.
+
+    Returns ``(voxels, coors, num_points, voxel_num)`` where voxels is (F, max_voxels, max_points,
+    C), coors (F, max_voxels, 3), num_points (F, max_voxels) and voxel_num a device int32 (F,)
+    tensor; rows >= voxel_num[f] of frame f are unspecified.  With ``sync=True`` additionally
+    returns the detector-style concatenation ``(voxels_cat, num_points_cat, coors_batch)`` with
+    ``coors_batch`` (sum M, 4) = [batch_idx, z, y, x] (openpcdet.py:69-76).
+    """
+    assert len(points) > 0
+    dev = points[0].device
+    c = points[0].size(1)
+    for p in points:
+        voxel_layer._check_points(p)
+        assert p.device == dev and p.size(1) == c
+    nf = len(points)
+    with torch.no_grad():
+        voxels = torch.empty((nf, max_voxels, max_points, c), dtype=torch.float32, device=dev)
+        coors = torch.empty((nf, max_voxels, 3), dtype=torch.int32, device=dev)
+        num = torch.empty((nf, max_voxels), dtype=torch.int32, device=dev)
+        voxel_num = torch.empty((nf,), dtype=torch.int32, device=dev)
+        frames = (_cabi.Frame * nf)()
+        n_max = 0
+        for i, p in enumerate(points):
+            frames[i] = _cabi.Frame(p.data_ptr(), p.size(0), voxels[i].data_ptr(), coors[i].data_ptr(),
+                                    num[i].data_ptr())
+            n_max = max(n_max, p.size(0))
+        L = _cabi.lib()
+        vs, rg = _cabi.f3(voxel_size), _cabi.f6(coors_range)
+        need = L.pcfe_hard_voxelize_workspace_bytes(n_max, nf, 0, vs, rg, max_points, max_voxels)
+        ws = workspace(dev, need)
+        rc = L.pcfe_hard_voxelize_batch_f32(frames, nf, c, vs, rg, max_points, max_voxels, ptr(voxel_num),
+                                            ptr(ws), ws.numel(), dev.index, stream_ptr(dev))
+        _cabi.check(rc, "pcfe_hard_voxelize_batch_f32")
+        if not sync:
+            return voxels, coors, num, voxel_num
+        counts = voxel_num.tolist()  # the one host synchronisation of the batch
+        vox_cat = torch.cat([voxels[i, :m] for i, m in enumerate(counts)], dim=0)
+        num_cat = torch.cat([num[i, :m] for i, m in enumerate(counts)], dim=0)
+        coors_batch = torch.cat(
+            [torch.nn.functional.pad(coors[i, :m], (1, 0), mode="constant", value=i) for i, m in enumerate(counts)],
+            dim=0)
+        return vox_cat, num_cat, coors_batch
+
+
+class HardVoxelizeBatchPlan:
+    """Pre-allocated batched hard voxelization for a fixed set of frame shapes: outputs and
+    scratch are allocated once, ``run()`` only enqueues the launch sequence on the current
+    stream (no allocation, no host synchronisation).  This is what a training loop that
+    voxelizes the same batch geometry every iteration (and bench.py) uses.
+    """
+
+    def __init__(self, sizes, num_features, voxel_size, coors_range, max_points, max_voxels, device,
+                 frames_in_flight=0):
+        self.device = torch.device(device)
+        self.sizes = [int(n) for n in sizes]
+        self.c = int(num_features)
+        self.max_points, self.max_voxels = int(max_points), int(max_voxels)
+        self.vs, self.rg = _cabi.f3(voxel_size), _cabi.f6(coors_range)
+        nf = len(self.sizes)
+        dev = self.device
+        self.voxels = torch.empty((nf, max_voxels, max_points, self.c), dtype=torch.float32, device=dev)
+        self.coors = torch.empty((nf, max_voxels, 3), dtype=torch.int32, device=dev)
+        self.num_points = torch.empty((nf, max_voxels), dtype=torch.int32, device=dev)
+        self.voxel_num = torch.zeros((nf,), dtype=torch.int32, device=dev)
+        L = _cabi.lib()
+        need = L.pcfe_hard_voxelize_workspace_bytes(max(self.sizes + [0]), nf, frames_in_flight, self.vs, self.rg,
+                                                    self.max_points, self.max_voxels)
+        self.ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        self.frames = (_cabi.Frame * nf)()
+
+    def bind(self, points):
+        """Points the plan at the frames' device buffers (list of contiguous (N_i, C) tensors)."""
+        assert len(points) == len(self.sizes)
+        for i, p in enumerate(points):
+            voxel_layer._check_points(p)
+            assert p.device == self.device and p.size(0) == self.sizes[i] and p.size(1) == self.c
+            self.frames[i] = _cabi.Frame(p.data_ptr(), p.size(0), self.voxels[i].data_ptr(),
+                                         self.coors[i].data_ptr(), self.num_points[i].data_ptr())
+        self._bound = points  # keep the tensors alive
+        return self
+
+    def run(self):
+        rc = _cabi.lib().pcfe_hard_voxelize_batch_f32(self.frames, len(self.sizes), self.c, self.vs, self.rg,
+                                                      self.max_points, self.max_voxels, ptr(self.voxel_num),
+                                                      ptr(self.ws), self.ws.numel(), self.device.index,
+                                                      stream_ptr(self.device))
+        _cabi.check(rc, "pcfe_hard_voxelize_batch_f32")
+        return self.voxels, self.coors, self.num_points, self.voxel_num
+
+
+class Voxelization(nn.Module):
+    """voxelize.py:64-122: same constructor arguments, attributes, forward and repr."""
+
+    def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels=20000):
+        super(Voxelization, self).__init__()
+        self.voxel_size = voxel_size
+        self.point_cloud_range = point_cloud_range
+        self.max_num_points = max_num_points
+        if isinstance(max_voxels, tuple):
+            self.max_voxels = max_voxels
+        else:
+            self.max_voxels = _pair(max_voxels)
+
+        point_cloud_range = torch.tensor(point_cloud_range, dtype=torch.float32)
+        voxel_size = torch.tensor(voxel_size, dtype=torch.float32)
+        grid_size = (point_cloud_range[3:] - point_cloud_range[:3]) / voxel_size
+        grid_size = torch.round(grid_size).long()
+        input_feat_shape = grid_size[:2]
+        self.grid_size = grid_size
+        # [w, h, d] -> [d, h, w]
+        self.pcd_shape = [*input_feat_shape, 1][::-1]
+
+    def forward(self, input):
+        if self.training:
+            max_voxels = self.max_voxels[0]
+        else:
+            max_voxels = self.max_voxels[1]
+        return voxelization(input, self.voxel_size, self.point_cloud_range, self.max_num_points, max_voxels)
+
+    def forward_batch(self, inputs, sync=True):
+        """All frames of a batch at once (see voxelize_batch)."""
+        max_voxels = self.max_voxels[0] if self.training else self.max_voxels[1]
+        return voxelize_batch(inputs, self.voxel_size, self.point_cloud_range, self.max_num_points, max_voxels,
+                              sync=sync)
+
+    def __repr__(self):
+        tmpstr = self.__class__.__name__ + '('
+        tmpstr += 'voxel_size=' + str(self.voxel_size)
+        tmpstr += ', point_cloud_range=' + str(self.point_cloud_range)
+        tmpstr += ', max_num_points=' + str(self.max_num_points)
+        tmpstr += ', max_voxels=' + str(self.max_voxels)
+        tmpstr += ')'
+        return tmpstr

@@ -1,0 +1,172 @@
+/*
+ * include/pcfe.h -- C ABI of the B200-native point-cloud front end (libpcfe.so).
+ *
+ * This is the drop-in boundary for the one hot path of Divadi/DetMatch this repository
+ * replaces: point-to-cell assignment (hard / dynamic voxelization) and point-to-box assignment
+ * (points_in_boxes_{gpu,batch,cpu}).  Every entry point below names the reference interface it
+ * replaces (paths relative to the reference tree).  Plain pointers and sizes only: no torch,
+ * pybind or C++ types cross this boundary.  INTEGRATION.md shows the binding a maintainer of
+ * the reference would add (ctypes / pybind stubs for voxel_layer and roiaware_pool3d_ext).
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers on CUDA device `device` unless marked "host".
+ *   - `stream` is a cudaStream_t (passed as void*); NULL means the legacy default stream.
+ *     Every call only ENQUEUES work on `stream`; nothing here synchronises the host.  Results
+ *     (including voxel counts) stay on the device -- the caller decides when to read them.
+ *   - The current CUDA device of the calling thread is preserved.
+ *   - Return value: 0 = PCFE_OK, < 0 = argument error (see enum), > 0 = a cudaError_t.
+ *     Never exit()s, never throws (the reference's launchers call exit(-1):
+ *     mmdet3d/ops/roiaware_pool3d/src/points_in_boxes_cuda.cu:120-125,145-149).
+ *   - float32 points only (the reference's CUDA path is float-only in practice:
+ *     mmdet3d/ops/voxel/src/voxelization_cuda.cu:294).
+ *   - Results are bit-identical to the reference's CPU ops (voxelization_cpu.cpp,
+ *     points_in_boxes_cpu.cpp), NOT to its CUDA ops where the two differ.
+ */
+#ifndef PCFE_H_
+#define PCFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCFE_VERSION 100 /* 0.1.0 */
+
+enum {
+  PCFE_OK = 0,
+  PCFE_ERR_NULL = -1,        /* a required pointer is NULL */
+  PCFE_ERR_SHAPE = -2,       /* negative size, c < 3, boxes/points inner dim wrong */
+  PCFE_ERR_GRID = -3,        /* voxel grid empty or has >= 2^32-1 cells */
+  PCFE_ERR_WORKSPACE = -4,   /* workspace too small (see *_workspace_bytes) */
+  PCFE_ERR_ALIGN = -5,       /* pointer not aligned to its element size */
+  PCFE_ERR_CAPS = -6,        /* max_points / max_voxels negative (use dynamic_voxelize for -1) */
+  PCFE_ERR_TOO_LARGE = -7,   /* n >= 2^31-1 points in one frame, or t too large */
+  PCFE_ERR_DEVICE = -8       /* not an sm_100 device / no CUDA device */
+};
+
+int pcfe_version(void);
+/* Static string for a return code (argument errors and cudaGetErrorString). */
+const char* pcfe_error_string(int code);
+/* Number of kernel launches + memsets enqueued by this library since load (bench.py's
+ * "gpu_launches" is the difference across the timed region). */
+uint64_t pcfe_launch_count(void);
+
+/* Optional per-kernel device timing of the hard-voxelize launch sequence (used by bench.py to
+ * attribute the step time; off by default, costs two event records per launch when on).
+ * pcfe_profile_report synchronises the recorded events, writes "name total_ms launches" lines
+ * into buf and clears the records; returns the number of lines. */
+int pcfe_profile_enable(int on);
+int pcfe_profile_report(char* buf, size_t cap);
+
+/* grid[j] = (int)roundf((range[3+j]-range[j])/voxel_size[j]) in float32, x y z order.
+ * Replaces: voxelization_cpu.cpp:119-122 / voxelization_cuda.cu:200-206.  Host-only helper. */
+int pcfe_grid_size(const float voxel_size[3], const float coors_range[6], int32_t grid[3]);
+
+/* ---------------------------------------------------------------------------------------------
+ * dynamic voxelization
+ * Replaces: voxel_layer.dynamic_voxelize(points, coors, voxel_size, coors_range, NDim=3)
+ *           mmdet3d/ops/voxel/src/voxelization.h:71-83, voxelization_cpu.cpp:144-169,
+ *           call site mmdet3d/ops/voxel/voxelize.py:42-44.
+ * points (n, c) float32 row-major, c >= 3; coors (n, 3) int32 = (z, y, x), or (-1,-1,-1) for a
+ * point outside the range (CPU semantics, voxelization_cpu.cpp:32-37; the reference's CUDA
+ * kernel writes partial -1s, voxelization_cuda.cu:38-54 -- not reproduced).
+ * voxel_size / coors_range are HOST float32 arrays (pybind narrows the Python floats to
+ * std::vector<float> at this same point).  n == 0 is a no-op.
+ * ------------------------------------------------------------------------------------------- */
+int pcfe_dynamic_voxelize_f32(const float* points, int64_t n, int c,
+                              const float voxel_size[3], const float coors_range[6],
+                              int32_t* coors, int device, void* stream);
+
+/* Batched: `num_frames` independent frames in one launch.  Host arrays of device pointers. */
+int pcfe_dynamic_voxelize_batch_f32(const float* const* points, const int64_t* n, int num_frames,
+                                    int c, const float voxel_size[3], const float coors_range[6],
+                                    int32_t* const* coors, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * hard voxelization
+ * Replaces: voxel_layer.hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size,
+ *                                     coors_range, max_points, max_voxels, NDim=3) -> voxel_num
+ *           mmdet3d/ops/voxel/src/voxelization.h:51-69, voxelization_cpu.cpp:43-142,
+ *           voxelization_cuda.cu:184-326; call site mmdet3d/ops/voxel/voxelize.py:46-58.
+ *
+ * Semantics (voxelization_cpu.cpp:68-96): distinct in-range voxels are numbered in order of
+ * their first point; the first `max_voxels` of them are kept; inside a voxel the first
+ * `max_points` points (by index) fill slots 0.. ; all other slots are +0.0f.
+ *   voxels      (max_voxels, max_points, c) float32   rows [0, voxel_num) are written COMPLETELY
+ *   coors       (max_voxels, 3) int32 (z, y, x)       (data and zero padding); rows >= voxel_num
+ *   num_points  (max_voxels,) int32                   are not touched.
+ *   voxel_num   device int32[1] = min(#distinct voxels, max_voxels).  The reference returns
+ *               this as a host int (forcing a device sync, voxelization_cuda.cu:322); here the
+ *               caller reads it when it needs it.
+ * max_points >= 0 and max_voxels >= 0 (the reference's -1 "unbounded" is routed to
+ * dynamic_voxelize by its Python wrapper, voxelize.py:41).
+ * workspace: >= pcfe_hard_voxelize_workspace_bytes(...) bytes, 256-byte aligned, device memory;
+ * contents are scratch.  n == 0 sets voxel_num = 0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pcfe_frame {
+  const float* points; /* (n, c) */
+  int64_t n;
+  float* voxels;       /* (max_voxels, max_points, c) */
+  int32_t* coors;      /* (max_voxels, 3) */
+  int32_t* num_points; /* (max_voxels,) */
+} pcfe_frame_t;
+
+/* Minimum workspace for a batch whose largest frame has n_max points.  `frames_in_flight`
+ * (1..num_frames) is how many frames are processed per wave; larger values need more memory
+ * but fewer launches.  Pass 0 to let the library pick (sized to keep scratch L2-resident). */
+size_t pcfe_hard_voxelize_workspace_bytes(int64_t n_max, int num_frames, int frames_in_flight,
+                                          const float voxel_size[3], const float coors_range[6],
+                                          int max_points, int max_voxels);
+
+int pcfe_hard_voxelize_f32(const float* points, int64_t n, int c,
+                           const float voxel_size[3], const float coors_range[6],
+                           int max_points, int max_voxels,
+                           float* voxels, int32_t* coors, int32_t* num_points,
+                           int32_t* voxel_num, void* workspace, size_t workspace_bytes,
+                           int device, void* stream);
+
+/* Batched: what the detectors' per-frame Python loop does (mmdet3d/models/detectors/
+ * openpcdet.py:59-76, voxelnet.py:50-67), as one launch sequence.  `frames` is a HOST array;
+ * voxel_num is device int32[num_frames]. */
+int pcfe_hard_voxelize_batch_f32(const pcfe_frame_t* frames, int num_frames, int c,
+                                 const float voxel_size[3], const float coors_range[6],
+                                 int max_points, int max_voxels, int32_t* voxel_num,
+                                 void* workspace, size_t workspace_bytes, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * points in boxes
+ * Replaces: roiaware_pool3d_ext.points_in_boxes_{gpu,batch,cpu}(boxes, points, out)
+ *           mmdet3d/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:40-47,126-136,
+ *           points_in_boxes_cuda.cu:51-203, points_in_boxes_cpu.cpp:16-69;
+ *           call sites mmdet3d/ops/roiaware_pool3d/points_in_boxes.py:46-48,78-80,119-121.
+ * boxes (b, t, 7) float32 = (cx, cy, cz_bottom, w, l, h, rz); points (b, m, 3) float32.
+ * The inside test is the CPU one (points_in_boxes_cpu.cpp:25-40) bit for bit: glibc-exact
+ * cosf/sinf of (float)(rz + pi/2), un-fused rotation, inclusive z slab, strict x/y faces.
+ *   _part   -> out (b, m)    int32: lowest box index containing the point, else -1   ("gpu")
+ *   _all    -> out (b, m, t) int32 0/1, point-major                                  ("batch")
+ *   _boxmajor: boxes (t,7), points (n,3) -> out (t, n) int32 0/1                     ("cpu" layout)
+ * Every element of `out` is written (no pre-fill needed).  b, m or t == 0 is a no-op.
+ * workspace: >= pcfe_points_in_boxes_workspace_bytes(b, t) bytes, 256-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcfe_points_in_boxes_workspace_bytes(int b, int t);
+
+int pcfe_points_in_boxes_part_f32(const float* boxes, const float* points, int b, int t, int64_t m,
+                                  int32_t* out, void* workspace, size_t workspace_bytes,
+                                  int device, void* stream);
+int pcfe_points_in_boxes_all_f32(const float* boxes, const float* points, int b, int t, int64_t m,
+                                 int32_t* out, void* workspace, size_t workspace_bytes,
+                                 int device, void* stream);
+int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float* points, int t, int64_t n,
+                                      int32_t* out, void* workspace, size_t workspace_bytes,
+                                      int device, void* stream);
+
+/* Test hook: device evaluation of the glibc-exact sinf/cosf used for the boxes.
+ * x, s, c are device float arrays of length n. */
+int pcfe_debug_sincosf(const float* x, int64_t n, float* s, float* c, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCFE_H_ */

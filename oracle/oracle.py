@@ -52,6 +52,9 @@ def lib():
         L.pcfe_oracle_host_sincosf.restype = None
         L.pcfe_oracle_sincosf_sweep.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, _u32p]
         L.pcfe_oracle_sincosf_sweep.restype = ctypes.c_int64
+        for name in ("pcfe_oracle_host_sincosf_array", "pcfe_oracle_sincosf_array"):
+            getattr(L, name).argtypes = [_f32p, ctypes.c_int64, _f32p, _f32p]
+            getattr(L, name).restype = None
         _lib = L
     return _lib
 
@@ -152,6 +155,15 @@ def sincosf(x, host=False):
     fn = lib().pcfe_oracle_host_sincosf if host else lib().pcfe_oracle_sincosf
     fn(ctypes.c_float(x), ctypes.byref(s), ctypes.byref(c))
     return np.float32(s.value), np.float32(c.value)
+
+
+def sincosf_array(x, host=True):
+    """sinf/cosf of every element of x with the host libm (host=True) or the restatement."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    s, c = np.empty_like(x), np.empty_like(x)
+    fn = lib().pcfe_oracle_host_sincosf_array if host else lib().pcfe_oracle_sincosf_array
+    fn(_p(x, _f32p), x.size, _p(s, _f32p), _p(c, _f32p))
+    return s, c
 
 
 def sincosf_sweep(lo_bits, hi_bits, stride=1):

@@ -315,6 +315,14 @@ void pcfe_oracle_host_sincosf(float x, float* sinp, float* cosp) {
   *cosp = cosf(vx);
 }
 
+void pcfe_oracle_host_sincosf_array(const float* x, int64_t n, float* sinp, float* cosp) {
+  for (int64_t i = 0; i < n; ++i) pcfe_oracle_host_sincosf(x[i], sinp + i, cosp + i);
+}
+
+void pcfe_oracle_sincosf_array(const float* x, int64_t n, float* sinp, float* cosp) {
+  for (int64_t i = 0; i < n; ++i) pcfe_oracle_sincosf(x[i], sinp + i, cosp + i);
+}
+
 int64_t pcfe_oracle_sincosf_sweep(uint32_t lo_bits, uint32_t hi_bits,
                                   uint32_t stride, uint32_t* first_bad) {
   int64_t bad = 0;

@@ -81,6 +81,10 @@ void pcfe_oracle_sincosf(float x, float* sinp, float* cosp);
 /* Host libm pass-through, so Python can compare without ctypes-ing libm. */
 void pcfe_oracle_host_sincosf(float x, float* sinp, float* cosp);
 
+/* Array forms (host libm / restated) for comparing against the device implementation. */
+void pcfe_oracle_host_sincosf_array(const float* x, int64_t n, float* sinp, float* cosp);
+void pcfe_oracle_sincosf_array(const float* x, int64_t n, float* sinp, float* cosp);
+
 /* Exhaustive sweep helper: compares restated vs host sinf/cosf for every
  * float whose bit pattern is in [lo_bits, hi_bits) (both signs are the caller's
  * business).  Returns the number of mismatches (sin or cos); first mismatching

@@ -1,0 +1,149 @@
+"""GPU parity tests for points_in_boxes_{gpu,batch,cpu}: CUDA path (through the C ABI) vs the
+CPU oracle (host libm trig, like the reference) and the golden vectors.  Bar: bit-exact."""
+import math
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from detmatch_b200 import _cabi, synth
+from detmatch_b200.ops import points_in_boxes_batch, points_in_boxes_cpu, points_in_boxes_gpu
+from oracle import oracle
+from tests.helpers import assert_same_bits, golden, golden_names
+
+pytestmark = pytest.mark.gpu
+
+
+def _all_three(pts, bxs, what):
+    """pts (B,M,3), bxs (B,T,7) numpy -> checks the three ops against the oracle."""
+    tp, tb = torch.from_numpy(pts).cuda(), torch.from_numpy(bxs).cuda()
+    exp_batch = oracle.points_in_boxes_batch(pts, bxs)
+    got = points_in_boxes_batch(tp, tb)
+    assert got.dtype == torch.int32 and tuple(got.shape) == exp_batch.shape
+    assert_same_bits(got.cpu().numpy(), exp_batch, what + " batch")
+    assert_same_bits(points_in_boxes_gpu(tp, tb).cpu().numpy(), oracle.points_in_boxes_gpu(pts, bxs), what + " gpu")
+    for b in range(pts.shape[0]):
+        assert_same_bits(points_in_boxes_cpu(tp[b], tb[b]).cpu().numpy(), oracle.points_in_boxes_cpu(pts[b], bxs[b]),
+                         what + f" cpu-layout b={b}")
+    return int(exp_batch.sum())
+
+
+@pytest.mark.parametrize("name", golden_names("pib_"))
+def test_golden(name):
+    g = golden(name)
+    out = points_in_boxes_cpu(torch.from_numpy(g["points"]).cuda(), torch.from_numpy(g["boxes"]).cuda())
+    assert_same_bits(out.cpu().numpy(), g["expected_cpu"], name)
+    # same through CPU tensors (uploaded, computed on the GPU, returned on the CPU)
+    out = points_in_boxes_cpu(torch.from_numpy(g["points"]), torch.from_numpy(g["boxes"]))
+    assert not out.is_cuda
+    assert_same_bits(out.numpy(), g["expected_cpu"], name + " via cpu tensors")
+    b = points_in_boxes_batch(torch.from_numpy(g["points"])[None].cuda(), torch.from_numpy(g["boxes"])[None].cuda())
+    assert_same_bits(b[0].t().contiguous().cpu().numpy(), g["expected_cpu"], name + " batch^T")
+
+
+def test_reference_literals():
+    """tests/test_models/test_common_modules/test_roiaware_pool3d.py:43-128."""
+    g = golden("pib_kat")
+    got = points_in_boxes_gpu(points=torch.from_numpy(g["gpu_points"]).cuda(), boxes=torch.from_numpy(g["gpu_boxes"]).cuda())
+    assert got.shape == torch.Size([2, 8])
+    assert_same_bits(got.cpu().numpy(), g["expected_gpu"], "points_in_boxes_gpu literal")
+    got = points_in_boxes_batch(points=torch.from_numpy(g["batch_points"]).cuda(), boxes=torch.from_numpy(g["batch_boxes"]).cuda())
+    assert got.shape == torch.Size([1, 15, 2])
+    assert_same_bits(got.cpu().numpy(), g["expected_batch"], "points_in_boxes_batch literal")
+    got = points_in_boxes_cpu(points=torch.from_numpy(g["points"]).cuda(), boxes=torch.from_numpy(g["boxes"]).cuda())
+    assert got.shape == torch.Size([2, 15])
+    assert_same_bits(got.cpu().numpy(), g["expected_cpu"], "points_in_boxes_cpu literal")
+
+
+@pytest.mark.parametrize("b,m,t", [(1, 1, 1), (2, 1000, 4), (3, 777, 5), (2, 5000, 200), (1, 3000, 199), (4, 64, 36),
+                                   (1, 2000, 1024), (1, 500, 1500), (1, 300, 2052), (2, 4099, 128)])
+def test_shapes_vs_oracle(b, m, t):
+    c3 = synth.CONFIGS["C3"]
+    pts = np.stack([synth.lidar_frame(m, 3, 100 * b + k + m, c3["r_max"]).numpy() for k in range(b)])
+    bxs = np.stack([synth.random_boxes(t, 7 * t + k, c3["point_cloud_range"]).numpy() for k in range(b)])
+    k = min(t, m)
+    bxs[:, :k, 0:2] = pts[:, :k, 0:2]     # make boxes hit something
+    bxs[:, :k, 2] = pts[:, :k, 2] - 0.5
+    inside = _all_three(pts, bxs, f"B={b} M={m} T={t}")
+    assert inside > 0
+
+
+def test_faces_edges_corners_and_special_values():
+    g = golden("pib_faces")
+    pts, bxs = g["points"][None], g["boxes"][None]
+    _all_three(pts, bxs, "faces")
+
+
+def test_c3_frame_vs_oracle():
+    """BASELINE config C3 shape: 120k points x 200 boxes (2 of the 16 frames against the oracle,
+    every frame for cross-op consistency)."""
+    c3 = synth.CONFIGS["C3"]
+    B = 16
+    pts = torch.stack([synth.lidar_frame(c3["n"], 3, synth.seed_for(3, k), c3["r_max"]) for k in range(B)])
+    bxs = torch.stack([synth.random_boxes(c3["boxes"], synth.seed_for(3, k) + 500, c3["point_cloud_range"]) for k in range(B)])
+    bxs[:, :50, 0:2] = pts[:, :50, 0:2]
+    bxs[:, :50, 2] = pts[:, :50, 2] - 0.5
+    tp, tb = pts.cuda(), bxs.cuda()
+    got = points_in_boxes_batch(tp, tb)
+    assert got.shape == (B, c3["n"], c3["boxes"])
+    for k in (0, 15):
+        exp = oracle.points_in_boxes_cpu(pts[k].numpy(), bxs[k].numpy())
+        assert exp.sum() > 1000
+        assert_same_bits(got[k].t().contiguous().cpu().numpy(), exp, f"C3 frame {k}")
+    # consistency of the three layouts on all frames
+    first = points_in_boxes_gpu(tp, tb)
+    any_hit = got.max(dim=2).values
+    arg = got.argmax(dim=2).int()
+    assert torch.equal(first, torch.where(any_hit > 0, arg, torch.full_like(arg, -1)))
+    assert torch.equal(points_in_boxes_cpu(tp[3], tb[3]), got[3].t())
+
+
+def test_empty():
+    z = torch.zeros
+    assert points_in_boxes_batch(z((2, 0, 3)).cuda(), z((2, 5, 7)).cuda()).shape == (2, 0, 5)
+    assert points_in_boxes_batch(z((2, 9, 3)).cuda(), z((2, 0, 7)).cuda()).shape == (2, 9, 0)
+    assert (points_in_boxes_gpu(z((2, 9, 3)).cuda(), z((2, 0, 7)).cuda()) == -1).all()
+    assert points_in_boxes_cpu(z((0, 3)).cuda(), z((4, 7)).cuda()).shape == (4, 0)
+    assert points_in_boxes_cpu(z((6, 3)).cuda(), z((0, 7)).cuda()).shape == (0, 6)
+
+
+def test_asserts_like_reference():
+    with pytest.raises(AssertionError):
+        points_in_boxes_gpu(torch.zeros((2, 4, 3)).cuda(), torch.zeros((1, 4, 7)).cuda())
+    with pytest.raises(AssertionError):
+        points_in_boxes_batch(torch.zeros((1, 4, 3)).cuda(), torch.zeros((1, 4, 6)).cuda())
+    with pytest.raises(AssertionError):
+        points_in_boxes_cpu(torch.zeros((4, 2)).cuda(), torch.zeros((4, 7)).cuda())
+
+
+def test_current_device_untouched():
+    """points_in_boxes.py:32-44 changes the current device as a side effect; we must not."""
+    before = torch.cuda.current_device()
+    points_in_boxes_gpu(torch.zeros((1, 4, 3)).cuda(), torch.zeros((1, 2, 7)).cuda())
+    assert torch.cuda.current_device() == before
+
+
+def _bits(f):
+    return struct.unpack("<I", struct.pack("<f", f))[0]
+
+
+def test_device_trig_equals_host_libm():
+    """cosa/sina come from a device restatement of glibc's sinf/cosf: compare with the HOST libm of
+    this machine (what the reference would call here) on 6 M angles incl. every box-yaw-sized one."""
+    lo, hi = _bits(2.0 ** -14), _bits(16.0)
+    sweeps = [np.arange(lo, hi, 61, dtype=np.int64), np.arange(_bits(16.0), _bits(120.0), 17, dtype=np.int64),
+              np.arange(_bits(120.0), 0x7F800000, 4099, dtype=np.int64), np.arange(0, lo, 8191, dtype=np.int64)]
+    u = np.concatenate(sweeps).astype(np.uint32)
+    u = np.concatenate([u, u | np.uint32(0x80000000), np.array([0x7F800000, 0xFF800000, 0x7FC00000], dtype=np.uint32)])
+    x = torch.from_numpy(u.view(np.float32).copy()).cuda()
+    s, c = torch.empty_like(x), torch.empty_like(x)
+    rc = _cabi.lib().pcfe_debug_sincosf(x.data_ptr(), x.numel(), s.data_ptr(), c.data_ptr(), 0,
+                                        torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    xs = x.cpu().numpy()
+    hs, hc = oracle.sincosf_array(xs, host=True)   # this machine's libm sinf/cosf
+    gs, gc = s.cpu().numpy(), c.cpu().numpy()
+    nan = np.isnan(hs) & np.isnan(gs) & np.isnan(hc) & np.isnan(gc)
+    bad = ((hs.view(np.uint32) != gs.view(np.uint32)) | (hc.view(np.uint32) != gc.view(np.uint32))) & ~nan
+    assert bad.sum() == 0, f"{int(bad.sum())} device sin/cos values differ from the host libm, first x bits {u[np.argmax(bad)]:#x}"

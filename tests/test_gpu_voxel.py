@@ -1,0 +1,263 @@
+"""GPU parity tests for hard / dynamic voxelization: CUDA path (through the C ABI) vs the CPU
+oracle and the committed golden vectors.  Bar: bit-exact voxels, coors, num_points_per_voxel."""
+import numpy as np
+import pytest
+import torch
+
+from detmatch_b200 import synth
+from detmatch_b200.ops import Voxelization, voxelization, voxelize_batch
+from detmatch_b200.ops.voxel import voxel_layer
+from oracle import oracle
+from tests.helpers import assert_same_bits, golden, golden_names
+
+pytestmark = pytest.mark.gpu
+
+KITTI = [0, -40, -3, 70.4, 40, 1]
+
+
+def _gpu_hard(pts, vs, rg, p, v):
+    out = voxelization(torch.from_numpy(np.ascontiguousarray(pts)).cuda(), list(vs), list(rg), int(p), int(v))
+    return [o.cpu().numpy() for o in out]
+
+
+def _check_hard(pts, vs, rg, p, v, what=""):
+    ev, ec, en = oracle.hard_voxelize(pts, vs, rg, p, v)
+    gv, gc, gn = _gpu_hard(pts, vs, rg, p, v)
+    assert_same_bits(gc, ec, what + " coors")
+    assert_same_bits(gn, en, what + " num")
+    assert_same_bits(gv, ev, what + " voxels")
+    return len(en)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("voxel_") if n != "voxel_generator_kat"])
+def test_golden_hard_and_dynamic(name):
+    g = golden(name)
+    gv, gc, gn = _gpu_hard(g["points"], g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
+    assert_same_bits(gc, g["coors"], "coors")
+    assert_same_bits(gn, g["num"], "num")
+    assert_same_bits(gv, g["voxels"], "voxels")
+    if "dyn_coors" in g:
+        d = voxelization(torch.from_numpy(g["points"]).cuda(), list(g["voxel_size"]), list(g["range"]), -1, -1)
+        assert_same_bits(d.cpu().numpy(), g["dyn_coors"], "dyn")
+
+
+def test_voxel_generator_kat_float32():
+    """tests/test_models/test_voxel_encoder/test_voxel_generator.py:6-22 literal (float32 input)."""
+    g = golden("voxel_generator_kat")
+    gv, gc, gn = _gpu_hard(g["points64"].astype(np.float32), g["voxel_size"], g["range"], g["max_points"], g["max_voxels"])
+    assert_same_bits(gc, g["coors"], "coors")
+    assert_same_bits(gn, g["num"], "num")
+    assert_same_bits(gv, g["voxels32"], "voxels")
+
+
+def test_reference_test_voxelization_flow():
+    """tests/test_models/test_voxel_encoder/test_voxelize.py:15-83 with the nn.Module API."""
+    g = golden("voxel_kitti_fixture")
+    vs, rg = [0.5, 0.5, 0.5], KITTI
+    hard = Voxelization(vs, rg, 1000)
+    dyn = Voxelization(vs, rg, -1)
+    points = torch.from_numpy(g["points"]).contiguous().to("cuda:0")
+    voxels, coors, num = hard.forward(points)
+    assert np.all(coors.cpu().numpy() == g["coors"])
+    assert np.all(voxels.cpu().numpy() == g["voxels"])
+    assert np.all(num.cpu().numpy() == g["num"])
+    dc = dyn.forward(points).cpu().numpy()
+    pts = g["points"]
+    for i in range(g["voxels"].shape[0]):
+        idx = np.all(dc == g["coors"][i], axis=1)
+        k = pts[idx].shape[0]
+        assert k > 0 and k == g["num"][i]
+        assert np.all(pts[idx] == g["voxels"][i][:k])
+
+
+@pytest.mark.parametrize("cfg_name,ci", [("C1", 1), ("C4", 4), ("C5", 5)])
+@pytest.mark.parametrize("kind", ["lidar", "uniform"])
+def test_full_size_frame_vs_oracle(cfg_name, ci, kind):
+    cfg = synth.CONFIGS[cfg_name]
+    if kind == "lidar":
+        pts = synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(ci, 0), cfg["r_max"]).numpy()
+    else:
+        pts = synth.uniform_frame(cfg["n"], cfg["c"], synth.seed_for(ci, 1), cfg["point_cloud_range"]).numpy()
+    m = _check_hard(pts, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], cfg["max_voxels"],
+                    f"{cfg_name}/{kind}")
+    assert m > 1000
+    d = voxelization(torch.from_numpy(pts).cuda(), cfg["voxel_size"], cfg["point_cloud_range"], -1, -1)
+    assert_same_bits(d.cpu().numpy(), oracle.dynamic_voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"]), "dyn")
+
+
+@pytest.mark.parametrize("p,v", [(1, 7), (3, 150), (5, 100000), (64, 50), (200, 3)])
+def test_caps(p, v):
+    rng = np.random.default_rng(p * 1000 + v)
+    pts = np.concatenate([rng.uniform([0, -4, -3], [8, 4, 1], size=(20011, 3)), rng.uniform(0, 1, size=(20011, 1))],
+                         axis=1).astype(np.float32)
+    _check_hard(pts, [0.5, 0.5, 0.5], KITTI, p, v, f"caps P={p} V={v}")
+
+
+def test_heavy_contention_single_voxel():
+    """All points in very few voxels: the sorted per-voxel lists must still come out in index order."""
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.uniform([1.0, 1.0, -1.0], [1.9, 1.4, -0.6], size=(50000, 3)),
+                          rng.uniform(0, 1, size=(50000, 2))], axis=1).astype(np.float32)
+    for p in (1, 5, 64, 333):
+        _check_hard(pts, [0.5, 0.5, 0.5], KITTI, p, 100, f"contention P={p}")
+
+
+@pytest.mark.parametrize("c", [3, 4, 5, 7])
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 4097])
+def test_shapes(c, n):
+    rng = np.random.default_rng(c * 100 + n)
+    pts = np.concatenate([rng.uniform([-2, -42, -3.5], [72, 42, 1.5], size=(n, 3)), rng.uniform(0, 1, size=(n, c - 3))],
+                         axis=1).astype(np.float32)
+    _check_hard(pts, [0.4, 0.4, 0.8], KITTI, 3, 500, f"C={c} N={n}")
+    d = voxelization(torch.from_numpy(pts).cuda(), [0.4, 0.4, 0.8], KITTI, -1, -1)
+    assert_same_bits(d.cpu().numpy(), oracle.dynamic_voxelize(pts, [0.4, 0.4, 0.8], KITTI), "dyn")
+
+
+def test_empty_and_all_out_of_range():
+    vs = [0.5, 0.5, 0.5]
+    v, c, n = voxelization(torch.zeros((0, 4), device="cuda"), vs, KITTI, 5, 10)
+    assert v.shape == (0, 5, 4) and c.shape == (0, 3) and n.shape == (0,)
+    assert voxelization(torch.zeros((0, 4), device="cuda"), vs, KITTI, -1, -1).shape == (0, 3)
+    far = torch.full((100, 4), 1e6, device="cuda")
+    v, c, n = voxelization(far, vs, KITTI, 5, 10)
+    assert v.shape[0] == 0
+    assert (voxelization(far, vs, KITTI, -1, -1) == -1).all()
+    v, c, n = voxelization(torch.rand((100, 4), device="cuda"), vs, KITTI, 5, 0)
+    assert v.shape[0] == 0
+
+
+def test_special_values_nan_inf():
+    g = golden("voxel_special")
+    pts = torch.from_numpy(g["points"]).cuda()
+    d = voxelization(pts, list(g["voxel_size"]), list(g["range"]), -1, -1).cpu().numpy()
+    assert_same_bits(d, g["dyn_coors"], "special dyn")
+    assert (d[8:16] == -1).all()  # NaN / Inf / huge rows
+
+
+def test_voxel_layer_dropin_signature():
+    """voxel_layer.hard_voxelize(points, voxels, coors, num, vs, range, P, V, 3) -> int, in place."""
+    g = golden("voxel_caps")
+    pts = torch.from_numpy(g["points"]).cuda()
+    P, V = int(g["max_points"]), int(g["max_voxels"])
+    voxels = pts.new_zeros((V, P, pts.size(1)))
+    coors = pts.new_zeros((V, 3), dtype=torch.int)
+    num = pts.new_zeros((V,), dtype=torch.int)
+    m = voxel_layer.hard_voxelize(pts, voxels, coors, num, list(g["voxel_size"]), list(g["range"]), P, V, 3)
+    assert isinstance(m, int) and m == len(g["num"])
+    assert_same_bits(voxels[:m].cpu().numpy(), g["voxels"], "voxels")
+    assert_same_bits(coors[:m].cpu().numpy(), g["coors"], "coors")
+    assert_same_bits(num[:m].cpu().numpy(), g["num"], "num")
+    with pytest.raises(RuntimeError, match="contiguous"):
+        voxel_layer.hard_voxelize(pts.t().contiguous().t(), voxels, coors, num, [0.5] * 3, KITTI, P, V, 3)
+    with pytest.raises(TypeError):
+        voxelization(pts.double(), [0.5] * 3, KITTI, P, V)
+
+
+def test_cpu_tensor_round_trip():
+    g = golden("voxel_caps")
+    v, c, n = voxelization(torch.from_numpy(g["points"]), list(g["voxel_size"]), list(g["range"]),
+                           int(g["max_points"]), int(g["max_voxels"]))
+    assert not v.is_cuda
+    assert_same_bits(v.numpy(), g["voxels"], "voxels")
+    assert_same_bits(c.numpy(), g["coors"], "coors")
+
+
+@pytest.mark.parametrize("cfg_name,ci,frames", [("C1", 1, 3), ("C4", 4, 6), ("C5", 5, 3)])
+def test_batched_ragged_vs_oracle(cfg_name, ci, frames):
+    cfg = synth.CONFIGS[cfg_name]
+    sizes = [cfg["n"] // 4 - 17 * k for k in range(frames)]
+    sizes[1] = 0 if frames > 2 else sizes[1]  # an empty frame in the middle of the batch
+    pts = [synth.lidar_frame(n, cfg["c"], synth.seed_for(ci, 30 + k), cfg["r_max"]) if n else torch.zeros((0, cfg["c"]))
+           for k, n in enumerate(sizes)]
+    mv = cfg["max_voxels"] // 4
+    vox, coors, num, vnum = voxelize_batch([p.cuda() for p in pts], cfg["voxel_size"], cfg["point_cloud_range"],
+                                           cfg["max_num_points"], mv, sync=False)
+    counts = vnum.cpu().tolist()
+    exp = [oracle.hard_voxelize(p.numpy(), cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], mv) for p in pts]
+    for k, (ev, ec, en) in enumerate(exp):
+        assert counts[k] == len(en)
+        assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"frame {k} coors")
+        assert_same_bits(num[k, :counts[k]].cpu().numpy(), en, f"frame {k} num")
+        assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"frame {k} voxels")
+    # detector-style concatenation (openpcdet.py:69-76)
+    vc, nc, cb = voxelize_batch([p.cuda() for p in pts], cfg["voxel_size"], cfg["point_cloud_range"],
+                                cfg["max_num_points"], mv, sync=True)
+    assert_same_bits(vc.cpu().numpy(), np.concatenate([e[0] for e in exp]), "cat voxels")
+    assert_same_bits(nc.cpu().numpy(), np.concatenate([e[2] for e in exp]), "cat num")
+    ecb = np.concatenate([np.pad(e[1], ((0, 0), (1, 0)), constant_values=k) for k, e in enumerate(exp)])
+    assert_same_bits(cb.cpu().numpy(), ecb.astype(np.int32), "coors_batch")
+
+
+def test_many_frames_more_than_one_wave():
+    """More frames than fit one wave / one kernel-parameter table (64)."""
+    cfg = synth.CONFIGS["C1"]
+    pts = [synth.lidar_frame(3000 + 7 * k, 4, 9000 + k, 80.0) for k in range(70)]
+    vox, coors, num, vnum = voxelize_batch([p.cuda() for p in pts], cfg["voxel_size"], cfg["point_cloud_range"], 5, 800,
+                                           sync=False)
+    counts = vnum.cpu().tolist()
+    for k in (0, 1, 33, 63, 64, 69):
+        ev, ec, en = oracle.hard_voxelize(pts[k].numpy(), cfg["voxel_size"], cfg["point_cloud_range"], 5, 800)
+        assert counts[k] == len(en)
+        assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"frame {k}")
+        assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"frame {k}")
+
+
+def test_full_c4_batch_properties():
+    """BASELINE config C4 at full size (64 x 180k x 5): size-independent properties on every frame
+    (computed on the GPU with torch ops), plus bit-exact oracle comparison on three frames."""
+    cfg = synth.CONFIGS["C4"]
+    F = 64
+    pts = [synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(4, k), cfg["r_max"]).cuda() for k in range(F)]
+    P, V = cfg["max_num_points"], cfg["max_voxels"]
+    vox, coors, num, vnum = voxelize_batch(pts, cfg["voxel_size"], cfg["point_cloud_range"], P, V, sync=False)
+    counts = vnum.cpu().tolist()
+    gx, gy, gz = 1504, 1504, 40
+    for k in range(F):
+        m = counts[k]
+        dyn = voxelization(pts[k], cfg["voxel_size"], cfg["point_cloud_range"], -1, -1).long()
+        valid = dyn[:, 0] >= 0
+        keys = (dyn[:, 0] * gy + dyn[:, 1]) * gx + dyn[:, 2]
+        uniq, inv = torch.unique(keys[valid], return_inverse=True)
+        assert m == min(len(uniq), V)
+        c = coors[k, :m].long()
+        vkeys = (c[:, 0] * gy + c[:, 1]) * gx + c[:, 2]
+        assert len(torch.unique(vkeys)) == m                      # every voxel once
+        # first-occurrence order: first point index of consecutive voxels is increasing
+        idx = torch.arange(len(keys), device="cuda")[valid]
+        first = torch.full((len(uniq),), len(keys), device="cuda", dtype=torch.long).scatter_reduce(0, inv, idx, "amin")
+        pos = torch.searchsorted(uniq, vkeys)
+        assert (uniq[pos] == vkeys).all()
+        fo = first[pos]
+        assert (fo[1:] > fo[:-1]).all()
+        # counts: min(#points in voxel, P); padding is exactly zero; slot 0 is the first point
+        cnt = torch.bincount(inv, minlength=len(uniq))[pos].clamp(max=P)
+        assert (num[k, :m].long() == cnt).all()
+        slot = torch.arange(P, device="cuda")[None, :, None]
+        pad = vox[k, :m] * (slot >= num[k, :m, None, None]).float()
+        assert (pad == 0).all() and (vox[k, :m].view(torch.int32)[(slot >= num[k, :m, None, None]).expand(-1, -1, 5)] == 0).all()
+        assert (vox[k, :m, 0] == pts[k][fo]).all()
+    for k in (0, 31, 63):
+        ev, ec, en = oracle.hard_voxelize(pts[k].cpu().numpy(), cfg["voxel_size"], cfg["point_cloud_range"], P, V)
+        assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"frame {k} voxels")
+        assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"frame {k} coors")
+        assert_same_bits(num[k, :counts[k]].cpu().numpy(), en, f"frame {k} num")
+
+
+def test_c2_dynamic_batch_16_frames():
+    """BASELINE config C2: 16 KITTI-shape frames, dynamic voxelization, vs the oracle."""
+    cfg = synth.CONFIGS["C2"]
+    for k in range(cfg["frames"]):
+        p = synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(2, k), cfg["r_max"])
+        d = voxelization(p.cuda(), cfg["voxel_size"], cfg["point_cloud_range"], -1, -1)
+        assert_same_bits(d.cpu().numpy(), oracle.dynamic_voxelize(p.numpy(), cfg["voxel_size"], cfg["point_cloud_range"]),
+                         f"C2 frame {k}")
+
+
+def test_repeatable():
+    """Atomics must not leak scheduling order into the result: two runs are bit-identical."""
+    cfg = synth.CONFIGS["C5"]
+    p = synth.lidar_frame(100000, 5, 4242, 60.0).cuda()
+    a = voxelization(p, cfg["voxel_size"], cfg["point_cloud_range"], 64, 40000)
+    b = voxelization(p, cfg["voxel_size"], cfg["point_cloud_range"], 64, 40000)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
