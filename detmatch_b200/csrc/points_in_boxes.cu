@@ -319,12 +319,15 @@ __global__ void fill_kernel(int32_t* out, long long n, int32_t v) {
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Returns PCFE_OK to proceed, 1 when there is nothing to compute, < 0 on argument errors.
+// `per_point_out` is the number of output elements per point (t for the mask layouts, 1 for the
+// first-hit layout): a call whose output is empty is a no-op whatever the pointers are.
 int check_common(const float* boxes, const float* points, const int32_t* out, int b, int t,
-                 int64_t m, void* ws, size_t ws_bytes) {
+                 int64_t m, int64_t per_point_out, void* ws, size_t ws_bytes) {
   if (b < 0 || t < 0 || m < 0) return PCFE_ERR_SHAPE;
   if (b > 65535) return PCFE_ERR_TOO_LARGE;
   if ((int64_t)b * (int64_t)t >= (1ll << 31) || m >= (1ll << 40)) return PCFE_ERR_TOO_LARGE;
-  if (b == 0 || m == 0) return 1;  // nothing to write
+  if (b == 0 || m == 0 || per_point_out == 0) return 1;  // nothing to write
   if (!points || !out) return PCFE_ERR_NULL;
   if (t > 0 && (!boxes || !ws)) return PCFE_ERR_NULL;
   if (((uintptr_t)boxes & 3) || ((uintptr_t)points & 3) || ((uintptr_t)out & 3)) return PCFE_ERR_ALIGN;
@@ -352,7 +355,7 @@ extern "C" size_t pcfe_points_in_boxes_workspace_bytes(int b, int t) {
 extern "C" int pcfe_points_in_boxes_part_f32(const float* boxes, const float* points, int b, int t,
                                              int64_t m, int32_t* out, void* ws, size_t ws_bytes,
                                              int device, void* stream) {
-  int rc = check_common(boxes, points, out, b, t, m, ws, ws_bytes);
+  int rc = check_common(boxes, points, out, b, t, m, 1, ws, ws_bytes);
   if (rc != PCFE_OK) return rc > 0 ? PCFE_OK : rc;
   DeviceGuard guard(device);
   PCFE_CUDA_TRY(guard.err);
@@ -374,7 +377,7 @@ extern "C" int pcfe_points_in_boxes_part_f32(const float* boxes, const float* po
 extern "C" int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float* points, int t,
                                                  int64_t n, int32_t* out, void* ws, size_t ws_bytes,
                                                  int device, void* stream) {
-  int rc = check_common(boxes, points, out, 1, t, n, ws, ws_bytes);
+  int rc = check_common(boxes, points, out, 1, t, n, t, ws, ws_bytes);
   if (rc != PCFE_OK) return rc > 0 ? PCFE_OK : rc;
   if (t == 0) return PCFE_OK;
   DeviceGuard guard(device);
@@ -391,9 +394,8 @@ extern "C" int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float
 extern "C" int pcfe_points_in_boxes_all_f32(const float* boxes, const float* points, int b, int t,
                                             int64_t m, int32_t* out, void* ws, size_t ws_bytes,
                                             int device, void* stream) {
-  int rc = check_common(boxes, points, out, b, t, m, ws, ws_bytes);
+  int rc = check_common(boxes, points, out, b, t, m, t, ws, ws_bytes);
   if (rc != PCFE_OK) return rc > 0 ? PCFE_OK : rc;
-  if (t == 0) return PCFE_OK;
   DeviceGuard guard(device);
   PCFE_CUDA_TRY(guard.err);
   cudaStream_t st = (cudaStream_t)stream;
