@@ -33,6 +33,7 @@ PROTOTYPES = {
     "pcfe_launch_count": (ctypes.c_uint64, []),
     "pcfe_profile_enable": (c_int, [c_int]),
     "pcfe_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
+    "pcfe_debug_set": (c_int, [ctypes.c_char_p, c_int]),
     "pcfe_grid_size": (c_int, [_f3, _f6, ctypes.POINTER(ctypes.c_int32)]),
     "pcfe_dynamic_voxelize_f32": (c_int, [c_void_p, c_int64, c_int, _f3, _f6, c_void_p, c_int, c_void_p]),
     "pcfe_dynamic_voxelize_batch_f32": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64), c_int, c_int,
@@ -105,3 +106,7 @@ def profile_report():
         name, ms, cnt = line.split()
         out[name] = (float(ms), int(cnt))
     return out
+
+
+def debug_set(name, value):
+    check(lib().pcfe_debug_set(name.encode(), int(value)), f"pcfe_debug_set({name})")

@@ -60,6 +60,11 @@ uint64_t pcfe_launch_count(void);
 int pcfe_profile_enable(int on);
 int pcfe_profile_report(char* buf, size_t cap);
 
+/* Test / tuning knobs (not part of the drop-in surface): "hv_path" 0 auto | 1 global-memory path |
+ * 2 shared-memory bucket path; "hv_force_overflow" 1 = every frame also takes the overflow
+ * fallback; "hv_bucket_avg" = target points per bucket. */
+int pcfe_debug_set(const char* name, int value);
+
 /* grid[j] = (int)roundf((range[3+j]-range[j])/voxel_size[j]) in float32, x y z order.
  * Replaces: voxelization_cpu.cpp:119-122 / voxelization_cuda.cu:200-206.  Host-only helper. */
 int pcfe_grid_size(const float voxel_size[3], const float coors_range[6], int32_t grid[3]);
