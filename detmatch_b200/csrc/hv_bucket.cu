@@ -23,8 +23,9 @@
 //   C  hv_scan_flags popcount prefix of the bitmask per frame; voxel_num = min(#cells, V).
 //   D  hvb_order    directory entry -> voxel id = rank of the cell's first point;
 //                   order[vid] = record offset.
-//   E  hvb_expand   voxel-id order: rows gathered through L2, staged in shared memory and written
-//                   as one contiguous float4 stream (data + zero padding), plus coors and counts.
+//   E  hvb_expand   voxel-id order: a warp resolves the source points of 32 consecutive output rows
+//                   and moves them with transposed, fully coalesced stores (data + zero padding);
+//                   plus coors and counts.
 //   F  fallback     (hv_global.cu, one CTA per frame) for frames whose bucket regions overflowed
 //                   (heavy duplication / adversarial keys); a no-op launch otherwise.
 #include <algorithm>
@@ -35,7 +36,7 @@ namespace pcfe {
 
 int hv_launch_scan(const uint32_t* bitmask, size_t bitmask_stride, uint32_t* prefix,
                    size_t prefix_stride, int words, int max_voxels, int32_t* voxel_num, int frames,
-                   cudaStream_t st);
+                   int paired, cudaStream_t st);
 int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size_t overflow_stride,
                     int force, char* scratch_base, size_t scratch_stride, const HvGlobalPlan& p,
                     uint32_t* bitmask, size_t bitmask_stride, uint32_t* prefix, size_t prefix_stride,
@@ -52,7 +53,7 @@ struct HvbWork {
   uint32_t* zero;        // [W] per-frame zeroed block: bitmask[words] | ctl
   size_t zero_stride;    // words
   size_t ctl_off;        // words: ctl = bucket_cnt[nb] | rec_cursor | dir_cursor | overflow
-  uint32_t* wordprefix;  // [W][words]
+  uint32_t* wordprefix;  // [W][2 * words]  {bitmask word, exclusive popcount prefix} pairs
   size_t word_stride;    // words
   int nb, log2_nb, cap, slots, log2_slots;
   uint32_t rec_words, dir_cap;
@@ -179,9 +180,13 @@ hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
 
   const int ne = (int)min(ctl[b], (uint32_t)cap);
   if (ne == 0) return;
-  for (int s = tid; s < S; s += kBucketThreads) {
-    hkey[s] = kEmpty;
-    hval[s] = 0u;
+  {  // hkey = kEmpty, hval = 0 (S is a multiple of 4; the two arrays are contiguous)
+    uint4* k4 = reinterpret_cast<uint4*>(hkey);
+    uint4* v4 = reinterpret_cast<uint4*>(hval);
+    for (int s = tid; s < S / 4; s += kBucketThreads) {
+      k4[s] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+      v4[s] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
   if (tid == 0) s_nclaimed = 0u;
   __syncthreads();
@@ -213,9 +218,11 @@ hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
   __syncthreads();
 
   // size the per-cell lists (min(count, P) entries each, in claim order) and the records
-  // (2 + len words each); cell j of chunk q is handled by thread j - q * kBucketThreads
+  // (2 + len words each) with ONE block scan of the packed pair (record words << 16 | list len):
+  // both totals stay below 2^16 because cap <= 2048.  Cell j of chunk q is handled by thread
+  // j - q * kBucketThreads, which also initialises the cell's list.
   const int nv = (int)s_nclaimed;
-  uint32_t run_lists = 0, run_rec = 0;
+  uint32_t run = 0;  // packed running totals
   uint32_t my_rec_off[kMaxCap / kBucketThreads];
 #pragma unroll
   for (int q = 0; q < kMaxCap / kBucketThreads; ++q) {
@@ -227,17 +234,18 @@ hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
       s = slotlist[j];
       len = min(hval[s], (uint32_t)pe);
     }
-    uint32_t tot_len, tot_rec;
-    const uint32_t ex_len = block_exscan(len, warp_sums, &tot_len);
-    __syncthreads();
-    const uint32_t ex_rec = block_exscan(j < nv ? len + 2u : 0u, warp_sums, &tot_rec);
-    if (j < nv) hval[s] = ((run_lists + ex_len) << 16) | len;
-    my_rec_off[q] = run_rec + ex_rec;
-    run_lists += tot_len;
-    run_rec += tot_rec;
-    __syncthreads();
+    uint32_t tot;
+    const uint32_t ex = run + block_exscan(j < nv ? ((len + 2u) << 16) | len : 0u, warp_sums, &tot);
+    if (j < nv) {
+      const uint32_t off = ex & 0xFFFFu;
+      hval[s] = (off << 16) | len;
+      for (uint32_t t = 0; t < len; ++t) lists[off + t] = kEmpty;
+    }
+    my_rec_off[q] = ex >> 16;
+    run += tot;
+    __syncthreads();  // warp_sums is reused by the next chunk
   }
-  for (uint32_t i = tid; i < run_lists; i += kBucketThreads) lists[i] = kEmpty;
+  const uint32_t run_rec = run >> 16;
   if (tid == 0) {
     s_rec_base = atomicAdd(&ctl[w.nb + kCtlRec], run_rec);
     s_dir_base = atomicAdd(&ctl[w.nb + kCtlDir], (uint32_t)nv);
@@ -291,23 +299,30 @@ hvb_order_kernel(const HvbWork w, const int max_voxels) {
   const uint32_t t = blockIdx.x * 256u + threadIdx.x;
   if (t >= ncell) return;
   const uint2 d = w.dir(f)[t];
-  const uint32_t vid = first_rank(w.bitmask(f), w.prefix(f), d.y);
+  // wordprefix holds {bitmask word, exclusive prefix} pairs: one 8-byte random read per cell
+  const uint2 bp = reinterpret_cast<const uint2*>(w.prefix(f))[d.y >> 5];
+  const uint32_t vid = bp.y + __popc(bp.x & ((1u << (d.y & 31)) - 1u));
   if (vid < (uint32_t)max_voxels) w.order(f)[vid] = d.x;  // voxelization_cpu.cpp:78
 }
 
 // ------------------------------------------------------------------------------------------
 // E: expansion in voxel-id order
 // ------------------------------------------------------------------------------------------
+// A warp owns 32 consecutive output rows (32 * C contiguous floats of the voxels buffer).  Lane l
+// first resolves the source point of row l (order -> record -> point index), then the warp moves
+// the 32 * C words in C fully coalesced store instructions: in iteration t lane l handles word
+// t * 32 + l of the chunk, i.e. column (word % C) of row (word / C), whose source index comes
+// from the owning lane by shuffle.  Gathers touch ~32 / C + 1 distinct point rows per instruction
+// instead of 32 (a per-thread row copy costs one L1 tag lookup per lane and column).
 constexpr int kExpThreads = 256;
-constexpr int kExpPerThread = 4;
-constexpr int kExpTile = kExpThreads * kExpPerThread;  // rows per CTA
+constexpr int kExpRowsPerWarp = 32;
+constexpr int kExpIters = 4;                                          // row groups per warp
+constexpr int kExpTile = (kExpThreads / 32) * kExpRowsPerWarp * kExpIters;  // rows per CTA
 
-template <int C, bool STAGED>
+template <int C>
 __global__ void __launch_bounds__(kExpThreads)
 hvb_expand_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
-                  const int c_rt, const int max_points, const int32_t* __restrict__ voxel_num,
-                  const int vec_ok) {
-  extern __shared__ __align__(16) float stage[];  // kExpTile * c floats when STAGED
+                  const int c_rt, const int max_points, const int32_t* __restrict__ voxel_num) {
   const int f = blockIdx.y;
   if (w.ctl(f)[w.nb + kCtlOverflow]) return;
   const HvFrame& fr = batch.f[f];
@@ -317,11 +332,11 @@ hvb_expand_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const 
   const long long r_base = (long long)blockIdx.x * kExpTile;
   const uint32_t* __restrict__ rec = w.rec(f);
   const uint32_t* __restrict__ order = w.order(f);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
   // coors + counts: one thread per voxel id
 #pragma unroll
-  for (int k = 0; k < kExpPerThread; ++k) {
+  for (int k = 0; k < kExpTile / kExpThreads; ++k) {
     const long long v = r_base + k * kExpThreads + tid;
     if (v < m) {
       const uint32_t q = order[v];
@@ -330,55 +345,78 @@ hvb_expand_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const 
     }
   }
   if (r_base >= rows) return;
-  const int nrows = (int)min((long long)kExpTile, rows - r_base);
+  const float* __restrict__ pts = fr.pts;
+  // Three phases with all kExpIters row groups of the warp in flight in each, so that the
+  // dependent chain order -> record -> point row costs three memory latencies per warp, not
+  // three per row group.
+  uint32_t q[kExpIters], s[kExpIters], src[kExpIters];
+  long long wr0[kExpIters];
 #pragma unroll
-  for (int k = 0; k < kExpPerThread; ++k) {
-    const int lr = k * kExpThreads + tid;
-    if (lr < nrows) {
-      const uint32_t r = (uint32_t)(r_base + lr);
-      const uint32_t vid = r / (uint32_t)max_points;
-      const uint32_t s = r - vid * (uint32_t)max_points;
-      const uint32_t q = order[vid];
-      const uint32_t len = rec[q + 1];
-      float* st = STAGED ? stage + (size_t)lr * c : fr.voxels + (size_t)r * c;
-      if (s < len) {
-        const float* __restrict__ src = fr.pts + (size_t)rec[q + 2 + s] * c;
-        if (C == 4 && vec_ok) {
-          *reinterpret_cast<float4*>(st) = __ldg(reinterpret_cast<const float4*>(src));
-        } else {
-          for (int j = 0; j < c; ++j) st[j] = __ldg(src + j);
-        }
-      } else {
-        if (C == 4 && vec_ok) {
-          *reinterpret_cast<float4*>(st) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          for (int j = 0; j < c; ++j) st[j] = 0.0f;
-        }
+  for (int it = 0; it < kExpIters; ++it) {
+    wr0[it] = r_base + ((long long)(it * (kExpThreads / 32) + wid)) * kExpRowsPerWarp;
+    const long long r = wr0[it] + lane;
+    q[it] = kEmpty;
+    s[it] = 0;
+    if (r < rows) {
+      const uint32_t vid = (uint32_t)r / (uint32_t)max_points;  // rows < 2^31 (checked by the plan)
+      s[it] = (uint32_t)r - vid * (uint32_t)max_points;
+      q[it] = order[vid];
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kExpIters; ++it) {
+    src[it] = kEmpty;  // point index feeding the row, kEmpty = zero padding
+    if (q[it] != kEmpty) {
+      // both loads are issued together; the arena has max_points words of slack behind the
+      // last record, so reading the list entry before knowing the length stays in bounds
+      const uint32_t len = rec[q[it] + 1];
+      const uint32_t idx = rec[q[it] + 2 + s[it]];
+      if (s[it] < len) src[it] = idx;
+    }
+  }
+  float v[kExpIters][C > 0 ? C : 1];
+  if (C > 0) {
+#pragma unroll
+    for (int it = 0; it < kExpIters; ++it) {
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        const int t = k * 32 + lane;
+        const int row = t / C;
+        const int col = t - row * C;
+        const uint32_t sidx = __shfl_sync(0xFFFFFFFFu, src[it], row);
+        v[it][k] = (sidx != kEmpty) ? __ldg(pts + (size_t)sidx * C + col) : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kExpIters; ++it) {
+      if (wr0[it] >= rows) break;  // warp-uniform
+      const int nwords = (int)min((long long)kExpRowsPerWarp, rows - wr0[it]) * C;
+      float* __restrict__ dst = fr.voxels + (size_t)wr0[it] * C;
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        const int t = k * 32 + lane;
+        if (t < nwords) __stcs(dst + t, v[it][k]);
+      }
+    }
+  } else {
+    for (int it = 0; it < kExpIters; ++it) {
+      if (wr0[it] >= rows) break;  // warp-uniform
+      const int nwords = (int)min((long long)kExpRowsPerWarp, rows - wr0[it]) * c;
+      float* __restrict__ dst = fr.voxels + (size_t)wr0[it] * c;
+      for (int t = lane; t < kExpRowsPerWarp * c; t += 32) {  // warp-uniform trip count
+        const int row = t / c;
+        const int col = t - row * c;
+        const uint32_t sidx = __shfl_sync(0xFFFFFFFFu, src[it], row & 31);
+        if (t < nwords) __stcs(dst + t, (sidx != kEmpty) ? __ldg(pts + (size_t)sidx * c + col) : 0.0f);
       }
     }
   }
-  if (!STAGED) return;
-  __syncthreads();
-  float* __restrict__ dst = fr.voxels + (size_t)r_base * c;
-  const int nfl = nrows * c;
-  if (vec_ok) {  // (r_base * c * 4) % 16 == 0 because kExpTile % 4 == 0
-    const int nv4 = nfl >> 2;
-    const float4* s4 = reinterpret_cast<const float4*>(stage);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int i = tid; i < nv4; i += kExpThreads) __stcs(&d4[i], s4[i]);
-    for (int i = (nv4 << 2) + tid; i < nfl; i += kExpThreads) dst[i] = stage[i];
-  } else {
-    for (int i = tid; i < nfl; i += kExpThreads) dst[i] = stage[i];
-  }
 }
 
-template <int C, bool STAGED>
-int launch_expand(dim3 grid, size_t smem, cudaStream_t st, const HvBatch& b, const HvbWork& w,
-                  const GridParams& g, int c, int p, const int32_t* vn, int vec_ok) {
-  if (smem > 48 * 1024)
-    PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_expand_kernel<C, STAGED>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  hvb_expand_kernel<C, STAGED><<<grid, kExpThreads, smem, st>>>(b, w, g, c, p, vn, vec_ok);
+template <int C>
+int launch_expand(dim3 grid, cudaStream_t st, const HvBatch& b, const HvbWork& w,
+                  const GridParams& g, int c, int p, const int32_t* vn) {
+  hvb_expand_kernel<C><<<grid, kExpThreads, 0, st>>>(b, w, g, c, p, vn);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
@@ -394,6 +432,7 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   int rc = hvg_make_plan(n_max, vs, rg, max_points, max_voxels, &p->slow);
   if (rc != PCFE_OK) return rc;
   if (max_points > 0xFFFF) return PCFE_ERR_CAPS;  // list length is packed into 16 bits
+  if ((int64_t)max_voxels * (int64_t)std::max(max_points, 1) >= (1ll << 31)) return PCFE_ERR_TOO_LARGE;
   p->g = p->slow.g;
   p->npad = p->slow.npad;
   p->words = p->slow.words;
@@ -404,7 +443,10 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   p->nb = 1 << lg;
   const int64_t avg = (n_max + p->nb - 1) / p->nb;
   if (avg + avg / 4 > kMaxCap) return PCFE_ERR_TOO_LARGE;  // caller uses the global path
-  p->cap = (int)std::min<int64_t>(kMaxCap, std::max<int64_t>(std::max(2 * avg, avg + 1024), 64));
+  // head-room for hash imbalance and for heavily populated cells (pillars): exceeding it is not
+  // an error, the frame just takes the fallback
+  p->cap = (int)std::min<int64_t>(kMaxCap, avg + std::max<int64_t>(avg / 2, 768) +
+                                               std::min<int64_t>(8 * (int64_t)max_points, 512));
   p->cap = (p->cap + 7) & ~7;
   int ls = 6;
   while ((1 << ls) < p->cap + p->cap / 4) ++ls;
@@ -414,7 +456,7 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   // arenas: every cell needs 2 + len words, sum(len) <= n, cells <= n  ->  3 * npad words
   p->rec_words = (size_t)3 * (size_t)p->npad;
   p->ent_b = align256((size_t)p->nb * (size_t)p->cap * sizeof(uint2));
-  p->rec_b = align256(p->rec_words * sizeof(uint32_t));
+  p->rec_b = align256((p->rec_words + (size_t)std::max(max_points, 1) + 8) * sizeof(uint32_t));  // + read slack
   p->dir_b = align256((size_t)p->npad * sizeof(uint2));
   const size_t vmax = (size_t)std::min<int64_t>(max_voxels, std::max<int64_t>(n_max, 1));
   p->order_b = align256(std::max<size_t>(vmax, 1) * sizeof(uint32_t));
@@ -424,7 +466,7 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   // the fallback reuses the frame's own region as table | lists | pslot
   const size_t slow = p->slow.table_b + p->slow.list_b + p->slow.pslot_b;
   p->region_b = std::max(fast, slow);
-  p->per_frame = p->region_b + 2 * p->word_b + p->cnt_b;
+  p->per_frame = p->region_b + 3 * p->word_b + p->cnt_b;  // bitmask + {bits, prefix} pairs
   p->smem_bucket = (size_t)(2 * p->slots + 2 * p->cap) * 4 + (size_t)(2 * p->cap) * 2;
   return PCFE_OK;
 }
@@ -447,16 +489,11 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
   w.zero_stride = zero_per / sizeof(uint32_t);
   w.ctl_off = p.word_b / sizeof(uint32_t);
   w.wordprefix = (uint32_t*)(zero_base + (size_t)wave * zero_per);
-  w.word_stride = p.word_b / sizeof(uint32_t);
+  w.word_stride = 2 * p.word_b / sizeof(uint32_t);
   w.nb = p.nb; w.log2_nb = p.log2_nb; w.cap = p.cap; w.slots = p.slots; w.log2_slots = p.log2_slots;
   w.rec_words = (uint32_t)p.rec_words;
   w.dir_cap = (uint32_t)p.npad;
 
-  bool vec_ok = true;  // float4 row stream needs 16-byte aligned voxel buffers (and points for C == 4)
-  for (int k = 0; k < num_frames && vec_ok; ++k)
-    vec_ok = !(((uintptr_t)frames[k].voxels & 15) || (c == 4 && ((uintptr_t)frames[k].points & 15)));
-  const size_t stage_b = (size_t)kExpTile * c * sizeof(float);
-  const bool staged = stage_b <= 96 * 1024;
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)p.smem_bucket));
   const int pe = std::max(max_points, 1);
@@ -489,7 +526,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       PCFE_LAUNCH_CHECK();
     }
     int rc = hv_launch_scan(w.zero, w.zero_stride, w.wordprefix, w.word_stride, wnpad / 32,
-                            max_voxels, voxel_num + f0, wv, st);
+                            max_voxels, voxel_num + f0, wv, 1, st);
     if (rc != PCFE_OK) return rc;
     {
       ProfScope ps("hvb_order", st);
@@ -503,10 +540,9 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       const int64_t rows = std::max<int64_t>(vmax * std::max(max_points, 1), 1);
       const dim3 grid((unsigned)((rows + kExpTile - 1) / kExpTile), (unsigned)wv);
       const int32_t* vn = voxel_num + f0;
-      if (!staged) rc = launch_expand<0, false>(grid, 0, st, b, w, p.g, c, max_points, vn, 0);
-      else if (c == 4 && vec_ok) rc = launch_expand<4, false>(grid, 0, st, b, w, p.g, c, max_points, vn, 1);
-      else if (c == 5) rc = launch_expand<5, true>(grid, stage_b, st, b, w, p.g, c, max_points, vn, vec_ok);
-      else rc = launch_expand<0, true>(grid, stage_b, st, b, w, p.g, c, max_points, vn, vec_ok);
+      if (c == 4) rc = launch_expand<4>(grid, st, b, w, p.g, c, max_points, vn);
+      else if (c == 5) rc = launch_expand<5>(grid, st, b, w, p.g, c, max_points, vn);
+      else rc = launch_expand<0>(grid, st, b, w, p.g, c, max_points, vn);
       if (rc != PCFE_OK) return rc;
     }
     rc = hvg_launch_slow(b, wv, w.zero + w.ctl_off + p.nb + kCtlOverflow, w.zero_stride,

@@ -193,7 +193,8 @@ constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads)
 hv_scan_flags_kernel(const uint32_t* __restrict__ bitmask_base, const size_t bitmask_stride,
                      uint32_t* __restrict__ prefix_base, const size_t prefix_stride,
-                     const int words, const int max_voxels, int32_t* __restrict__ voxel_num) {
+                     const int words, const int max_voxels, int32_t* __restrict__ voxel_num,
+                     const int paired /* 1: prefix array holds {bitmask word, prefix} pairs */) {
   const int f = blockIdx.x;
   const uint32_t* __restrict__ bitmask = bitmask_base + (size_t)f * bitmask_stride;
   uint32_t* __restrict__ wordprefix = prefix_base + (size_t)f * prefix_stride;
@@ -211,8 +212,10 @@ hv_scan_flags_kernel(const uint32_t* __restrict__ bitmask_base, const size_t bit
   for (int j = 0; j < per; ++j) {
     const int idx = w0 + j;
     if (idx < words) {
-      wordprefix[idx] = run;
-      run += __popc(bitmask[idx]);
+      const uint32_t bits = bitmask[idx];
+      if (paired) reinterpret_cast<uint2*>(wordprefix)[idx] = make_uint2(bits, run);
+      else wordprefix[idx] = run;
+      run += __popc(bits);
     }
   }
   if (threadIdx.x == 0) voxel_num[f] = (int32_t)min(total, (uint32_t)max_voxels);
@@ -220,10 +223,10 @@ hv_scan_flags_kernel(const uint32_t* __restrict__ bitmask_base, const size_t bit
 
 int hv_launch_scan(const uint32_t* bitmask, size_t bitmask_stride, uint32_t* prefix,
                    size_t prefix_stride, int words, int max_voxels, int32_t* voxel_num, int frames,
-                   cudaStream_t st) {
+                   int paired, cudaStream_t st) {
   ProfScope ps("hv_scan_flags", st);
-  hv_scan_flags_kernel<<<frames, kScanThreads, 0, st>>>(bitmask, bitmask_stride, prefix,
-                                                       prefix_stride, words, max_voxels, voxel_num);
+  hv_scan_flags_kernel<<<frames, kScanThreads, 0, st>>>(bitmask, bitmask_stride, prefix, prefix_stride,
+                                                       words, max_voxels, voxel_num, paired);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
@@ -438,7 +441,7 @@ int hvg_run(const pcfe_frame_t* frames, int num_frames, int c, const HvGlobalPla
       PCFE_LAUNCH_CHECK();
     }
     int rc = hv_launch_scan(w.bitmask, w.word_stride, w.wordprefix, w.word_stride, wwords,
-                            max_voxels, voxel_num + f0, wv, st);
+                            max_voxels, voxel_num + f0, wv, 0, st);
     if (rc != PCFE_OK) return rc;
     {
       ProfScope ps("hvg_assign", st);

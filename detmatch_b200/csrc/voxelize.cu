@@ -90,7 +90,7 @@ __global__ void hv_zero_counts_kernel(int32_t* voxel_num, int n) {
   if (i < n) voxel_num[i] = 0;
 }
 
-constexpr size_t kL2ScratchBudget = 48ull << 20;  // keep a wave's scratch resident in L2
+constexpr size_t kL2ScratchBudget = 1ull << 30;  // measured: fewer, larger waves beat L2-resident scratch (launch gaps dominate)
 
 struct HvChoice {
   bool bucket;
