@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--frames-in-flight", type=int, default=0)
+    ap.add_argument("--hv-wave", type=int, default=0, help="tuning: frames per wave (0 = library default)")
+    ap.add_argument("--hv-bucket-avg", type=int, default=0, help="tuning: target points per bucket")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (default: all cores, <= 64)")
     return ap.parse_args()
 
@@ -232,6 +234,10 @@ def run_ours(args):
     cfg = workload_config(args)
     F, N, C = cfg["frames"], cfg["n"], cfg["c"]
     P, V = cfg["max_num_points"], cfg["max_voxels"]
+    if args.hv_wave:
+        _cabi.debug_set("hv_wave", args.hv_wave)
+    if args.hv_bucket_avg:
+        _cabi.debug_set("hv_bucket_avg", args.hv_bucket_avg)
 
     # synthetic frames, generated on the host; each rank has its own 64 frames
     host = [synth.lidar_frame(N, C, synth.seed_for(cfg["index"], rank * F + k), cfg["r_max"]).pin_memory() for k in range(F)]

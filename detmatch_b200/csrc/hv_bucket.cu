@@ -29,6 +29,7 @@
 //   F  fallback     (hv_global.cu, one CTA per frame) for frames whose bucket regions overflowed
 //                   (heavy duplication / adversarial keys); a no-op launch otherwise.
 #include <algorithm>
+#include <mutex>
 
 #include "hv_common.cuh"
 
@@ -46,28 +47,35 @@ int g_opt_bucket_avg = 1024;  // target points per bucket (tunable through pcfe_
 
 namespace {
 
+struct __align__(16) Cell {  // one occupied voxel of a frame
+  uint32_t key;       // linear cell index
+  uint32_t len;       // min(#points, P): entries in its list
+  uint32_t list_off;  // offset of its ascending point-index list in the frame's list arena
+  uint32_t first;     // its first point (== list entry 0)
+};
+
 struct HvbWork {
-  char* region;          // [W] per-frame scratch: ent | rec | dir | order
+  char* region;          // [W] per-frame scratch: ent | lists | cells | vcell
   size_t region_stride;  // bytes
-  size_t rec_off, dir_off, order_off;  // byte offsets inside a frame region
+  size_t lst_off, cells_off, vcell_off;  // byte offsets inside a frame region
   uint32_t* zero;        // [W] per-frame zeroed block: bitmask[words] | ctl
   size_t zero_stride;    // words
-  size_t ctl_off;        // words: ctl = bucket_cnt[nb] | rec_cursor | dir_cursor | overflow
+  size_t ctl_off;        // words: ctl = bucket_cnt[nb] | list_cursor | cell_cursor | overflow
   uint32_t* wordprefix;  // [W][2 * words]  {bitmask word, exclusive popcount prefix} pairs
   size_t word_stride;    // words
   int nb, log2_nb, cap, slots, log2_slots;
-  uint32_t rec_words, dir_cap;
+  uint32_t arena_cap;    // capacity of the list arena and of the cell array (entries)
 
   __device__ __forceinline__ uint2* ent(int f) const { return reinterpret_cast<uint2*>(region + (size_t)f * region_stride); }
-  __device__ __forceinline__ uint32_t* rec(int f) const { return reinterpret_cast<uint32_t*>(region + (size_t)f * region_stride + rec_off); }
-  __device__ __forceinline__ uint2* dir(int f) const { return reinterpret_cast<uint2*>(region + (size_t)f * region_stride + dir_off); }
-  __device__ __forceinline__ uint32_t* order(int f) const { return reinterpret_cast<uint32_t*>(region + (size_t)f * region_stride + order_off); }
+  __device__ __forceinline__ uint32_t* lst(int f) const { return reinterpret_cast<uint32_t*>(region + (size_t)f * region_stride + lst_off); }
+  __device__ __forceinline__ Cell* cells(int f) const { return reinterpret_cast<Cell*>(region + (size_t)f * region_stride + cells_off); }
+  __device__ __forceinline__ Cell* vcell(int f) const { return reinterpret_cast<Cell*>(region + (size_t)f * region_stride + vcell_off); }
   __device__ __forceinline__ uint32_t* bitmask(int f) const { return zero + (size_t)f * zero_stride; }
   __device__ __forceinline__ uint32_t* ctl(int f) const { return zero + (size_t)f * zero_stride + ctl_off; }
   __device__ __forceinline__ uint32_t* prefix(int f) const { return wordprefix + (size_t)f * word_stride; }
 };
 // ctl word indices after the nb bucket counters
-constexpr int kCtlRec = 0, kCtlDir = 1, kCtlOverflow = 2;
+constexpr int kCtlList = 0, kCtlCell = 1, kCtlOverflow = 2;
 
 // ------------------------------------------------------------------------------------------
 // A: partition points into hash buckets
@@ -157,7 +165,7 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
 // B: one CTA per (frame, bucket), everything in shared memory
 // ------------------------------------------------------------------------------------------
 constexpr int kBucketThreads = 256;
-constexpr int kMaxCap = 2048;  // entries per bucket; kMaxCap / kBucketThreads record offsets in registers
+constexpr int kMaxCap = 2048;  // entries per bucket (list offsets are packed into 16 bits)
 
 // dynamic shared memory (words): hkey[S] | hval[S] | eidx[cap] | lists[cap] | eslot[cap] (u16) |
 // slotlist[cap] (u16)
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(kBucketThreads)
 hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ uint32_t warp_sums[33];
-  __shared__ uint32_t s_nclaimed, s_rec_base, s_dir_base;
+  __shared__ uint32_t s_nclaimed, s_list_base, s_cell_base;
 
   const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
   uint32_t* ctl = w.ctl(f);
@@ -217,17 +225,13 @@ hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
   }
   __syncthreads();
 
-  // size the per-cell lists (min(count, P) entries each, in claim order) and the records
-  // (2 + len words each) with ONE block scan of the packed pair (record words << 16 | list len):
-  // both totals stay below 2^16 because cap <= 2048.  Cell j of chunk q is handled by thread
-  // j - q * kBucketThreads, which also initialises the cell's list.
+  // size the per-cell lists (min(count, P) entries each, in claim order) with a block scan; cell
+  // j of chunk q is handled by thread j - q * kBucketThreads, which also initialises its list
   const int nv = (int)s_nclaimed;
-  uint32_t run = 0;  // packed running totals
-  uint32_t my_rec_off[kMaxCap / kBucketThreads];
-#pragma unroll
-  for (int q = 0; q < kMaxCap / kBucketThreads; ++q) {
-    const int j = q * kBucketThreads + tid;
-    if (q * kBucketThreads >= nv) break;  // block-uniform
+  uint32_t run_lists = 0;
+#pragma unroll 1
+  for (int j0 = 0; j0 < nv; j0 += kBucketThreads) {
+    const int j = j0 + tid;
     uint32_t len = 0;
     int s = 0;
     if (j < nv) {
@@ -235,20 +239,17 @@ hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
       len = min(hval[s], (uint32_t)pe);
     }
     uint32_t tot;
-    const uint32_t ex = run + block_exscan(j < nv ? ((len + 2u) << 16) | len : 0u, warp_sums, &tot);
+    const uint32_t off = run_lists + block_exscan(len, warp_sums, &tot);
     if (j < nv) {
-      const uint32_t off = ex & 0xFFFFu;
       hval[s] = (off << 16) | len;
       for (uint32_t t = 0; t < len; ++t) lists[off + t] = kEmpty;
     }
-    my_rec_off[q] = ex >> 16;
-    run += tot;
+    run_lists += tot;
     __syncthreads();  // warp_sums is reused by the next chunk
   }
-  const uint32_t run_rec = run >> 16;
   if (tid == 0) {
-    s_rec_base = atomicAdd(&ctl[w.nb + kCtlRec], run_rec);
-    s_dir_base = atomicAdd(&ctl[w.nb + kCtlDir], (uint32_t)nv);
+    s_list_base = atomicAdd(&ctl[w.nb + kCtlList], run_lists);
+    s_cell_base = atomicAdd(&ctl[w.nb + kCtlCell], (uint32_t)nv);
   }
   __syncthreads();
 
@@ -259,164 +260,163 @@ hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
   }
   __syncthreads();
 
-  // emit records + directory entries and flag first points
-  const uint32_t rec_base = s_rec_base, dir_base = s_dir_base;
-  if (rec_base + run_rec > w.rec_words || dir_base + (uint32_t)nv > w.dir_cap) {
-    if (tid == 0) ctl[w.nb + kCtlOverflow] = 1u;  // cannot happen: arenas are sized for n points
+  // emit: the CTA's lists are contiguous in shared memory in claim order, so the list arena gets
+  // one coalesced copy; every cell becomes one 16-byte record; first points are flagged
+  const uint32_t list_base = s_list_base, cell_base = s_cell_base;
+  if (list_base + run_lists > w.arena_cap || cell_base + (uint32_t)nv > w.arena_cap) {
+    if (tid == 0) ctl[w.nb + kCtlOverflow] = 1u;  // cannot happen: arenas hold one entry per point
     return;
   }
-  uint32_t* __restrict__ rec = w.rec(f);
-  uint2* __restrict__ dir = w.dir(f);
+  uint32_t* __restrict__ glst = w.lst(f) + list_base;
+  for (uint32_t i = tid; i < run_lists; i += kBucketThreads) glst[i] = lists[i];
+  Cell* __restrict__ cells = w.cells(f) + cell_base;
   uint32_t* __restrict__ bitmask = w.bitmask(f);
-#pragma unroll
-  for (int q = 0; q < kMaxCap / kBucketThreads; ++q) {
-    const int j = q * kBucketThreads + tid;
-    if (j >= nv) break;
+  for (int j = tid; j < nv; j += kBucketThreads) {
     const int s = slotlist[j];
     const uint32_t hv = hval[s];
-    const uint32_t len = hv & 0xFFFFu;  // >= 1: every claimed cell has a point and pe >= 1
-    const uint32_t* lst = lists + (hv >> 16);
-    const uint32_t off = rec_base + my_rec_off[q];
-    uint32_t* r = rec + off;
-    r[0] = hkey[s];
-    r[1] = len;
-    for (uint32_t t = 0; t < len; ++t) r[2 + t] = lst[t];
-    const uint32_t first = lst[0];  // lists are ascending: entry 0 is the cell's first point
-    dir[dir_base + j] = make_uint2(off, first);
-    atomicOr(&bitmask[first >> 5], 1u << (first & 31));
+    const uint32_t off = hv >> 16;
+    Cell cl;
+    cl.key = hkey[s];
+    cl.len = hv & 0xFFFFu;  // >= 1: every claimed cell has a point and pe >= 1
+    cl.list_off = list_base + off;
+    cl.first = lists[off];  // lists are ascending: entry 0 is the cell's first point
+    cells[j] = cl;
+    atomicOr(&bitmask[cl.first >> 5], 1u << (cl.first & 31));
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// D: voxel id of every cell; order[vid] = record offset
+// D: voxel id of every cell = rank of its first point; vcell[vid] = cell
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 hvb_order_kernel(const HvbWork w, const int max_voxels) {
   const int f = blockIdx.y;
   const uint32_t* ctl = w.ctl(f);
   if (ctl[w.nb + kCtlOverflow]) return;
-  const uint32_t ncell = min(ctl[w.nb + kCtlDir], w.dir_cap);
+  const uint32_t ncell = min(ctl[w.nb + kCtlCell], w.arena_cap);
   const uint32_t t = blockIdx.x * 256u + threadIdx.x;
   if (t >= ncell) return;
-  const uint2 d = w.dir(f)[t];
+  const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(w.cells(f)) + t);
   // wordprefix holds {bitmask word, exclusive prefix} pairs: one 8-byte random read per cell
-  const uint2 bp = reinterpret_cast<const uint2*>(w.prefix(f))[d.y >> 5];
-  const uint32_t vid = bp.y + __popc(bp.x & ((1u << (d.y & 31)) - 1u));
-  if (vid < (uint32_t)max_voxels) w.order(f)[vid] = d.x;  // voxelization_cpu.cpp:78
+  const uint2 bp = reinterpret_cast<const uint2*>(w.prefix(f))[raw.w >> 5];
+  const uint32_t vid = bp.y + __popc(bp.x & ((1u << (raw.w & 31)) - 1u));
+  if (vid < (uint32_t)max_voxels)  // voxelization_cpu.cpp:78
+    reinterpret_cast<uint4*>(w.vcell(f))[vid] = raw;
 }
 
 // ------------------------------------------------------------------------------------------
 // E: expansion in voxel-id order
 // ------------------------------------------------------------------------------------------
-// A warp owns 32 consecutive output rows (32 * C contiguous floats of the voxels buffer).  Lane l
-// first resolves the source point of row l (order -> record -> point index), then the warp moves
-// the 32 * C words in C fully coalesced store instructions: in iteration t lane l handles word
-// t * 32 + l of the chunk, i.e. column (word % C) of row (word / C), whose source index comes
-// from the owning lane by shuffle.  Gathers touch ~32 / C + 1 distinct point rows per instruction
-// instead of 32 (a per-thread row copy costs one L1 tag lookup per lane and column).
-constexpr int kExpThreads = 256;
-constexpr int kExpRowsPerWarp = 32;
-constexpr int kExpIters = 4;                                          // row groups per warp
-constexpr int kExpTile = (kExpThreads / 32) * kExpRowsPerWarp * kExpIters;  // rows per CTA
+// A warp owns tiles of VT consecutive voxels = VT * P * C contiguous output floats, staged in
+// shared memory: the stage is zeroed (that is the padding), every REAL row (slot < len) is
+// gathered into place -- C == 5 rows with two aligned 16-byte loads, C == 4 with one -- and the
+// tile leaves as one float4 stream.  Padding rows (two thirds of the C4 output) cost no loads and
+// a quarter of a store instruction per word.
+constexpr int kExpWarps = 4;
+constexpr int kExpThreads = kExpWarps * 32;
+constexpr int kExpTilesPerWarp = 2;
+constexpr int kExpStageWords = 1024;  // per warp (a 32-voxel C4 tile is 800 words)
+
+template <int C>
+__device__ __forceinline__ void stage_row(const float* __restrict__ pts, uint32_t idx, int n, int c,
+                                          float* st, bool vec_ok) {
+  if (C == 4 && vec_ok) {
+    *reinterpret_cast<float4*>(st) = __ldg(reinterpret_cast<const float4*>(pts) + idx);
+  } else if (C == 5 && vec_ok && idx + 1u < (uint32_t)n) {
+    // words [5 idx, 5 idx + 5) lie inside the two aligned 16-byte chunks starting at word
+    // (5 idx) & ~3; idx + 1 < n keeps the second chunk inside the buffer
+    const uint32_t w0 = idx * 5u;
+    const float4* p4 = reinterpret_cast<const float4*>(pts) + (w0 >> 2);
+    const float4 a = __ldg(p4), b = __ldg(p4 + 1);
+    const uint32_t o = w0 & 3u;
+    const float r0 = a.x, r1 = a.y, r2 = a.z, r3 = a.w, r4 = b.x, r5 = b.y, r6 = b.z, r7 = b.w;
+    st[0] = o == 0 ? r0 : o == 1 ? r1 : o == 2 ? r2 : r3;
+    st[1] = o == 0 ? r1 : o == 1 ? r2 : o == 2 ? r3 : r4;
+    st[2] = o == 0 ? r2 : o == 1 ? r3 : o == 2 ? r4 : r5;
+    st[3] = o == 0 ? r3 : o == 1 ? r4 : o == 2 ? r5 : r6;
+    st[4] = o == 0 ? r4 : o == 1 ? r5 : o == 2 ? r6 : r7;
+  } else {
+    const float* __restrict__ src = pts + (size_t)idx * c;
+    for (int j = 0; j < c; ++j) st[j] = __ldg(src + j);
+  }
+}
+
+constexpr int kExpChunk = 8;  // list slots resolved per lane per round (loads in flight)
 
 template <int C>
 __global__ void __launch_bounds__(kExpThreads)
 hvb_expand_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
-                  const int c_rt, const int max_points, const int32_t* __restrict__ voxel_num) {
+                  const int c_rt, const int max_points, const int vt,
+                  const int32_t* __restrict__ voxel_num, const int vec_ok) {
+  extern __shared__ __align__(16) float stage_all[];
   const int f = blockIdx.y;
   if (w.ctl(f)[w.nb + kCtlOverflow]) return;
   const HvFrame& fr = batch.f[f];
   const int c = C > 0 ? C : c_rt;
   const int m = voxel_num[f];
-  const long long rows = (long long)m * max_points;
-  const long long r_base = (long long)blockIdx.x * kExpTile;
-  const uint32_t* __restrict__ rec = w.rec(f);
-  const uint32_t* __restrict__ order = w.order(f);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-
-  // coors + counts: one thread per voxel id
-#pragma unroll
-  for (int k = 0; k < kExpTile / kExpThreads; ++k) {
-    const long long v = r_base + k * kExpThreads + tid;
-    if (v < m) {
-      const uint32_t q = order[v];
-      decode_key(rec[q], g, fr.coors + (size_t)v * 3);
-      fr.num[v] = (int32_t)min(rec[q + 1], (uint32_t)max_points);
-    }
-  }
-  if (r_base >= rows) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tile_words = vt * max_points * c;
+  float* stage = stage_all + (size_t)wid * kExpStageWords;
+  const Cell* __restrict__ vcell = w.vcell(f);
+  const uint32_t* __restrict__ lst = w.lst(f);
   const float* __restrict__ pts = fr.pts;
-  // Three phases with all kExpIters row groups of the warp in flight in each, so that the
-  // dependent chain order -> record -> point row costs three memory latencies per warp, not
-  // three per row group.
-  uint32_t q[kExpIters], s[kExpIters], src[kExpIters];
-  long long wr0[kExpIters];
-#pragma unroll
-  for (int it = 0; it < kExpIters; ++it) {
-    wr0[it] = r_base + ((long long)(it * (kExpThreads / 32) + wid)) * kExpRowsPerWarp;
-    const long long r = wr0[it] + lane;
-    q[it] = kEmpty;
-    s[it] = 0;
-    if (r < rows) {
-      const uint32_t vid = (uint32_t)r / (uint32_t)max_points;  // rows < 2^31 (checked by the plan)
-      s[it] = (uint32_t)r - vid * (uint32_t)max_points;
-      q[it] = order[vid];
+  // lane -> (voxel of the tile, slot group): vt voxels x (32 / vt) lanes each; a lane handles
+  // slots sg, sg + 32/vt, ... of its voxel.  vt == 32: one lane per voxel, all its slots.
+  const int v = lane & (vt - 1);
+  const int sg = lane / vt;
+  const int sstep = 32 / vt;
+
+#pragma unroll 1
+  for (int it = 0; it < kExpTilesPerWarp; ++it) {
+    const int v0 = ((blockIdx.x * kExpWarps + wid) * kExpTilesPerWarp + it) * vt;
+    if (v0 >= m) break;  // warp-uniform
+    const int nvox = min(vt, m - v0);
+    uint4 cl = make_uint4(0u, 0u, 0u, 0u);  // key, len, list_off, first
+    if (v < nvox) cl = __ldg(reinterpret_cast<const uint4*>(vcell) + (v0 + v));
+    // the zero padding (overlaps the latency of the cell load)
+    for (int i = lane; i < (tile_words + 3) / 4; i += 32)
+      reinterpret_cast<float4*>(stage)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    const uint32_t len = min(cl.y, (uint32_t)max_points);
+    if (v < nvox && sg == 0) {
+      decode_key(cl.x, g, fr.coors + (size_t)(v0 + v) * 3);
+      fr.num[v0 + v] = (int32_t)len;
     }
-  }
+    float* vstage = stage + (size_t)v * max_points * c;
+    for (uint32_t s0 = sg; s0 < len; s0 += kExpChunk * sstep) {
+      uint32_t idx[kExpChunk];
 #pragma unroll
-  for (int it = 0; it < kExpIters; ++it) {
-    src[it] = kEmpty;  // point index feeding the row, kEmpty = zero padding
-    if (q[it] != kEmpty) {
-      // both loads are issued together; the arena has max_points words of slack behind the
-      // last record, so reading the list entry before knowing the length stays in bounds
-      const uint32_t len = rec[q[it] + 1];
-      const uint32_t idx = rec[q[it] + 2 + s[it]];
-      if (s[it] < len) src[it] = idx;
-    }
-  }
-  float v[kExpIters][C > 0 ? C : 1];
-  if (C > 0) {
+      for (int j = 0; j < kExpChunk; ++j) {  // all list loads of the round are issued together
+        const uint32_t s = s0 + j * sstep;
+        idx[j] = s < len ? __ldg(lst + cl.z + s) : kEmpty;
+      }
 #pragma unroll
-    for (int it = 0; it < kExpIters; ++it) {
-#pragma unroll
-      for (int k = 0; k < C; ++k) {
-        const int t = k * 32 + lane;
-        const int row = t / C;
-        const int col = t - row * C;
-        const uint32_t sidx = __shfl_sync(0xFFFFFFFFu, src[it], row);
-        v[it][k] = (sidx != kEmpty) ? __ldg(pts + (size_t)sidx * C + col) : 0.0f;
+      for (int j = 0; j < kExpChunk; ++j) {
+        const uint32_t s = s0 + j * sstep;
+        if (idx[j] != kEmpty) stage_row<C>(pts, idx[j], fr.n, c, vstage + (size_t)s * c, vec_ok != 0);
       }
     }
-#pragma unroll
-    for (int it = 0; it < kExpIters; ++it) {
-      if (wr0[it] >= rows) break;  // warp-uniform
-      const int nwords = (int)min((long long)kExpRowsPerWarp, rows - wr0[it]) * C;
-      float* __restrict__ dst = fr.voxels + (size_t)wr0[it] * C;
-#pragma unroll
-      for (int k = 0; k < C; ++k) {
-        const int t = k * 32 + lane;
-        if (t < nwords) __stcs(dst + t, v[it][k]);
-      }
+    __syncwarp();
+    const size_t w0 = (size_t)v0 * max_points * c;
+    float* __restrict__ dst = fr.voxels + w0;
+    const int nwords = nvox * max_points * c;
+    if (vec_ok && (w0 & 3) == 0) {
+      const int n4 = nwords >> 2;
+      for (int i = lane; i < n4; i += 32)
+        __stcs(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(stage)[i]);
+      for (int i = (n4 << 2) + lane; i < nwords; i += 32) dst[i] = stage[i];
+    } else {
+      for (int i = lane; i < nwords; i += 32) dst[i] = stage[i];
     }
-  } else {
-    for (int it = 0; it < kExpIters; ++it) {
-      if (wr0[it] >= rows) break;  // warp-uniform
-      const int nwords = (int)min((long long)kExpRowsPerWarp, rows - wr0[it]) * c;
-      float* __restrict__ dst = fr.voxels + (size_t)wr0[it] * c;
-      for (int t = lane; t < kExpRowsPerWarp * c; t += 32) {  // warp-uniform trip count
-        const int row = t / c;
-        const int col = t - row * c;
-        const uint32_t sidx = __shfl_sync(0xFFFFFFFFu, src[it], row & 31);
-        if (t < nwords) __stcs(dst + t, (sidx != kEmpty) ? __ldg(pts + (size_t)sidx * c + col) : 0.0f);
-      }
-    }
+    __syncwarp();
   }
 }
 
 template <int C>
 int launch_expand(dim3 grid, cudaStream_t st, const HvBatch& b, const HvbWork& w,
-                  const GridParams& g, int c, int p, const int32_t* vn) {
-  hvb_expand_kernel<C><<<grid, kExpThreads, 0, st>>>(b, w, g, c, p, vn);
+                  const GridParams& g, int c, int p, int vt, const int32_t* vn, int vec_ok) {
+  const size_t smem = (size_t)kExpWarps * kExpStageWords * sizeof(float);
+  hvb_expand_kernel<C><<<grid, kExpThreads, smem, st>>>(b, w, g, c, p, vt, vn, vec_ok);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
@@ -428,7 +428,6 @@ int launch_expand(dim3 grid, cudaStream_t st, const HvBatch& b, const HvbWork& w
 // ------------------------------------------------------------------------------------------
 int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], int max_points,
                   int max_voxels, HvBucketPlan* p) {
-  (void)c;
   int rc = hvg_make_plan(n_max, vs, rg, max_points, max_voxels, &p->slow);
   if (rc != PCFE_OK) return rc;
   if (max_points > 0xFFFF) return PCFE_ERR_CAPS;  // list length is packed into 16 bits
@@ -453,53 +452,96 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   p->log2_slots = ls;
   p->slots = 1 << ls;
   if (p->log2_nb + p->log2_slots > 32) return PCFE_ERR_TOO_LARGE;
-  // arenas: every cell needs 2 + len words, sum(len) <= n, cells <= n  ->  3 * npad words
-  p->rec_words = (size_t)3 * (size_t)p->npad;
+  // arenas: one list entry per point at most, one cell per point at most
   p->ent_b = align256((size_t)p->nb * (size_t)p->cap * sizeof(uint2));
-  p->rec_b = align256((p->rec_words + (size_t)std::max(max_points, 1) + 8) * sizeof(uint32_t));  // + read slack
-  p->dir_b = align256((size_t)p->npad * sizeof(uint2));
+  p->lst_b = align256((size_t)p->npad * sizeof(uint32_t));
+  p->cells_b = align256((size_t)p->npad * sizeof(Cell));
   const size_t vmax = (size_t)std::min<int64_t>(max_voxels, std::max<int64_t>(n_max, 1));
-  p->order_b = align256(std::max<size_t>(vmax, 1) * sizeof(uint32_t));
+  p->vcell_b = align256(std::max<size_t>(vmax, 1) * sizeof(Cell));
   p->word_b = align256((size_t)p->words * sizeof(uint32_t));
   p->cnt_b = align256((size_t)(p->nb + 4) * sizeof(uint32_t));
-  const size_t fast = p->ent_b + p->rec_b + p->dir_b + p->order_b;
+  const size_t fast = p->ent_b + p->lst_b + p->cells_b + p->vcell_b;
   // the fallback reuses the frame's own region as table | lists | pslot
   const size_t slow = p->slow.table_b + p->slow.list_b + p->slow.pslot_b;
   p->region_b = std::max(fast, slow);
   p->per_frame = p->region_b + 3 * p->word_b + p->cnt_b;  // bitmask + {bits, prefix} pairs
+  // expansion tile: voxels per warp such that a tile fits the per-warp stage
+  if ((int64_t)std::max(max_points, 1) * c > kExpStageWords) return PCFE_ERR_TOO_LARGE;
+  p->exp_vt = 32;
+  while (p->exp_vt > 1 && (int64_t)p->exp_vt * std::max(max_points, 1) * c > kExpStageWords) p->exp_vt >>= 1;
   p->smem_bucket = (size_t)(2 * p->slots + 2 * p->cap) * 4 + (size_t)(2 * p->cap) * 2;
+  return PCFE_OK;
+}
+
+// Two auxiliary streams per device so that consecutive waves overlap: the bucket kernel is bound
+// by shared-memory atomics, bin/expand by DRAM, so wave k+1's grouping hides under wave k's
+// expansion.  Forked from / joined to the caller's stream with events; the caller sees plain
+// stream-ordered semantics.
+struct AuxStreams {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+};
+static AuxStreams g_aux[64];
+static std::mutex g_aux_mu;
+
+static int get_aux(int device, AuxStreams** out) {
+  if (device < 0 || device >= 64) return PCFE_ERR_DEVICE;
+  AuxStreams& a = g_aux[device];
+  if (!a.fork) {
+    for (int k = 0; k < 2; ++k) {
+      PCFE_CUDA_TRY(cudaStreamCreateWithFlags(&a.s[k], cudaStreamNonBlocking));
+      PCFE_CUDA_TRY(cudaEventCreateWithFlags(&a.join[k], cudaEventDisableTiming));
+    }
+    PCFE_CUDA_TRY(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+  }
+  *out = &a;
   return PCFE_OK;
 }
 
 int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPlan& p,
             int max_points, int max_voxels, int32_t* voxel_num, void* workspace, int wave,
-            cudaStream_t st) {
-  // scratch layout per wave: [frame regions] x wave | [bitmask | ctl] x wave (zeroed per wave) |
-  // [wordprefix] x wave
-  char* base = (char*)workspace;
+            int nbuf, int device, cudaStream_t user_st) {
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  const int nwaves = (num_frames + wave - 1) / wave;
+  const bool overlap = nbuf >= 2 && nwaves >= 2;
+  AuxStreams* aux = nullptr;
+  if (overlap) {
+    int rc = get_aux(device, &aux);
+    if (rc != PCFE_OK) return rc;
+    PCFE_CUDA_TRY(cudaEventRecord(aux->fork, user_st));
+    for (int k = 0; k < 2; ++k) PCFE_CUDA_TRY(cudaStreamWaitEvent(aux->s[k], aux->fork, 0));
+  }
+  // scratch layout per wave buffer: [frame regions] x wave | [bitmask | ctl] x wave (zeroed per
+  // wave) | [wordprefix pairs] x wave
+  const size_t buf_bytes = (size_t)wave * p.per_frame;
   HvbWork w;
-  w.region = base;
   w.region_stride = p.region_b;
-  w.rec_off = p.ent_b;
-  w.dir_off = p.ent_b + p.rec_b;
-  w.order_off = p.ent_b + p.rec_b + p.dir_b;
-  char* zero_base = base + (size_t)wave * p.region_b;
+  w.lst_off = p.ent_b;
+  w.cells_off = p.ent_b + p.lst_b;
+  w.vcell_off = p.ent_b + p.lst_b + p.cells_b;
   const size_t zero_per = p.word_b + p.cnt_b;
-  w.zero = (uint32_t*)zero_base;
   w.zero_stride = zero_per / sizeof(uint32_t);
   w.ctl_off = p.word_b / sizeof(uint32_t);
-  w.wordprefix = (uint32_t*)(zero_base + (size_t)wave * zero_per);
   w.word_stride = 2 * p.word_b / sizeof(uint32_t);
   w.nb = p.nb; w.log2_nb = p.log2_nb; w.cap = p.cap; w.slots = p.slots; w.log2_slots = p.log2_slots;
-  w.rec_words = (uint32_t)p.rec_words;
-  w.dir_cap = (uint32_t)p.npad;
+  w.arena_cap = (uint32_t)p.npad;
 
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)p.smem_bucket));
   const int pe = std::max(max_points, 1);
+  int vec_ok = 1;  // float4 tile stream / vector row loads need 16-byte aligned buffers
+  for (int k = 0; k < num_frames && vec_ok; ++k)
+    vec_ok = !(((uintptr_t)frames[k].voxels & 15) || ((uintptr_t)frames[k].points & 15));
 
-  for (int f0 = 0; f0 < num_frames; f0 += wave) {
+  int wave_idx = 0;
+  for (int f0 = 0; f0 < num_frames; f0 += wave, ++wave_idx) {
     const int wv = std::min(wave, num_frames - f0);
+    cudaStream_t st = overlap ? aux->s[wave_idx & 1] : user_st;
+    char* base = (char*)workspace + (overlap ? (size_t)(wave_idx & 1) * buf_bytes : 0);
+    char* zero_base = base + (size_t)wave * p.region_b;
+    w.region = base;
+    w.zero = (uint32_t*)zero_base;
+    w.wordprefix = (uint32_t*)(zero_base + (size_t)wave * zero_per);
     HvBatch b;
     int64_t wn_max = 0;
     for (int k = 0; k < wv; ++k) {
@@ -536,13 +578,13 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     }
     {
       ProfScope ps("hvb_expand", st);
-      const int64_t vmax = std::min<int64_t>(max_voxels, wn_max);
-      const int64_t rows = std::max<int64_t>(vmax * std::max(max_points, 1), 1);
-      const dim3 grid((unsigned)((rows + kExpTile - 1) / kExpTile), (unsigned)wv);
+      const int64_t vmax = std::max<int64_t>(std::min<int64_t>(max_voxels, wn_max), 1);
+      const int per_cta = kExpWarps * kExpTilesPerWarp * p.exp_vt;
+      const dim3 grid((unsigned)((vmax + per_cta - 1) / per_cta), (unsigned)wv);
       const int32_t* vn = voxel_num + f0;
-      if (c == 4) rc = launch_expand<4>(grid, st, b, w, p.g, c, max_points, vn);
-      else if (c == 5) rc = launch_expand<5>(grid, st, b, w, p.g, c, max_points, vn);
-      else rc = launch_expand<0>(grid, st, b, w, p.g, c, max_points, vn);
+      if (c == 4) rc = launch_expand<4>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
+      else if (c == 5) rc = launch_expand<5>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
+      else rc = launch_expand<0>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
       if (rc != PCFE_OK) return rc;
     }
     rc = hvg_launch_slow(b, wv, w.zero + w.ctl_off + p.nb + kCtlOverflow, w.zero_stride,
@@ -550,6 +592,12 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
                          w.zero_stride, w.wordprefix, w.word_stride, c, max_points, max_voxels,
                          voxel_num + f0, st);
     if (rc != PCFE_OK) return rc;
+  }
+  if (overlap) {
+    for (int k = 0; k < 2; ++k) {
+      PCFE_CUDA_TRY(cudaEventRecord(aux->join[k], aux->s[k]));
+      PCFE_CUDA_TRY(cudaStreamWaitEvent(user_st, aux->join[k], 0));
+    }
   }
   return PCFE_OK;
 }

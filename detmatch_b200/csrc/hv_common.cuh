@@ -130,20 +130,23 @@ struct HvBucketPlan {
   int nb, log2_nb;        // buckets per frame
   int cap;                // entries per bucket region
   int slots, log2_slots;  // shared-memory hash slots per bucket
-  size_t rec_words;       // record arena per frame (words)
+  int exp_vt;             // voxels per warp tile of the expansion kernel
   // per-frame byte sizes (256-aligned)
-  size_t ent_b, rec_b, dir_b, order_b, word_b, cnt_b, region_b, per_frame;
+  size_t ent_b, lst_b, cells_b, vcell_b, word_b, cnt_b, region_b, per_frame;
   size_t smem_bucket;     // dynamic shared memory of the bucket kernel
   // the overflow fallback (single CTA per frame) reuses the frame's own scratch region
   HvGlobalPlan slow;
 };
 int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], int max_points,
                   int max_voxels, HvBucketPlan* p);
+// `nbuf` (1 or 2) wave buffers of wave * p.per_frame bytes each are available in `workspace`;
+// with 2 buffers and >= 2 waves consecutive waves overlap on two internal streams.
 int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPlan& p,
             int max_points, int max_voxels, int32_t* voxel_num, void* workspace, int wave,
-            cudaStream_t st);
+            int nbuf, int device, cudaStream_t st);
 
 extern int g_opt_hv_path;         // 0 auto, 1 force global path, 2 force bucket path
+extern int g_opt_hv_wave;         // frames per wave (0 = automatic)
 extern int g_opt_force_overflow;  // 1: bucket path treats every frame as overflowed (tests)
 
 }  // namespace pcfe

@@ -44,6 +44,7 @@ void prof_end(cudaStream_t st) {
 
 int g_opt_hv_path = 0;
 int g_opt_force_overflow = 0;
+int g_opt_hv_wave = 0;
 extern int g_opt_bucket_avg;
 
 namespace {
@@ -113,9 +114,15 @@ int choose_path(int64_t n_max, int c, const float vs[3], const float rg[6], int 
   return PCFE_OK;
 }
 
-int auto_wave(size_t per_frame, int num_frames) {
+// Frames per wave.  Measured on B200 (C4): one 64-frame wave 0.66 ms; launch gaps make many
+// small waves slower (wave 8: 1.05 ms).  Overlapping two 32-frame waves on two streams gains
+// only ~1 % (every kernel already fills the SMs), so overlap is used only when a batch needs
+// more than one wave anyway.
+int auto_wave(size_t per_frame, int num_frames, bool bucket) {
+  if (g_opt_hv_wave > 0) return std::min(std::min(g_opt_hv_wave, kMaxWave), std::max(num_frames, 1));
   size_t w = kL2ScratchBudget / per_frame;
   w = std::max<size_t>(1, std::min<size_t>(w, (size_t)kMaxWave));
+  (void)bucket;
   return (int)std::min<size_t>(w, (size_t)std::max(num_frames, 1));
 }
 
@@ -183,9 +190,10 @@ extern "C" size_t pcfe_hard_voxelize_workspace_bytes(int64_t n_max, int num_fram
   if (choose_path(n_max, 4, vs, rg, max_points, max_voxels, &ch) != PCFE_OK) return 0;
   // sized for whichever path needs more, so a later pcfe_debug_set cannot invalidate it
   const size_t per = std::max(ch.per_frame, ch.gp.per_frame);
-  int w = frames_in_flight > 0 ? std::min(frames_in_flight, kMaxWave) : auto_wave(per, num_frames);
+  int w = frames_in_flight > 0 ? std::min(frames_in_flight, kMaxWave) : auto_wave(per, num_frames, ch.bucket);
   w = std::min(w, std::max(num_frames, 1));
-  return (size_t)w * per;
+  const int nbuf = (ch.bucket && num_frames > w) ? 2 : 1;  // double-buffered waves overlap
+  return (size_t)w * per * nbuf;
 }
 
 extern "C" int pcfe_hard_voxelize_batch_f32(const pcfe_frame_t* frames, int num_frames, int c,
@@ -222,10 +230,17 @@ extern "C" int pcfe_hard_voxelize_batch_f32(const pcfe_frame_t* frames, int num_
   }
   if (!workspace) return PCFE_ERR_NULL;
   if ((uintptr_t)workspace & 255) return PCFE_ERR_ALIGN;
-  const int wave = (int)std::min<size_t>(std::min(kMaxWave, num_frames), workspace_bytes / ch.per_frame);
-  if (wave < 1) return PCFE_ERR_WORKSPACE;
+  const size_t fit = workspace_bytes / ch.per_frame;  // frames whose scratch fits
+  if (fit < 1) return PCFE_ERR_WORKSPACE;
+  int wave = auto_wave(ch.per_frame, num_frames, ch.bucket);
+  int nbuf = (ch.bucket && num_frames > wave && fit >= 2 * (size_t)wave) ? 2 : 1;
+  if ((size_t)wave * nbuf > fit) {  // smaller workspace than recommended: single buffer, smaller waves
+    nbuf = 1;
+    wave = (int)std::min<size_t>(wave, fit);
+  }
   if (ch.bucket)
-    return hvb_run(frames, num_frames, c, ch.bp, max_points, max_voxels, voxel_num, workspace, wave, st);
+    return hvb_run(frames, num_frames, c, ch.bp, max_points, max_voxels, voxel_num, workspace, wave,
+                   nbuf, device, st);
   return hvg_run(frames, num_frames, c, ch.gp, max_points, max_voxels, voxel_num, workspace, wave, st);
 }
 
@@ -247,6 +262,7 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   if (!strcmp(name, "hv_path")) g_opt_hv_path = value;
   else if (!strcmp(name, "hv_force_overflow")) g_opt_force_overflow = value;
   else if (!strcmp(name, "hv_bucket_avg")) g_opt_bucket_avg = value;
+  else if (!strcmp(name, "hv_wave")) g_opt_hv_wave = value;
   else return PCFE_ERR_SHAPE;
   return PCFE_OK;
 }

@@ -49,9 +49,11 @@ def test_workspace_sizing(lib):
     vs, rg = _cabi.f3([0.1, 0.1, 0.15]), _cabi.f6([-75.2, -75.2, -2, 75.2, 75.2, 4])
     one = lib.pcfe_hard_voxelize_workspace_bytes(180000, 1, 1, vs, rg, 5, 150000)
     assert one > 0 and one % 256 == 0
-    assert lib.pcfe_hard_voxelize_workspace_bytes(180000, 64, 4, vs, rg, 5, 150000) == 4 * one
+    # more frames than one wave: two wave buffers so that consecutive waves can overlap
+    assert lib.pcfe_hard_voxelize_workspace_bytes(180000, 64, 4, vs, rg, 5, 150000) == 2 * 4 * one
+    assert lib.pcfe_hard_voxelize_workspace_bytes(180000, 4, 4, vs, rg, 5, 150000) == 4 * one
     auto = lib.pcfe_hard_voxelize_workspace_bytes(180000, 64, 0, vs, rg, 5, 150000)
-    assert auto % one == 0 and one <= auto <= 64 * one
+    assert auto % one == 0 and one <= auto <= 2 * 64 * one
     # empty grid -> 0 (error)
     assert lib.pcfe_hard_voxelize_workspace_bytes(10, 1, 1, vs, _cabi.f6([0, 0, 0, 0, 0, 0]), 5, 10) == 0
     assert lib.pcfe_points_in_boxes_workspace_bytes(16, 200) == 16 * 200 * 32
