@@ -26,6 +26,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = "C4"
+# DRAM traffic per 64-frame step from the committed ncu capture (profiles/r01_v3_ncu_summary.txt):
+# hvb_bin 292.6 MB + hvb_bucket 176.9 MB + hvb_order 146.1 MB + hvb_expand 1022.3 MB
+NCU_TRAFFIC_BYTES_PER_STEP = {"C4": 1_637_900_000}
+NCU_EXPAND_TRAFFIC = {"C4": 1_022_300_000}
+KEPT_POINTS_PER_FRAME = {"C4": 156_000}  # points surviving the max_points cap (oracle, seed 4000)
 METRIC = "hard_voxelize_throughput"
 UNIT = "Mpoints/s"
 
@@ -214,6 +219,26 @@ def _config_dict(cfg, args, frames_per_step):
 
 
 # --------------------------------------------------------------------------------------------
+# multi-GPU plumbing (no data-path collective: frames shard, only times are reduced)
+# --------------------------------------------------------------------------------------------
+def frame_seeds(cfg_index, rank, frames_per_rank):
+    """Global frame ids owned by `rank`: a contiguous block, disjoint across ranks."""
+    return [rank * frames_per_rank + k for k in range(frames_per_rank)]
+
+
+def max_over_ranks(value, device=None):
+    """MAX of a python float over all ranks (identity when not distributed).  Works with nccl
+    (device tensor) and gloo (CPU tensor)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -240,7 +265,8 @@ def run_ours(args):
         _cabi.debug_set("hv_bucket_avg", args.hv_bucket_avg)
 
     # synthetic frames, generated on the host; each rank has its own 64 frames
-    host = [synth.lidar_frame(N, C, synth.seed_for(cfg["index"], rank * F + k), cfg["r_max"]).pin_memory() for k in range(F)]
+    host = [synth.lidar_frame(N, C, synth.seed_for(cfg["index"], fid), cfg["r_max"]).pin_memory()
+            for fid in frame_seeds(cfg["index"], rank, F)]
     pts = [h.to(dev, non_blocking=True) for h in host]
     torch.cuda.synchronize(dev)
     plan = HardVoxelizeBatchPlan([N] * F, C, cfg["voxel_size"], cfg["point_cloud_range"], P, V, dev,
@@ -279,10 +305,7 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         clocks = sampler.stop()
         clocks["note"] = "timed region < sampling period; sampled during an identical untimed loop right after"
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = max_over_ranks(ms_total, dev) / args.steps
     total_points = world * F * N
     value = total_points / (ms_step * 1e-3) / 1e6
 
@@ -318,10 +341,24 @@ def run_ours(args):
     algo = algorithmic_bytes(N, C, P, m_list)  # one rank's step
     achieved = algo / (ms_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
-                "kernel": "hard-voxelize launch sequence (memset + K1..K5 per wave), per GPU",
-                "algorithmic_bytes_per_step": algo, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_BYTES_PER_STEP.get(args.workload),
+                "kernel": "hard-voxelize launch sequence per GPU (hvb_bin, hvb_bucket, hv_scan_flags, hvb_order, "
+                          "hvb_expand); achieved = algorithmic bytes of the step / CUDA-event step time",
+                "algorithmic_bytes_per_step": algo, "peak_source": peak_src + " (of measured)",
+                "traffic_source": "sum of dram__bytes_read+write over the step's kernels, ncu --set full, "
+                                  "profiles/r01_v3_ncu_summary.txt",
                 "mean_voxels_per_frame": round(sum(m_list) / len(m_list), 1)}
+    if kernels and "hvb_expand" in kernels:
+        # dominant kernel: writes every returned element once, reads the kept rows and the cell records
+        kept = KEPT_POINTS_PER_FRAME.get(args.workload)
+        m_tot = sum(m_list)
+        k_bytes = m_tot * (P * C * 4 + 16) + m_tot * 16 + (kept * F * (C * 4 + 4) if kept else 0)
+        k_ms = kernels["hvb_expand"]["ms_per_step"]
+        roofline["dominant_kernel"] = {"name": "hvb_expand", "ms_per_launch": k_ms,
+                                       "algorithmic_bytes_per_launch": k_bytes,
+                                       "achieved": round(k_bytes / (k_ms * 1e-3) / 1e9, 1),
+                                       "frac": round(k_bytes / (k_ms * 1e-3) / 1e9 / peak, 4),
+                                       "traffic": NCU_EXPAND_TRAFFIC.get(args.workload)}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -343,30 +380,59 @@ def run_ours(args):
 def run_e2e(args, cfg, plan, host, pts, dev, world, barrier):
     """Same metric through the public batched call with HOST buffers: every step copies the 64
     frames from pinned host memory to the device, voxelizes, reads voxel_num back and copies the
-    returned rows (voxels[:M], coors[:M], num_points[:M] of every frame) into pinned host memory."""
+    returned rows (voxels[:M], coors[:M], num_points[:M] of every frame) into pinned host memory.
+
+    The batch is cut into chunks of 8 frames on three streams (H2D, compute, D2H) so that the
+    upload of chunk i+1, the kernels of chunk i and the download of chunk i-1 overlap; the
+    device-to-host size of a chunk is only known once its voxel_num has reached the host, which
+    is the one host synchronisation per chunk."""
     import torch
-    import torch.distributed as dist
+    from detmatch_b200.ops.voxel import HardVoxelizeBatchPlan
     F, N, C = cfg["frames"], cfg["n"], cfg["c"]
     P, V = cfg["max_num_points"], cfg["max_voxels"]
+    CH = 8 if F % 8 == 0 else F
+    chunks = [list(range(i, i + CH)) for i in range(0, F, CH)]
+    plans = [HardVoxelizeBatchPlan([N] * CH, C, cfg["voxel_size"], cfg["point_cloud_range"], P, V, dev).bind(
+        [pts[k] for k in ch]) for ch in chunks]
     out_vox = torch.empty((F, V, P, C), dtype=torch.float32).pin_memory()
     out_coors = torch.empty((F, V, 3), dtype=torch.int32).pin_memory()
     out_num = torch.empty((F, V), dtype=torch.int32).pin_memory()
+    cnt_host = [torch.empty((CH,), dtype=torch.int32).pin_memory() for _ in chunks]
+    s_in, s_comp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     h2d = F * N * C * 4
 
     def step():
-        for k in range(F):
-            pts[k].copy_(host[k], non_blocking=True)
-        voxels, coors, num, vnum = plan.run()
-        counts = vnum.cpu().tolist()  # sync: the caller needs M to size what it reads
-        d2h = F * 4
-        for k, m in enumerate(counts):
-            out_vox[k, :m].copy_(voxels[k, :m], non_blocking=True)
-            out_coors[k, :m].copy_(coors[k, :m], non_blocking=True)
-            out_num[k, :m].copy_(num[k, :m], non_blocking=True)
-            d2h += m * (P * C * 4 + 16)
-        torch.cuda.synchronize(dev)
+        ev_c = []
+        for i, ch in enumerate(chunks):
+            with torch.cuda.stream(s_in):
+                for k in ch:
+                    pts[k].copy_(host[k], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            with torch.cuda.stream(s_comp):
+                s_comp.wait_event(ev_in)
+                plans[i].run()
+                cnt_host[i].copy_(plans[i].voxel_num, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_comp)
+                ev_c.append(ev)
+        d2h = 0
+        for i, ch in enumerate(chunks):
+            ev_c[i].synchronize()  # the caller needs M to size what it reads back
+            counts = cnt_host[i].tolist()
+            d2h += len(ch) * 4
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_c[i])
+                for j, k in enumerate(ch):
+                    m = counts[j]
+                    out_vox[k, :m].copy_(plans[i].voxels[j, :m], non_blocking=True)
+                    out_coors[k, :m].copy_(plans[i].coors[j, :m], non_blocking=True)
+                    out_num[k, :m].copy_(plans[i].num_points[j, :m], non_blocking=True)
+                    d2h += m * (P * C * 4 + 16)
+        s_out.synchronize()
         return d2h
 
+    torch.cuda.synchronize(dev)
     step()
     barrier()
     t0 = time.perf_counter()
@@ -374,14 +440,15 @@ def run_e2e(args, cfg, plan, host, pts, dev, world, barrier):
     for _ in range(args.e2e_steps):
         d2h = step()
     torch.cuda.synchronize(dev)
-    dt = (time.perf_counter() - t0) / args.e2e_steps
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps, dev)
+    # the downloaded rows are the device results (spot check, outside the timed region)
+    k = F - 1
+    m = int(cnt_host[-1][-1])
+    assert torch.equal(out_vox[k, :m], plans[-1].voxels[CH - 1, :m].cpu())
     return {"value": round(world * F * N / dt / 1e6, 1), "unit": UNIT, "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt * 1e3, 3), "steps": args.e2e_steps,
-            "api": "HardVoxelizeBatchPlan.run (pcfe_hard_voxelize_batch_f32) with pinned host in/out buffers"}
+            "api": "HardVoxelizeBatchPlan.run (pcfe_hard_voxelize_batch_f32), pinned host in/out buffers, "
+                   "8-frame chunks pipelined on H2D / compute / D2H streams"}
 
 
 def cpu_baseline_subprocess(args):

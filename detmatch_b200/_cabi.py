@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpcfe.so")
+# PCFE_LIB selects another build of the same library (kernel tuning experiments only)
+LIB_PATH = os.environ.get("PCFE_LIB") or os.path.join(_HERE, "lib", "libpcfe.so")
 
 _lib = None
 

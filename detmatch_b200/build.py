@@ -40,21 +40,27 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """`defines`/`out` build a tuning variant (e.g. defines=["PCFE_BUCKET_THREADS=128"],
+    out="lib/libpcfe_bt128.so"); the default build takes neither."""
+    target = os.path.join(HERE, out) if out else LIB
+    if not force and not out and not stale():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    cmd += ["-D" + d for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", target]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libpcfe.so")
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="-f" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[3:] for a in sys.argv[1:] if a.startswith("-o=")]
+    print(build(force="-f" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -164,7 +164,10 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
 // ------------------------------------------------------------------------------------------
 // B: one CTA per (frame, bucket), everything in shared memory
 // ------------------------------------------------------------------------------------------
-constexpr int kBucketThreads = 256;
+#ifndef PCFE_BUCKET_THREADS
+#define PCFE_BUCKET_THREADS 256
+#endif
+constexpr int kBucketThreads = PCFE_BUCKET_THREADS;
 constexpr int kMaxCap = 2048;  // entries per bucket (list offsets are packed into 16 bits)
 
 // dynamic shared memory (words): hkey[S] | hval[S] | eidx[cap] | lists[cap] | eslot[cap] (u16) |
@@ -312,9 +315,15 @@ hvb_order_kernel(const HvbWork w, const int max_voxels) {
 // gathered into place -- C == 5 rows with two aligned 16-byte loads, C == 4 with one -- and the
 // tile leaves as one float4 stream.  Padding rows (two thirds of the C4 output) cost no loads and
 // a quarter of a store instruction per word.
-constexpr int kExpWarps = 4;
+#ifndef PCFE_EXP_WARPS
+#define PCFE_EXP_WARPS 4
+#endif
+constexpr int kExpWarps = PCFE_EXP_WARPS;
 constexpr int kExpThreads = kExpWarps * 32;
-constexpr int kExpTilesPerWarp = 2;
+#ifndef PCFE_EXP_TILES
+#define PCFE_EXP_TILES 2
+#endif
+constexpr int kExpTilesPerWarp = PCFE_EXP_TILES;
 constexpr int kExpStageWords = 1024;  // per warp (a 32-voxel C4 tile is 800 words)
 
 template <int C>
@@ -322,6 +331,7 @@ __device__ __forceinline__ void stage_row(const float* __restrict__ pts, uint32_
                                           float* st, bool vec_ok) {
   if (C == 4 && vec_ok) {
     *reinterpret_cast<float4*>(st) = __ldg(reinterpret_cast<const float4*>(pts) + idx);
+#ifndef PCFE_EXP_SCALAR_ROWS
   } else if (C == 5 && vec_ok && idx + 1u < (uint32_t)n) {
     // words [5 idx, 5 idx + 5) lie inside the two aligned 16-byte chunks starting at word
     // (5 idx) & ~3; idx + 1 < n keeps the second chunk inside the buffer
@@ -335,13 +345,17 @@ __device__ __forceinline__ void stage_row(const float* __restrict__ pts, uint32_
     st[2] = o == 0 ? r2 : o == 1 ? r3 : o == 2 ? r4 : r5;
     st[3] = o == 0 ? r3 : o == 1 ? r4 : o == 2 ? r5 : r6;
     st[4] = o == 0 ? r4 : o == 1 ? r5 : o == 2 ? r6 : r7;
+#endif
   } else {
     const float* __restrict__ src = pts + (size_t)idx * c;
     for (int j = 0; j < c; ++j) st[j] = __ldg(src + j);
   }
 }
 
-constexpr int kExpChunk = 8;  // list slots resolved per lane per round (loads in flight)
+#ifndef PCFE_EXP_CHUNK
+#define PCFE_EXP_CHUNK 8
+#endif
+constexpr int kExpChunk = PCFE_EXP_CHUNK;  // list slots resolved per lane per round (loads in flight)
 
 template <int C>
 __global__ void __launch_bounds__(kExpThreads)
