@@ -1,0 +1,101 @@
+"""Device-time survey of every op on the five BASELINE configs (not the headline bench):
+python tests/native/bench_ops.py  -> one line per config with ms, GB/s algorithmic, % of HBM peak."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from detmatch_b200 import _cabi, synth  # noqa: E402
+from detmatch_b200.ops import points_in_boxes_batch, points_in_boxes_gpu  # noqa: E402
+from detmatch_b200.ops.roiaware_pool3d import roiaware_pool3d_ext  # noqa: E402
+from detmatch_b200.ops.voxel import HardVoxelizeBatchPlan  # noqa: E402
+from detmatch_b200._torch_glue import ptr, stream_ptr  # noqa: E402
+
+PEAK = 6549.1
+p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.exists(p):
+    PEAK = float(json.load(open(p))["hbm_gbs"])
+
+
+def timeit(fn, reps=30, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def report(name, ms, nbytes, units, unit_name):
+    gbs = nbytes / ms / 1e6
+    print(f"{name:44s} {ms:9.4f} ms  {units / ms / 1e3:10.1f} M{unit_name}/s  {gbs:8.1f} GB/s algorithmic  {gbs / PEAK:6.1%} of {PEAK:.0f}")
+
+
+def hard(name, frames=None):
+    cfg = synth.CONFIGS[name]
+    F = frames or cfg["frames"]
+    ci = int(name[1])
+    pts = [synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(ci, k), cfg["r_max"]).cuda() for k in range(F)]
+    plan = HardVoxelizeBatchPlan([cfg["n"]] * F, cfg["c"], cfg["voxel_size"], cfg["point_cloud_range"],
+                                 cfg["max_num_points"], cfg["max_voxels"], "cuda:0").bind(pts)
+    ms = timeit(plan.run)
+    m = plan.voxel_num.cpu().tolist()
+    nbytes = sum(cfg["n"] * cfg["c"] * 4 + mm * (cfg["max_num_points"] * cfg["c"] * 4 + 16) for mm in m)
+    report(f"{name} hard voxelize x{F} (M~{sum(m) // F})", ms, nbytes, F * cfg["n"], "pts")
+    _cabi.profile(True)
+    plan.run()
+    torch.cuda.synchronize()
+    rep = _cabi.profile_report()
+    _cabi.profile(False)
+    print("      ", {k: round(v[0], 4) for k, v in rep.items()})
+
+
+def dynamic():
+    cfg = synth.CONFIGS["C2"]
+    F = cfg["frames"]
+    pts = [synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(2, k), cfg["r_max"]).cuda() for k in range(F)]
+    coors = [torch.empty((cfg["n"], 3), dtype=torch.int32, device="cuda") for _ in range(F)]
+    L = _cabi.lib()
+    import ctypes
+    pp = (ctypes.c_void_p * F)(*[t.data_ptr() for t in pts])
+    cc = (ctypes.c_void_p * F)(*[t.data_ptr() for t in coors])
+    nn = (ctypes.c_int64 * F)(*[cfg["n"]] * F)
+    vs, rg = _cabi.f3(cfg["voxel_size"]), _cabi.f6(cfg["point_cloud_range"])
+    dev = torch.device("cuda:0")
+
+    def run():
+        _cabi.check(L.pcfe_dynamic_voxelize_batch_f32(pp, nn, F, cfg["c"], vs, rg, cc, 0, stream_ptr(dev)), "dyn")
+    ms = timeit(run)
+    report(f"C2 dynamic voxelize x{F} (one batched launch)", ms, F * cfg["n"] * (cfg["c"] * 4 + 12), F * cfg["n"], "pts")
+
+
+def pib():
+    c3 = synth.CONFIGS["C3"]
+    B, M, T = c3["frames"], c3["n"], c3["boxes"]
+    pts = torch.stack([synth.lidar_frame(M, 3, synth.seed_for(3, k), c3["r_max"]) for k in range(B)]).cuda()
+    bxs = torch.stack([synth.random_boxes(T, synth.seed_for(3, k) + 500, c3["point_cloud_range"]) for k in range(B)]).cuda()
+    out = torch.empty((B, M, T), dtype=torch.int32, device="cuda")
+    ms = timeit(lambda: roiaware_pool3d_ext.points_in_boxes_batch(bxs, pts, out))
+    report(f"C3 points_in_boxes_batch {B}x{M}x{T}", ms, B * M * T * 4 + B * M * 12 + B * T * 28, B * M * T, "pairs")
+    out2 = torch.empty((B, M), dtype=torch.int32, device="cuda")
+    ms = timeit(lambda: roiaware_pool3d_ext.points_in_boxes_gpu(bxs, pts, out2))
+    report(f"C3-shape points_in_boxes_gpu {B}x{M}x{T}", ms, B * M * 16 + B * T * 28, B * M * T, "pairs")
+    out3 = torch.empty((T, M), dtype=torch.int32, device="cuda")
+    ms = timeit(lambda: roiaware_pool3d_ext.points_in_boxes_cpu(bxs[0], pts[0], out3))
+    report(f"C3-shape points_in_boxes_cpu-layout 1x{M}x{T}", ms, M * T * 4 + M * 12, M * T, "pairs")
+
+
+if __name__ == "__main__":
+    torch.cuda.set_device(0)
+    hard("C1", 16)
+    dynamic()
+    pib()
+    hard("C4")
+    hard("C5", 16)
