@@ -67,7 +67,20 @@ __device__ __forceinline__ uint32_t list_peek(const uint32_t* p) {
 template <bool GLOBAL>
 __device__ __forceinline__ void sorted_insert(uint32_t* lst, const int p, uint32_t v) {
   if (list_peek<GLOBAL>(&lst[p - 1]) < v) return;  // list already full of smaller indices
-  for (int s = 0; s < p; ++s) {
+  int s = 0;
+  if (p > 8) {
+    // The list is ascending at every instant (an atomicMin at entry s is only issued by a thread
+    // that has seen smaller values in all entries before s), so the first entry that can take v
+    // is found by bisection; entries skipped hold values < v for good.
+    int lo = 0, hi = p - 1;  // lst[hi] >= v was just observed
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (list_peek<GLOBAL>(&lst[mid]) < v) lo = mid + 1;
+      else hi = mid;
+    }
+    s = lo;
+  }
+  for (; s < p; ++s) {
     if (list_peek<GLOBAL>(&lst[s]) < v) continue;  // monotone: a stale read is only conservative
     const uint32_t old = atomicMin(&lst[s], v);
     if (old == kEmpty) return;

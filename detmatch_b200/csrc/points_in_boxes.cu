@@ -147,7 +147,10 @@ __device__ __forceinline__ int in_box(float x, float y, float z, const PBox& b) 
   const float sy = __fsub_rn(y, b.cy);
   const float lx = __fadd_rn(__fmul_rn(sx, b.cosa), __fmul_rn(sy, -b.sina));
   const float ly = __fadd_rn(__fmul_rn(sx, b.sina), __fmul_rn(sy, b.cosa));
-  const bool in = (lx > -b.hl) & (lx < b.hl) & (ly > -b.hw) & (ly < b.hw);
+  // (lx > -hl) & (lx < hl)  <=>  |lx| < hl for every hl (negative, zero, Inf and NaN included:
+  // both forms are false whenever hl <= 0 or anything is NaN, and |+-Inf| < Inf is false like
+  // the two one-sided tests)
+  const bool in = (fabsf(lx) < b.hl) & (fabsf(ly) < b.hw);
   return (in & !z_out) ? 1 : 0;
 }
 
