@@ -44,6 +44,7 @@ int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size
                     int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st);
 
 int g_opt_bucket_avg = 1024;  // target points per bucket (tunable through pcfe_debug_set)
+int g_opt_bucket_variant = 0;  // 1: always use the general (count + atomicMin lists) bucket kernel
 
 namespace {
 
@@ -289,6 +290,124 @@ hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
 }
 
 // ------------------------------------------------------------------------------------------
+// B': the same job for P <= PT (PT = 5 or 8): cells keep their points in a linked list built with
+// one shared-memory atomicExch per entry; then one thread per cell walks the chain and keeps the
+// P smallest point indices in sorted REGISTERS (branch-free min/max insertion), so there is no
+// count pass, no second pass over the entries and no list array in shared memory.  Lists go to
+// the arena straight from registers: consecutive cells write consecutive ranges.
+// dynamic shared memory (words): hkey[S] | head[S] | eidx[cap] | enext[cap] (u16) | slotlist[cap] (u16)
+// ------------------------------------------------------------------------------------------
+template <int PT>
+__global__ void __launch_bounds__(kBucketThreads)
+hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ uint32_t warp_sums[33];
+  __shared__ uint32_t s_nclaimed, s_list_base, s_cell_base;
+  constexpr uint32_t kNil = 0xFFFFu;
+
+  const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
+  uint32_t* ctl = w.ctl(f);
+  if (ctl[w.nb + kCtlOverflow]) return;
+  const int S = w.slots, cap = w.cap;
+  uint32_t* hkey = smem;
+  uint32_t* head = hkey + S;  // entry number of the most recently linked point of the cell
+  uint32_t* eidx = head + S;
+  uint16_t* enext = reinterpret_cast<uint16_t*>(eidx + cap);
+  uint16_t* slotlist = enext + cap;
+
+  const int ne = (int)min(ctl[b], (uint32_t)cap);
+  if (ne == 0) return;
+  {
+    uint4* k4 = reinterpret_cast<uint4*>(hkey);  // hkey and head are contiguous: 2 * S words
+    for (int s = tid; s < S / 2; s += kBucketThreads) k4[s] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+  }
+  if (tid == 0) s_nclaimed = 0u;
+  __syncthreads();
+
+  const uint2* __restrict__ ent = w.ent(f) + (size_t)b * cap;
+  const uint32_t smask = (uint32_t)S - 1u;
+  const int sshift = 32 - w.log2_nb - w.log2_slots;
+  for (int e = tid; e < ne; e += kBucketThreads) {
+    const uint2 en = __ldcs(&ent[e]);
+    uint32_t s = ((en.x * kGold) >> sshift) & smask;
+    while (true) {
+      uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&hkey[s]);
+      if (cur == en.x) break;
+      if (cur == kEmpty) {
+        cur = atomicCAS(&hkey[s], kEmpty, en.x);
+        if (cur == kEmpty) {
+          slotlist[atomicAdd(&s_nclaimed, 1u)] = (uint16_t)s;
+          break;
+        }
+        if (cur == en.x) break;
+      }
+      s = (s + 1u) & smask;
+    }
+    const uint32_t prev = atomicExch(&head[s], (uint32_t)e);
+    enext[e] = (uint16_t)(prev == kEmpty ? kNil : prev);
+    eidx[e] = en.y;
+  }
+  __syncthreads();
+
+  const int nv = (int)s_nclaimed;
+  uint32_t* __restrict__ glst = w.lst(f);
+  Cell* __restrict__ cells = w.cells(f);
+  uint32_t* __restrict__ bitmask = w.bitmask(f);
+#pragma unroll 1
+  for (int j0 = 0; j0 < nv; j0 += kBucketThreads) {
+    const int j = j0 + tid;
+    uint32_t sorted[PT];
+#pragma unroll
+    for (int t = 0; t < PT; ++t) sorted[t] = kEmpty;
+    uint32_t cnt = 0, key = 0;
+    if (j < nv) {
+      const int s = slotlist[j];
+      key = hkey[s];
+      uint32_t e = head[s];
+      while (e != kNil) {  // chain walk; the P smallest indices stay in registers, ascending
+        uint32_t v = eidx[e];
+        e = enext[e];
+        ++cnt;
+#pragma unroll
+        for (int t = 0; t < PT; ++t) {
+          const uint32_t lo = min(sorted[t], v);
+          v = max(sorted[t], v);
+          sorted[t] = lo;
+        }
+      }
+    }
+    const uint32_t len = min(cnt, (uint32_t)pe);
+    uint32_t tot;
+    const uint32_t off = block_exscan(len, warp_sums, &tot);
+    const int ncell = min(kBucketThreads, nv - j0);
+    if (tid == 0) {
+      s_list_base = atomicAdd(&ctl[w.nb + kCtlList], tot);
+      s_cell_base = atomicAdd(&ctl[w.nb + kCtlCell], (uint32_t)ncell);
+    }
+    __syncthreads();
+    const uint32_t list_base = s_list_base, cell_base = s_cell_base;
+    if (list_base + tot > w.arena_cap || cell_base + (uint32_t)ncell > w.arena_cap) {
+      if (tid == 0) ctl[w.nb + kCtlOverflow] = 1u;  // cannot happen: arenas hold one entry per point
+      return;
+    }
+    if (j < nv) {
+      const uint32_t lo = list_base + off;
+#pragma unroll
+      for (int t = 0; t < PT; ++t)
+        if ((uint32_t)t < len) glst[lo + t] = sorted[t];
+      Cell cl;
+      cl.key = key;
+      cl.len = len;
+      cl.list_off = lo;
+      cl.first = sorted[0];
+      cells[cell_base + tid] = cl;
+      atomicOr(&bitmask[sorted[0] >> 5], 1u << (sorted[0] & 31));
+    }
+    __syncthreads();  // s_list_base / warp_sums are reused by the next chunk
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // D: voxel id of every cell = rank of its first point; vcell[vid] = cell
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -426,6 +545,109 @@ hvb_expand_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const 
   }
 }
 
+// ---- P fixed at compile time (P = 5: KITTI / Waymo voxels): no loops, no zero-fill pass ----------
+// Lane = voxel.  The lane loads its cell record, then its PT list entries and the rows behind
+// them (all independent: up to 2 * PT 16-byte loads in flight per lane), and writes all PT * C
+// words of its voxel -- data or zeros -- into the warp's stage; the stage leaves as a float4
+// stream.  Key decoding uses host-computed reciprocals instead of two 32-bit divisions.
+struct KeyDecode {
+  uint32_t plane, gx;          // gx * gy, gx
+  uint32_t m_plane, m_gx;      // floor(2^32 / plane), floor(2^32 / gx)
+};
+
+__device__ __forceinline__ uint32_t div_small_err(uint32_t n, uint32_t d, uint32_t m) {
+  uint32_t q = __umulhi(n, m);  // true quotient - 2 <= q <= true quotient
+  uint32_t r = n - q * d;
+  if (r >= d) { ++q; r -= d; }
+  if (r >= d) { ++q; }
+  return q;
+}
+
+template <int C, int PT>
+__global__ void __launch_bounds__(kExpThreads)
+hvb_expand_fixed_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const KeyDecode kd,
+                        const int32_t* __restrict__ voxel_num, const int vec_ok) {
+  __shared__ __align__(16) float stage_all[kExpWarps * 32 * PT * C];
+  const int f = blockIdx.y;
+  if (w.ctl(f)[w.nb + kCtlOverflow]) return;
+  const HvFrame& fr = batch.f[f];
+  const int m = voxel_num[f];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* stage = stage_all + wid * (32 * PT * C);
+  const uint4* __restrict__ vcell = reinterpret_cast<const uint4*>(w.vcell(f));
+  const uint32_t* __restrict__ lst = w.lst(f);
+  const float* __restrict__ pts = fr.pts;
+  const uint32_t n = (uint32_t)fr.n;
+  float* st = stage + lane * (PT * C);
+
+#pragma unroll 1
+  for (int it = 0; it < kExpTilesPerWarp; ++it) {
+    const int v0 = ((blockIdx.x * kExpWarps + wid) * kExpTilesPerWarp + it) * 32;
+    if (v0 >= m) break;  // warp-uniform
+    const int nvox = min(32, m - v0);
+    uint4 cl = make_uint4(0u, 0u, 0u, 0u);  // key, len, list_off, first
+    if (lane < nvox) cl = __ldg(vcell + v0 + lane);
+    const uint32_t len = min(cl.y, (uint32_t)PT);
+    uint32_t idx[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) idx[j] = (uint32_t)j < len ? __ldg(lst + cl.z + j) : kEmpty;
+    if (lane < nvox) {
+      const uint32_t cz = div_small_err(cl.x, kd.plane, kd.m_plane);
+      const uint32_t rem = cl.x - cz * kd.plane;
+      const uint32_t cy = div_small_err(rem, kd.gx, kd.m_gx);
+      int32_t* co = fr.coors + (uint32_t)(v0 + lane) * 3u;
+      co[0] = (int32_t)cz;
+      co[1] = (int32_t)cy;
+      co[2] = (int32_t)(rem - cy * kd.gx);
+      fr.num[v0 + lane] = (int32_t)len;
+    }
+    float r[PT][C];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+#pragma unroll
+      for (int k = 0; k < C; ++k) r[j][k] = 0.0f;
+      if (idx[j] != kEmpty) {
+        if (C == 4 && vec_ok) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(pts) + idx[j]);
+          r[j][0] = a.x; r[j][1] = a.y; r[j][2] = a.z; r[j][3] = a.w;
+        } else if (C == 5 && vec_ok && idx[j] + 1u < n) {
+          const uint32_t w0 = idx[j] * 5u;
+          const float4* p4 = reinterpret_cast<const float4*>(pts) + (w0 >> 2);
+          const float4 a = __ldg(p4), b = __ldg(p4 + 1);
+          const uint32_t o = w0 & 3u;
+          // shift the 8 loaded words left by o in two conditional steps (by 1, then by 2)
+          const bool o1 = o & 1u, o2 = o & 2u;
+          const float t0 = o1 ? a.y : a.x, t1 = o1 ? a.z : a.y, t2 = o1 ? a.w : a.z, t3 = o1 ? b.x : a.w;
+          const float t4 = o1 ? b.y : b.x, t5 = o1 ? b.z : b.y, t6 = o1 ? b.w : b.z;
+          r[j][0] = o2 ? t2 : t0; r[j][1] = o2 ? t3 : t1; r[j][2] = o2 ? t4 : t2;
+          r[j][3 % C] = o2 ? t5 : t3; r[j][4 % C] = o2 ? t6 : t4;
+        } else {
+          const float* __restrict__ src = pts + (size_t)idx[j] * C;
+#pragma unroll
+          for (int k = 0; k < C; ++k) r[j][k] = __ldg(src + k);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PT; ++j)
+#pragma unroll
+      for (int k = 0; k < C; ++k) st[j * C + k] = r[j][k];
+    __syncwarp();
+    const uint32_t w0 = (uint32_t)v0 * (PT * C);
+    float* __restrict__ dst = fr.voxels + w0;
+    const int nwords = nvox * (PT * C);
+    if (vec_ok) {  // w0 % 4 == 0 because v0 % 32 == 0
+      const int n4 = nwords >> 2;
+      for (int i = lane; i < n4; i += 32)
+        __stcs(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(stage)[i]);
+      for (int i = (n4 << 2) + lane; i < nwords; i += 32) dst[i] = stage[i];
+    } else {
+      for (int i = lane; i < nwords; i += 32) dst[i] = stage[i];
+    }
+    __syncwarp();
+  }
+}
+
 template <int C>
 int launch_expand(dim3 grid, cudaStream_t st, const HvBatch& b, const HvbWork& w,
                   const GridParams& g, int c, int p, int vt, const int32_t* vn, int vec_ok) {
@@ -542,6 +764,10 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
 
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)p.smem_bucket));
+  PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)p.smem_bucket));
+  PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)p.smem_bucket));
   const int pe = std::max(max_points, 1);
   int vec_ok = 1;  // float4 tile stream / vector row loads need 16-byte aligned buffers
   for (int k = 0; k < num_frames && vec_ok; ++k)
@@ -578,7 +804,14 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     {
       ProfScope ps("hvb_bucket", st);
       const dim3 grid((unsigned)p.nb, (unsigned)wv);
-      hvb_bucket_kernel<<<grid, kBucketThreads, p.smem_bucket, st>>>(w, pe);
+      // chains are indexed with 16 bits (0xFFFF = end): cap <= kMaxCap = 2048 always fits
+      const size_t smem_small = (size_t)(2 * p.slots + p.cap) * 4 + (size_t)(2 * p.cap) * 2;
+      if (pe <= 5 && g_opt_bucket_variant != 1)
+        hvb_bucket_small_kernel<5><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
+      else if (pe <= 8 && g_opt_bucket_variant != 1)
+        hvb_bucket_small_kernel<8><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
+      else
+        hvb_bucket_kernel<<<grid, kBucketThreads, p.smem_bucket, st>>>(w, pe);
       PCFE_LAUNCH_CHECK();
     }
     int rc = hv_launch_scan(w.zero, w.zero_stride, w.wordprefix, w.word_stride, wnpad / 32,
@@ -596,7 +829,18 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       const int per_cta = kExpWarps * kExpTilesPerWarp * p.exp_vt;
       const dim3 grid((unsigned)((vmax + per_cta - 1) / per_cta), (unsigned)wv);
       const int32_t* vn = voxel_num + f0;
-      if (c == 4) rc = launch_expand<4>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
+      if (max_points == 5 && (c == 4 || c == 5) && max_voxels < (1 << 24)) {
+        KeyDecode kd;
+        kd.plane = (uint32_t)p.g.gx * (uint32_t)p.g.gy;
+        kd.gx = (uint32_t)p.g.gx;
+        kd.m_plane = (uint32_t)(0x100000000ull / kd.plane);
+        kd.m_gx = (uint32_t)(0x100000000ull / kd.gx);
+        const int per = kExpWarps * kExpTilesPerWarp * 32;
+        const dim3 fgrid((unsigned)((vmax + per - 1) / per), (unsigned)wv);
+        if (c == 4) hvb_expand_fixed_kernel<4, 5><<<fgrid, kExpThreads, 0, st>>>(b, w, kd, vn, vec_ok);
+        else hvb_expand_fixed_kernel<5, 5><<<fgrid, kExpThreads, 0, st>>>(b, w, kd, vn, vec_ok);
+        PCFE_LAUNCH_CHECK();
+      } else if (c == 4) rc = launch_expand<4>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
       else if (c == 5) rc = launch_expand<5>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
       else rc = launch_expand<0>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
       if (rc != PCFE_OK) return rc;

@@ -46,6 +46,7 @@ int g_opt_hv_path = 0;
 int g_opt_force_overflow = 0;
 int g_opt_hv_wave = 0;
 extern int g_opt_bucket_avg;
+extern int g_opt_bucket_variant;
 
 namespace {
 
@@ -263,6 +264,7 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_force_overflow")) g_opt_force_overflow = value;
   else if (!strcmp(name, "hv_bucket_avg")) g_opt_bucket_avg = value;
   else if (!strcmp(name, "hv_wave")) g_opt_hv_wave = value;
+  else if (!strcmp(name, "hv_bucket_variant")) g_opt_bucket_variant = value;
   else return PCFE_ERR_SHAPE;
   return PCFE_OK;
 }

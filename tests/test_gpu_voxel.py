@@ -15,18 +15,21 @@ pytestmark = pytest.mark.gpu
 KITTI = [0, -40, -3, 70.4, 40, 1]
 
 
-@pytest.fixture(autouse=True, params=["bucket", "global", "fallback"])
+@pytest.fixture(autouse=True, params=["bucket", "bucket_general", "global", "fallback"])
 def hv_mode(request):
-    """Every test runs against the three hard-voxelize implementations behind the one entry point:
-    the shared-memory bucket path (default), the global-memory path, and the bucket path with
-    every frame forced through its overflow fallback."""
+    """Every test runs against all hard-voxelize implementations behind the one entry point: the
+    shared-memory bucket path (default: register-sorted chains for P <= 8, atomicMin lists
+    otherwise), the bucket path with the general kernel forced, the global-memory path, and the
+    bucket path with every frame forced through its overflow fallback."""
     from detmatch_b200 import _cabi
     mode = request.param
-    _cabi.debug_set("hv_path", {"bucket": 0, "global": 1, "fallback": 0}[mode])
+    _cabi.debug_set("hv_path", 1 if mode == "global" else 0)
     _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
+    _cabi.debug_set("hv_bucket_variant", 1 if mode == "bucket_general" else 0)
     yield mode
     _cabi.debug_set("hv_path", 0)
     _cabi.debug_set("hv_force_overflow", 0)
+    _cabi.debug_set("hv_bucket_variant", 0)
 
 
 def _gpu_hard(pts, vs, rg, p, v):
