@@ -26,10 +26,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = "C4"
-# DRAM traffic per 64-frame step from the committed ncu capture (profiles/r01_v3_ncu_summary.txt):
-# hvb_bin 292.6 MB + hvb_bucket 176.9 MB + hvb_order 146.1 MB + hvb_expand 1022.3 MB
-NCU_TRAFFIC_BYTES_PER_STEP = {"C4": 1_637_900_000}
-NCU_EXPAND_TRAFFIC = {"C4": 1_022_300_000}
+# DRAM traffic per 64-frame step from the committed ncu capture (profiles/r01_v4_ncu_summary.txt):
+# hvb_bin 293.8 MB + hvb_bucket 177.7 MB + hv_scan 1.5 MB + hvb_order 147.0 MB + hvb_expand 1025.8 MB
+NCU_TRAFFIC_BYTES_PER_STEP = {"C4": 1_645_800_000}
+NCU_EXPAND_TRAFFIC = {"C4": 1_025_800_000}
 KEPT_POINTS_PER_FRAME = {"C4": 156_000}  # points surviving the max_points cap (oracle, seed 4000)
 METRIC = "hard_voxelize_throughput"
 UNIT = "Mpoints/s"
@@ -348,7 +348,7 @@ def run_ours(args):
                           "hvb_expand); achieved = algorithmic bytes of the step / CUDA-event step time",
                 "algorithmic_bytes_per_step": algo, "peak_source": peak_src + " (of measured)",
                 "traffic_source": "sum of dram__bytes_read+write over the step's kernels, ncu --set full, "
-                                  "profiles/r01_v3_ncu_summary.txt",
+                                  "profiles/r01_v4_ncu_summary.txt",
                 "mean_voxels_per_frame": round(sum(m_list) / len(m_list), 1)}
     if kernels and "hvb_expand" in kernels:
         # dominant kernel: writes every returned element once, reads the kept rows and the cell records

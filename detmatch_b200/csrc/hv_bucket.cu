@@ -81,8 +81,14 @@ constexpr int kCtlList = 0, kCtlCell = 1, kCtlOverflow = 2;
 // ------------------------------------------------------------------------------------------
 // A: partition points into hash buckets
 // ------------------------------------------------------------------------------------------
-constexpr int kBinThreads = 512;
-constexpr int kBinPerThread = 8;
+#ifndef PCFE_BIN_THREADS
+#define PCFE_BIN_THREADS 512
+#endif
+#ifndef PCFE_BIN_PER_THREAD
+#define PCFE_BIN_PER_THREAD 8
+#endif
+constexpr int kBinThreads = PCFE_BIN_THREADS;
+constexpr int kBinPerThread = PCFE_BIN_PER_THREAD;
 constexpr int kBinTile = kBinThreads * kBinPerThread;  // 4096 points
 constexpr int kMaxBuckets = 1024;
 
@@ -353,33 +359,43 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
   uint32_t* __restrict__ glst = w.lst(f);
   Cell* __restrict__ cells = w.cells(f);
   uint32_t* __restrict__ bitmask = w.bitmask(f);
+  // kCellsPerThread cells per thread and round (cells tid, tid + T, ...): a typical bucket
+  // (~370 cells) needs one round, i.e. one block scan and three barriers for the whole tail
+  constexpr int kCellsPerThread = 2;
 #pragma unroll 1
-  for (int j0 = 0; j0 < nv; j0 += kBucketThreads) {
-    const int j = j0 + tid;
-    uint32_t sorted[PT];
+  for (int j0 = 0; j0 < nv; j0 += kCellsPerThread * kBucketThreads) {
+    uint32_t sorted[kCellsPerThread][PT];
+    uint32_t key[kCellsPerThread], len[kCellsPerThread];
+    uint32_t mine = 0;
 #pragma unroll
-    for (int t = 0; t < PT; ++t) sorted[t] = kEmpty;
-    uint32_t cnt = 0, key = 0;
-    if (j < nv) {
-      const int s = slotlist[j];
-      key = hkey[s];
-      uint32_t e = head[s];
-      while (e != kNil) {  // chain walk; the P smallest indices stay in registers, ascending
-        uint32_t v = eidx[e];
-        e = enext[e];
-        ++cnt;
+    for (int u = 0; u < kCellsPerThread; ++u) {
+      const int j = j0 + u * kBucketThreads + tid;
 #pragma unroll
-        for (int t = 0; t < PT; ++t) {
-          const uint32_t lo = min(sorted[t], v);
-          v = max(sorted[t], v);
-          sorted[t] = lo;
+      for (int t = 0; t < PT; ++t) sorted[u][t] = kEmpty;
+      uint32_t cnt = 0;
+      key[u] = 0;
+      if (j < nv) {
+        const int s = slotlist[j];
+        key[u] = hkey[s];
+        uint32_t e = head[s];
+        while (e != kNil) {  // chain walk; the P smallest indices stay in registers, ascending
+          uint32_t v = eidx[e];
+          e = enext[e];
+          ++cnt;
+#pragma unroll
+          for (int t = 0; t < PT; ++t) {
+            const uint32_t lo = min(sorted[u][t], v);
+            v = max(sorted[u][t], v);
+            sorted[u][t] = lo;
+          }
         }
       }
+      len[u] = min(cnt, (uint32_t)pe);
+      mine += len[u];
     }
-    const uint32_t len = min(cnt, (uint32_t)pe);
     uint32_t tot;
-    const uint32_t off = block_exscan(len, warp_sums, &tot);
-    const int ncell = min(kBucketThreads, nv - j0);
+    uint32_t off = block_exscan(mine, warp_sums, &tot);
+    const int ncell = min(kCellsPerThread * kBucketThreads, nv - j0);
     if (tid == 0) {
       s_list_base = atomicAdd(&ctl[w.nb + kCtlList], tot);
       s_cell_base = atomicAdd(&ctl[w.nb + kCtlCell], (uint32_t)ncell);
@@ -390,20 +406,25 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
       if (tid == 0) ctl[w.nb + kCtlOverflow] = 1u;  // cannot happen: arenas hold one entry per point
       return;
     }
-    if (j < nv) {
-      const uint32_t lo = list_base + off;
 #pragma unroll
-      for (int t = 0; t < PT; ++t)
-        if ((uint32_t)t < len) glst[lo + t] = sorted[t];
-      Cell cl;
-      cl.key = key;
-      cl.len = len;
-      cl.list_off = lo;
-      cl.first = sorted[0];
-      cells[cell_base + tid] = cl;
-      atomicOr(&bitmask[sorted[0] >> 5], 1u << (sorted[0] & 31));
+    for (int u = 0; u < kCellsPerThread; ++u) {
+      const int jl = u * kBucketThreads + tid;  // cell number inside this round
+      if (j0 + jl < nv) {
+        const uint32_t lo = list_base + off;
+#pragma unroll
+        for (int t = 0; t < PT; ++t)
+          if ((uint32_t)t < len[u]) glst[lo + t] = sorted[u][t];
+        Cell cl;
+        cl.key = key[u];
+        cl.len = len[u];
+        cl.list_off = lo;
+        cl.first = sorted[u][0];
+        cells[cell_base + jl] = cl;
+        atomicOr(&bitmask[sorted[u][0] >> 5], 1u << (sorted[u][0] & 31));
+        off += len[u];
+      }
     }
-    __syncthreads();  // s_list_base / warp_sums are reused by the next chunk
+    __syncthreads();  // s_list_base / warp_sums are reused by the next round
   }
 }
 

@@ -278,3 +278,37 @@ def test_repeatable():
     b = voxelization(p, cfg["voxel_size"], cfg["point_cloud_range"], 64, 40000)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("c", [4, 5])
+def test_unaligned_buffers(c):
+    """Points / voxels buffers that are only 4-byte aligned (views into larger tensors) must take
+    the scalar paths and still be exact; also exercises the last-row guard of the vector loads."""
+    from detmatch_b200 import _cabi
+    from detmatch_b200._torch_glue import ptr, stream_ptr, workspace
+    cfg = synth.CONFIGS["C4"]
+    n, P, V = 30011, 5, 20000
+    base = synth.lidar_frame(n + 1, c, 777, 80.0).cuda()
+    pts = base.view(-1)[c:].view(n, c)                       # starts 4*c bytes into the allocation
+    assert pts.data_ptr() % 16 != 0 or c == 4
+    vox_store = torch.empty(V * P * c + 1, dtype=torch.float32, device="cuda")
+    voxels = vox_store[1:].view(V, P, c)                       # 4-byte aligned only
+    coors = torch.empty((V, 3), dtype=torch.int32, device="cuda")
+    num = torch.empty((V,), dtype=torch.int32, device="cuda")
+    vnum = torch.empty(1, dtype=torch.int32, device="cuda")
+    L = _cabi.lib()
+    vs, rg = _cabi.f3(cfg["voxel_size"]), _cabi.f6(cfg["point_cloud_range"])
+    ws = workspace(pts.device, L.pcfe_hard_voxelize_workspace_bytes(n, 1, 1, vs, rg, P, V))
+    rc = L.pcfe_hard_voxelize_f32(ptr(pts), n, c, vs, rg, P, V, ptr(voxels), ptr(coors), ptr(num), ptr(vnum),
+                                  ptr(ws), ws.numel(), 0, stream_ptr(pts.device))
+    assert rc == 0
+    m = int(vnum.item())
+    ev, ec, en = oracle.hard_voxelize(pts.cpu().numpy(), cfg["voxel_size"], cfg["point_cloud_range"], P, V)
+    assert m == len(en)
+    assert_same_bits(voxels[:m].cpu().numpy(), ev, "voxels")
+    assert_same_bits(coors[:m].cpu().numpy(), ec, "coors")
+    assert_same_bits(num[:m].cpu().numpy(), en, "num")
+    # aligned buffers whose LAST point is kept: the two-chunk row load must not read past the end
+    pts2 = synth.lidar_frame(4096, c, 778, 80.0)
+    pts2[-1, :3] = torch.tensor([1.0, 1.0, 0.0])
+    _check_hard(pts2.numpy(), cfg["voxel_size"], cfg["point_cloud_range"], P, V, "last row")
