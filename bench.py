@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--frames-in-flight", type=int, default=0)
     ap.add_argument("--hv-wave", type=int, default=0, help="tuning: frames per wave (0 = library default)")
     ap.add_argument("--hv-bucket-avg", type=int, default=0, help="tuning: target points per bucket")
+    ap.add_argument("--debug", action="append", default=[], metavar="NAME=VALUE",
+                    help="tuning: pcfe_debug_set knob (repeatable), e.g. --debug mega_d1=3")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (default: all cores, <= 64)")
     return ap.parse_args()
 
@@ -263,6 +265,9 @@ def run_ours(args):
         _cabi.debug_set("hv_wave", args.hv_wave)
     if args.hv_bucket_avg:
         _cabi.debug_set("hv_bucket_avg", args.hv_bucket_avg)
+    for kv in args.debug:
+        name, _, val = kv.partition("=")
+        _cabi.debug_set(name, int(val))
 
     # synthetic frames, generated on the host; each rank has its own 64 frames
     host = [synth.lidar_frame(N, C, synth.seed_for(cfg["index"], fid), cfg["r_max"]).pin_memory()

@@ -716,7 +716,7 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   const size_t vmax = (size_t)std::min<int64_t>(max_voxels, std::max<int64_t>(n_max, 1));
   p->vcell_b = align256(std::max<size_t>(vmax, 1) * sizeof(Cell));
   p->word_b = align256((size_t)p->words * sizeof(uint32_t));
-  p->cnt_b = align256((size_t)(p->nb + 4) * sizeof(uint32_t));
+  p->cnt_b = align256((size_t)(p->nb + 16) * sizeof(uint32_t)) + 256;  // also covers hv_mega.cu's ctl + ticket
   const size_t fast = p->ent_b + p->lst_b + p->cells_b + p->vcell_b;
   // the fallback reuses the frame's own region as table | lists | pslot
   const size_t slow = p->slow.table_b + p->slow.list_b + p->slow.pslot_b;

@@ -244,20 +244,23 @@ hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, const uint32_t* __r
                       const size_t scratch_stride, const HvGlobalPlan p,
                       uint32_t* __restrict__ bitmask_base, const size_t bitmask_stride,
                       uint32_t* __restrict__ prefix_base, const size_t prefix_stride, const int c,
-                      const int max_points, const int max_voxels, int32_t* __restrict__ voxel_num) {
-  const int f = blockIdx.x;
-  if (!force && overflow[(size_t)f * overflow_stride] == 0) return;
+                      const int max_points, const int max_voxels, int32_t* __restrict__ voxel_num,
+                      const int frames, const int ring) {
+  // CTA r serves frames r, r + ring, ... one after the other in scratch region r (ring == frames:
+  // one frame per CTA)
+  __shared__ uint32_t warp_sums[33];
+  __shared__ uint32_t carry;
+  for (int f = blockIdx.x; f < frames; f += ring) {
+  if (!force && overflow[(size_t)f * overflow_stride] == 0) continue;
   const HvFrame& fr = batch.f[f];
   const int n = fr.n;
   const int tid = threadIdx.x;
-  char* scratch = scratch_base + (size_t)f * scratch_stride;
+  char* scratch = scratch_base + (size_t)blockIdx.x * scratch_stride;
   uint2* table = reinterpret_cast<uint2*>(scratch);
   uint32_t* idxlist = reinterpret_cast<uint32_t*>(scratch + p.table_b);
   int32_t* pslot = reinterpret_cast<int32_t*>(scratch + p.table_b + p.list_b);
   uint32_t* bitmask = bitmask_base + (size_t)f * bitmask_stride;
   uint32_t* wordprefix = prefix_base + (size_t)f * prefix_stride;
-  __shared__ uint32_t warp_sums[33];
-  __shared__ uint32_t carry;
 
   // phase 0: scratch init (table + lists are contiguous)
   {
@@ -336,6 +339,8 @@ hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, const uint32_t* __r
     for (int s = 0; s < max_points; ++s) cnt += (__ldcg(&lst[s]) != kEmpty) ? 1 : 0;
     fr.num[v] = cnt;
   }
+  __syncthreads();  // the next frame reuses the scratch region and `carry`
+  }
 }
 
 int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size_t overflow_stride,
@@ -345,7 +350,21 @@ int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size
   ProfScope ps("hv_slow_fallback", st);
   hvg_slow_frame_kernel<<<frames, kSlowThreads, 0, st>>>(
       b, overflow, overflow_stride, force, scratch_base, scratch_stride, p, bitmask, bitmask_stride,
-      prefix, prefix_stride, c, max_points, max_voxels, voxel_num);
+      prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, frames);
+  PCFE_LAUNCH_CHECK();
+  return PCFE_OK;
+}
+
+// hv_mega.cu: `ring` scratch regions shared by frames f, f + ring, ...
+int hvg_launch_slow_ring(const HvBatch& b, int frames, int ring, const uint32_t* overflow,
+                         size_t overflow_stride, int force, char* scratch_base, size_t scratch_stride,
+                         const HvGlobalPlan& p, uint32_t* bitmask, size_t bitmask_stride,
+                         uint32_t* prefix, size_t prefix_stride, int c, int max_points,
+                         int max_voxels, int32_t* voxel_num, cudaStream_t st) {
+  ProfScope ps("hv_slow_fallback", st);
+  hvg_slow_frame_kernel<<<std::min(frames, ring), kSlowThreads, 0, st>>>(
+      b, overflow, overflow_stride, force, scratch_base, scratch_stride, p, bitmask, bitmask_stride,
+      prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, ring);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }

@@ -47,6 +47,7 @@ int g_opt_force_overflow = 0;
 int g_opt_hv_wave = 0;
 extern int g_opt_bucket_avg;
 extern int g_opt_bucket_variant;
+extern int g_opt_mega_d1, g_opt_mega_d2, g_opt_mega_d3, g_opt_mega_ring, g_opt_mega_ctas, g_opt_mega_stats;
 
 namespace {
 
@@ -239,6 +240,14 @@ extern "C" int pcfe_hard_voxelize_batch_f32(const pcfe_frame_t* frames, int num_
     nbuf = 1;
     wave = (int)std::min<size_t>(wave, fit);
   }
+  if (ch.bucket && g_opt_hv_path == 3) {
+    // experimental: the persistent frame pipeline (hv_mega.cu); measured slower than the launch
+    // sequence on B200 (0.73 vs 0.56 ms per C4 step: dependency waits + register-limited occupancy)
+    int ring = 0;
+    if (hvm_eligible(frames, num_frames, c, ch.bp, max_points, max_voxels, workspace_bytes, &ring))
+      return hvm_run(frames, num_frames, c, ch.bp, max_points, max_voxels, voxel_num, workspace, ring,
+                     device, st);
+  }
   if (ch.bucket)
     return hvb_run(frames, num_frames, c, ch.bp, max_points, max_voxels, voxel_num, workspace, wave,
                    nbuf, device, st);
@@ -265,6 +274,12 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_bucket_avg")) g_opt_bucket_avg = value;
   else if (!strcmp(name, "hv_wave")) g_opt_hv_wave = value;
   else if (!strcmp(name, "hv_bucket_variant")) g_opt_bucket_variant = value;
+  else if (!strcmp(name, "mega_d1")) g_opt_mega_d1 = value;
+  else if (!strcmp(name, "mega_d2")) g_opt_mega_d2 = value;
+  else if (!strcmp(name, "mega_d3")) g_opt_mega_d3 = value;
+  else if (!strcmp(name, "mega_ring")) g_opt_mega_ring = value;
+  else if (!strcmp(name, "mega_ctas")) g_opt_mega_ctas = value;
+  else if (!strcmp(name, "mega_stats")) g_opt_mega_stats = value;
   else return PCFE_ERR_SHAPE;
   return PCFE_OK;
 }

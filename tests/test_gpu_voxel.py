@@ -15,16 +15,17 @@ pytestmark = pytest.mark.gpu
 KITTI = [0, -40, -3, 70.4, 40, 1]
 
 
-@pytest.fixture(autouse=True, params=["bucket", "bucket_general", "global", "fallback"])
+@pytest.fixture(autouse=True, params=["bucket", "bucket_general", "global", "fallback", "pipeline", "pipeline_fallback"])
 def hv_mode(request):
     """Every test runs against all hard-voxelize implementations behind the one entry point: the
     shared-memory bucket path (default: register-sorted chains for P <= 8, atomicMin lists
-    otherwise), the bucket path with the general kernel forced, the global-memory path, and the
-    bucket path with every frame forced through its overflow fallback."""
+    otherwise), the bucket path with the general kernel forced, the global-memory path, the bucket
+    path with every frame forced through its overflow fallback, and the experimental persistent
+    frame pipeline (hv_mega.cu) with and without forced fallback."""
     from detmatch_b200 import _cabi
     mode = request.param
-    _cabi.debug_set("hv_path", 1 if mode == "global" else 0)
-    _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
+    _cabi.debug_set("hv_path", {"global": 1, "pipeline": 3, "pipeline_fallback": 3}.get(mode, 0))
+    _cabi.debug_set("hv_force_overflow", 1 if mode in ("fallback", "pipeline_fallback") else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "bucket_general" else 0)
     yield mode
     _cabi.debug_set("hv_path", 0)
