@@ -45,6 +45,11 @@ int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size
 
 int g_opt_bucket_avg = 1024;  // target points per bucket (tunable through pcfe_debug_set)
 int g_opt_bucket_variant = 0;  // 1: always use the general (count + atomicMin lists) bucket kernel
+int g_opt_no_fast_div = 0;      // 1: __fdiv_rn for every point (no hoisted reciprocal)
+int g_opt_expand_variant = 0;  // 1: un-pipelined fixed-P expansion kernel
+int g_opt_expand_skip = 0;      // timing experiments only (wrong output)
+int g_opt_expand_prefetch = 1;
+int g_opt_expand_pad_kb = 0;    // experiment: extra dynamic smem per expansion CTA (limits its occupancy)  // frames of L2 prefetch distance in the pipelined expansion (0 = off)
 
 namespace {
 
@@ -92,9 +97,9 @@ constexpr int kBinPerThread = PCFE_BIN_PER_THREAD;
 constexpr int kBinTile = kBinThreads * kBinPerThread;  // 4096 points
 constexpr int kMaxBuckets = 1024;
 
-__global__ void __launch_bounds__(kBinThreads)
+__global__ void __launch_bounds__(kBinThreads, 3)
 hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
-               const int c) {
+               const int c, const int fast_div) {
   __shared__ uint32_t hist[kMaxBuckets];   // entries of this tile per bucket
   __shared__ uint32_t soff[kMaxBuckets];   // exclusive prefix of hist (staging offsets)
   __shared__ uint32_t gbase[kMaxBuckets];  // position of this tile's run inside the bucket
@@ -106,25 +111,29 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
   const int tid = threadIdx.x;
   const int tile0 = blockIdx.x * kBinTile;
   if (tile0 >= fr.n) return;
+  // all row loads of the thread are issued before any arithmetic: one exposed DRAM latency per
+  // tile (the per-point division has a slow-path branch the compiler will not hoist loads over)
+  float px[kBinPerThread], py[kBinPerThread], pz[kBinPerThread];
+  const float qnan = __int_as_float(0x7FC00000);
+#pragma unroll
+  for (int k = 0; k < kBinPerThread; ++k) {
+    const int i = tile0 + k * kBinThreads + tid;
+    px[k] = qnan;  // past the end: NaN fails every range test
+    py[k] = qnan;
+    pz[k] = qnan;
+    if (i < fr.n) load_xyz(fr.pts, i, c, px[k], py[k], pz[k]);
+  }
   for (int b = tid; b < w.nb; b += kBinThreads) hist[b] = 0;
   __syncthreads();
 
+  const FastAxes fa = make_fast_axes(g);
   uint32_t key[kBinPerThread];
   uint32_t rank[kBinPerThread];
   const int shift = 32 - w.log2_nb;
 #pragma unroll
   for (int k = 0; k < kBinPerThread; ++k) {
-    const int i = tile0 + k * kBinThreads + tid;
-    key[k] = kEmpty;
-    if (i < fr.n) {
-      float x, y, z;
-      load_xyz(fr.pts, i, c, x, y, z);
-      int cx, cy, cz;
-      key[k] = point_key(x, y, z, g, cx, cy, cz);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < kBinPerThread; ++k) {
+    key[k] = point_key_fast(px[k], py[k], pz[k], g, fa, fast_div != 0);
+    rank[k] = 0;
     if (key[k] != kEmpty) {
       const uint32_t b = w.log2_nb ? (key[k] * kGold) >> shift : 0u;
       rank[k] = atomicAdd(&hist[b], 1u);
@@ -137,15 +146,13 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
   for (int b0 = 0; b0 < w.nb; b0 += kBinThreads) {
     const int b = b0 + tid;
     const uint32_t h = b < w.nb ? hist[b] : 0u;
+    uint32_t gb = 0;
+    if (h) gb = atomicAdd(&ctl[b], h);  // in flight during the block scan
     uint32_t tot;
     const uint32_t ex = block_exscan(h, warp_sums, &tot);
     if (b < w.nb) {
       soff[b] = total + ex;
-      uint32_t gb = 0;
-      if (h) {
-        gb = atomicAdd(&ctl[b], h);
-        if (gb + h > (uint32_t)w.cap) ctl[w.nb + kCtlOverflow] = 1u;  // frame takes the fallback
-      }
+      if (gb + h > (uint32_t)w.cap) ctl[w.nb + kCtlOverflow] = 1u;  // frame takes the fallback
       gbase[b] = gb;
     }
     total += tot;
@@ -669,6 +676,140 @@ hvb_expand_fixed_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, 
   }
 }
 
+// ---- the same tile, software-pipelined over the tiles of a warp ------------------------------------
+// A tile needs three dependent round trips (cell record -> list entries -> rows).  Here a warp owns
+// kPipeTiles consecutive tiles and keeps one round trip of each kind in flight at any time: while the
+// rows of tile t are on their way it has already issued the list loads of tile t + 1 and the record
+// load of tile t + 2, so the loop pays ONE memory latency per tile instead of three.
+#ifndef PCFE_EXP_PIPE_TILES
+#define PCFE_EXP_PIPE_TILES 4
+#endif
+constexpr int kPipeTiles = PCFE_EXP_PIPE_TILES;
+
+template <int C, int PT>
+__global__ void __launch_bounds__(kExpThreads)
+hvb_expand_pipe_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const KeyDecode kd,
+                       const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist,
+                       const int skip /* timing experiments only: 1 no row loads, 2 no list loads */) {
+  __shared__ __align__(16) float stage_all[kExpWarps * 32 * PT * C];
+  const int f = blockIdx.y;
+  // The row gathers below are random 32-byte sector reads; served from DRAM they waste most of
+  // every burst.  So the CTAs expanding frame f pull frame f + pf_dist into L2 with sequential
+  // bulk prefetches (one slice per CTA), and the gathers of that frame hit L2 later.
+  if (pf_dist > 0 && f + pf_dist < frames && threadIdx.x < 32) {
+    const HvFrame& nf = batch.f[f + pf_dist];
+    const size_t total = ((size_t)nf.n * C * 4) & ~(size_t)15;
+    const size_t slice = ((total + gridDim.x - 1) / gridDim.x + 511) & ~(size_t)511;  // 32 lanes x 16 B
+    const size_t lo = (size_t)blockIdx.x * slice + (size_t)threadIdx.x * (slice / 32);
+    if (lo < total) {
+      const uint32_t bytes = (uint32_t)min(slice / 32, total - lo);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(nf.pts) + lo), "r"(bytes) : "memory");
+    }
+  }
+  if (w.ctl(f)[w.nb + kCtlOverflow]) return;
+  const HvFrame& fr = batch.f[f];
+  const int m = voxel_num[f];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* stage = stage_all + wid * (32 * PT * C);
+  const uint4* __restrict__ vcell = reinterpret_cast<const uint4*>(w.vcell(f));
+  const uint32_t* __restrict__ lst = w.lst(f);
+  const float* __restrict__ pts = fr.pts;
+  float* st = stage + lane * (PT * C);
+  const int vbase = (blockIdx.x * kExpWarps + wid) * (kPipeTiles * 32);
+  if (vbase >= m) return;  // warp-uniform
+
+  auto load_cell = [&](int v0) {
+    uint4 cl = make_uint4(0u, 0u, 0u, 0u);  // key, len, list_off, first
+    if (v0 + lane < m) cl = __ldg(vcell + v0 + lane);
+    return cl;
+  };
+  uint4 cl_cur = load_cell(vbase);
+  uint4 cl_nxt = load_cell(vbase + 32);
+  uint32_t idx_cur[PT];
+  {
+    const uint32_t len = min(cl_cur.y, (uint32_t)PT);
+#pragma unroll
+    for (int j = 0; j < PT; ++j) idx_cur[j] = ((uint32_t)j < len && !(skip & 2)) ? __ldg(lst + cl_cur.z + j) : kEmpty;
+  }
+
+#pragma unroll 1
+  for (int it = 0; it < kPipeTiles; ++it) {
+    const int v0 = vbase + it * 32;
+    if (v0 >= m) break;  // warp-uniform
+    const int nvox = min(32, m - v0);
+    // rows of this tile
+    float4 ra[PT], rb[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      ra[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx_cur[j] != kEmpty && !(skip & 1)) {
+        if (C == 4) {
+          ra[j] = __ldg(reinterpret_cast<const float4*>(pts) + idx_cur[j]);
+        } else {
+          // words [5 idx, 5 idx + 5) lie inside the two aligned 16-byte chunks starting at word
+          // (5 idx) & ~3.  Both chunks hold at least one word of the row, so both lie inside the
+          // (16-byte aligned) buffer's allocation even for the last row.
+          const uint32_t w0 = idx_cur[j] * 5u;
+          const float4* p4 = reinterpret_cast<const float4*>(pts) + (w0 >> 2);
+          ra[j] = __ldg(p4);
+          rb[j] = __ldg(p4 + 1);
+        }
+      }
+    }
+    // list entries of the next tile, cell records of the one after
+    uint32_t idx_nxt[PT];
+    {
+      const uint32_t len = min(cl_nxt.y, (uint32_t)PT);
+#pragma unroll
+      for (int j = 0; j < PT; ++j) idx_nxt[j] = ((uint32_t)j < len && !(skip & 2)) ? __ldg(lst + cl_nxt.z + j) : kEmpty;
+    }
+    const uint4 cl_nn = load_cell(v0 + 64);
+    // coordinates and count of this tile's voxels
+    const uint32_t len = min(cl_cur.y, (uint32_t)PT);
+    if (lane < nvox) {
+      const uint32_t cz = div_small_err(cl_cur.x, kd.plane, kd.m_plane);
+      const uint32_t rem = cl_cur.x - cz * kd.plane;
+      const uint32_t cy = div_small_err(rem, kd.gx, kd.m_gx);
+      int32_t* co = fr.coors + (uint32_t)(v0 + lane) * 3u;
+      co[0] = (int32_t)cz;
+      co[1] = (int32_t)cy;
+      co[2] = (int32_t)(rem - cy * kd.gx);
+      fr.num[v0 + lane] = (int32_t)len;
+    }
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      if (C == 4) {
+        *reinterpret_cast<float4*>(st + j * 4) = ra[j];
+      } else {
+        const float4 a = ra[j], b = rb[j];
+        const uint32_t o = (idx_cur[j] * 5u) & 3u;  // kEmpty * 5 & 3 = 3: zeros either way
+        const bool o1 = o & 1u, o2 = o & 2u;
+        const float t0 = o1 ? a.y : a.x, t1 = o1 ? a.z : a.y, t2 = o1 ? a.w : a.z, t3 = o1 ? b.x : a.w;
+        const float t4 = o1 ? b.y : b.x, t5 = o1 ? b.z : b.y, t6 = o1 ? b.w : b.z;
+        st[j * C + 0] = o2 ? t2 : t0;
+        st[j * C + 1] = o2 ? t3 : t1;
+        st[j * C + 2] = o2 ? t4 : t2;
+        st[j * C + 3] = o2 ? t5 : t3;
+        st[j * C + 4 % C] = o2 ? t6 : t4;
+      }
+    }
+    __syncwarp();
+    const uint32_t w0 = (uint32_t)v0 * (PT * C);  // % 4 == 0 because v0 % 32 == 0
+    float* __restrict__ dst = fr.voxels + w0;
+    const int nwords = nvox * (PT * C);
+    const int n4 = nwords >> 2;
+    for (int i = lane; i < n4; i += 32)
+      __stcs(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(stage)[i]);
+    for (int i = (n4 << 2) + lane; i < nwords; i += 32) dst[i] = stage[i];
+    __syncwarp();
+    cl_cur = cl_nxt;
+    cl_nxt = cl_nn;
+#pragma unroll
+    for (int j = 0; j < PT; ++j) idx_cur[j] = idx_nxt[j];
+  }
+}
+
 template <int C>
 int launch_expand(dim3 grid, cudaStream_t st, const HvBatch& b, const HvbWork& w,
                   const GridParams& g, int c, int p, int vt, const int32_t* vn, int vec_ok) {
@@ -819,7 +960,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     {
       ProfScope ps("hvb_bin", st);
       const dim3 grid((unsigned)((wn_max + kBinTile - 1) / kBinTile), (unsigned)wv);
-      hvb_bin_kernel<<<grid, kBinThreads, 0, st>>>(b, w, p.g, c);
+      hvb_bin_kernel<<<grid, kBinThreads, 0, st>>>(b, w, p.g, c, fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0);
       PCFE_LAUNCH_CHECK();
     }
     {
@@ -858,7 +999,17 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         kd.m_gx = (uint32_t)(0x100000000ull / kd.gx);
         const int per = kExpWarps * kExpTilesPerWarp * 32;
         const dim3 fgrid((unsigned)((vmax + per - 1) / per), (unsigned)wv);
-        if (c == 4) hvb_expand_fixed_kernel<4, 5><<<fgrid, kExpThreads, 0, st>>>(b, w, kd, vn, vec_ok);
+        const int pper = kExpWarps * kPipeTiles * 32;
+        const dim3 pgrid((unsigned)((vmax + pper - 1) / pper), (unsigned)wv);
+        if (vec_ok && g_opt_expand_variant == 0) {
+          const size_t pad = (size_t)g_opt_expand_pad_kb << 10;
+          if (pad) {
+            PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_expand_pipe_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+            PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_expand_pipe_kernel<5, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+          }
+          if (c == 4) hvb_expand_pipe_kernel<4, 5><<<pgrid, kExpThreads, pad, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, g_opt_expand_skip);
+          else hvb_expand_pipe_kernel<5, 5><<<pgrid, kExpThreads, pad, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, g_opt_expand_skip);
+        } else if (c == 4) hvb_expand_fixed_kernel<4, 5><<<fgrid, kExpThreads, 0, st>>>(b, w, kd, vn, vec_ok);
         else hvb_expand_fixed_kernel<5, 5><<<fgrid, kExpThreads, 0, st>>>(b, w, kd, vn, vec_ok);
         PCFE_LAUNCH_CHECK();
       } else if (c == 4) rc = launch_expand<4>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);

@@ -47,6 +47,11 @@ int g_opt_force_overflow = 0;
 int g_opt_hv_wave = 0;
 extern int g_opt_bucket_avg;
 extern int g_opt_bucket_variant;
+extern int g_opt_expand_variant;
+extern int g_opt_expand_pad_kb;
+extern int g_opt_no_fast_div;
+extern int g_opt_expand_prefetch;
+extern int g_opt_expand_skip;
 extern int g_opt_mega_d1, g_opt_mega_d2, g_opt_mega_d3, g_opt_mega_ring, g_opt_mega_ctas, g_opt_mega_stats;
 
 namespace {
@@ -85,6 +90,28 @@ dyn_voxelize_kernel(const __grid_constant__ DynBatch batch, const GridParams g, 
     o[0] = ok ? cz : -1;
     o[1] = ok ? cy : -1;
     o[2] = ok ? cx : -1;
+  }
+}
+
+// test hook: point_key_fast() against point_key() for every float32 bit pattern of x
+__global__ void axis_sweep_kernel(const GridParams g, const int fast, unsigned long long* out) {
+  const FastAxes fa = make_fast_axes(g);
+  const float y = __fadd_rn(g.y0, g.vy), z = __fadd_rn(g.z0, g.vz);  // an in-range cell on the other axes
+  unsigned long long bad = 0, first = ~0ull;
+  const uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) * 256u;
+  for (uint32_t k = 0; k < 256u; ++k) {
+    const float x = __uint_as_float(base + k);
+    int cx, cy, cz;
+    const uint32_t want = point_key(x, y, z, g, cx, cy, cz);
+    const uint32_t got = point_key_fast(x, y, z, g, fa, fast != 0);
+    if (want != got) {
+      ++bad;
+      first = min(first, (unsigned long long)(base + k));
+    }
+  }
+  if (bad) {
+    atomicAdd(&out[0], bad);
+    atomicMin(&out[1], first);
   }
 }
 
@@ -264,6 +291,23 @@ extern "C" int pcfe_hard_voxelize_f32(const float* points, int64_t n, int c, con
                                       workspace, workspace_bytes, device, stream);
 }
 
+extern "C" int pcfe_debug_axis_sweep(float lo, float vs, float hi, uint64_t* out, int device, void* stream) {
+  if (!out) return PCFE_ERR_NULL;
+  const float v3[3] = {vs, vs, vs};
+  const float r6[6] = {lo, lo, lo, hi, hi, hi};
+  GridParams g;
+  make_grid_params(v3, r6, &g);
+  if (g.gx <= 0) return PCFE_ERR_GRID;
+  DeviceGuard guard(device);
+  PCFE_CUDA_TRY(guard.err);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint64_t init[2] = {0ull, ~0ull};
+  PCFE_CUDA_TRY(cudaMemcpyAsync(out, init, sizeof init, cudaMemcpyHostToDevice, st));
+  axis_sweep_kernel<<<(1u << 24) / 256u, 256, 0, st>>>(g, fast_div_sizes_ok(g) ? 1 : 0, (unsigned long long*)out);
+  PCFE_LAUNCH_CHECK();
+  return PCFE_OK;
+}
+
 // Test / tuning knobs: "hv_path" (0 auto, 1 global-memory path, 2 bucket path),
 // "hv_force_overflow" (1: every frame also runs the overflow fallback), "hv_bucket_avg"
 // (target points per bucket).  Returns PCFE_ERR_SHAPE for an unknown name.
@@ -274,6 +318,11 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_bucket_avg")) g_opt_bucket_avg = value;
   else if (!strcmp(name, "hv_wave")) g_opt_hv_wave = value;
   else if (!strcmp(name, "hv_bucket_variant")) g_opt_bucket_variant = value;
+  else if (!strcmp(name, "hv_expand_variant")) g_opt_expand_variant = value;
+  else if (!strcmp(name, "hv_expand_prefetch")) g_opt_expand_prefetch = value;
+  else if (!strcmp(name, "hv_no_fast_div")) g_opt_no_fast_div = value;
+  else if (!strcmp(name, "hv_expand_pad_kb")) g_opt_expand_pad_kb = value;
+  else if (!strcmp(name, "hv_expand_skip")) g_opt_expand_skip = value;
   else if (!strcmp(name, "mega_d1")) g_opt_mega_d1 = value;
   else if (!strcmp(name, "mega_d2")) g_opt_mega_d2 = value;
   else if (!strcmp(name, "mega_d3")) g_opt_mega_d3 = value;

@@ -171,6 +171,11 @@ int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float* points, i
  * x, s, c are device float arrays of length n. */
 int pcfe_debug_sincosf(const float* x, int64_t n, float* s, float* c, int device, void* stream);
 
+/* Test hook: the bin kernel's hoisted-reciprocal cell computation against the plain IEEE divide
+ * (voxelization_cpu.cpp:23-29) for EVERY float32 bit pattern of one coordinate, on the grid
+ * [lo, hi) with cell size vs on all axes.  out = device uint64[2]: {mismatches, first bad bits}. */
+int pcfe_debug_axis_sweep(float lo, float vs, float hi, uint64_t* out, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

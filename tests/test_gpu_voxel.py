@@ -313,3 +313,19 @@ def test_unaligned_buffers(c):
     pts2 = synth.lidar_frame(4096, c, 778, 80.0)
     pts2[-1, :3] = torch.tensor([1.0, 1.0, 0.0])
     _check_hard(pts2.numpy(), cfg["voxel_size"], cfg["point_cloud_range"], P, V, "last row")
+
+
+@pytest.mark.parametrize("lo,vs,hi", [(0.0, 0.05, 70.4), (-40.0, 0.05, 40.0), (-3.0, 0.1, 1.0), (-75.2, 0.1, 75.2),
+                                      (-2.0, 0.15, 4.0), (-50.0, 0.25, 50.0), (-5.0, 8.0, 3.0), (-51.2, 0.2, 51.2),
+                                      (-1.0, 1.0 / 3.0, 1.0), (0.5, 1e-3, 9.5), (-1e4, 7.77, 1e4)])
+def test_fast_division_equals_ieee_divide_exhaustive(lo, vs, hi, hv_mode):
+    """The bin kernel divides with a hoisted reciprocal + three fused steps (ptxas's own fast path)
+    instead of __fdiv_rn per point: checked for ALL 2^32 float32 values of a coordinate."""
+    if hv_mode != "bucket":
+        pytest.skip("path-independent")
+    from detmatch_b200 import _cabi
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    rc = _cabi.lib().pcfe_debug_axis_sweep(lo, vs, hi, out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    bad, first = out.cpu().tolist()
+    assert bad == 0, f"{bad} coordinates disagree with the IEEE divide, first bits {first & 0xFFFFFFFF:#x}"
