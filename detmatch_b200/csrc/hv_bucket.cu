@@ -64,6 +64,7 @@ struct HvbWork {
   char* region;          // [W] per-frame scratch: ent | lists | cells | vcell
   size_t region_stride;  // bytes
   size_t lst_off, cells_off, vcell_off;  // byte offsets inside a frame region
+  size_t rec_off, firsts_off;            // record-at-first-point variant: ent | rec | firsts
   uint32_t* zero;        // [W] per-frame zeroed block: bitmask[words] | ctl
   size_t zero_stride;    // words
   size_t ctl_off;        // words: ctl = bucket_cnt[nb] | list_cursor | cell_cursor | overflow
@@ -76,6 +77,8 @@ struct HvbWork {
   __device__ __forceinline__ uint32_t* lst(int f) const { return reinterpret_cast<uint32_t*>(region + (size_t)f * region_stride + lst_off); }
   __device__ __forceinline__ Cell* cells(int f) const { return reinterpret_cast<Cell*>(region + (size_t)f * region_stride + cells_off); }
   __device__ __forceinline__ Cell* vcell(int f) const { return reinterpret_cast<Cell*>(region + (size_t)f * region_stride + vcell_off); }
+  __device__ __forceinline__ uint4* rec(int f) const { return reinterpret_cast<uint4*>(region + (size_t)f * region_stride + rec_off); }
+  __device__ __forceinline__ uint32_t* firsts(int f) const { return reinterpret_cast<uint32_t*>(region + (size_t)f * region_stride + firsts_off); }
   __device__ __forceinline__ uint32_t* bitmask(int f) const { return zero + (size_t)f * zero_stride; }
   __device__ __forceinline__ uint32_t* ctl(int f) const { return zero + (size_t)f * zero_stride + ctl_off; }
   __device__ __forceinline__ uint32_t* prefix(int f) const { return wordprefix + (size_t)f * word_stride; }
@@ -99,44 +102,93 @@ constexpr int kMaxBuckets = 1024;
 
 __global__ void __launch_bounds__(kBinThreads, 3)
 hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
-               const int c, const int fast_div) {
+               const int c, const int use_fast_div) {
   __shared__ uint32_t hist[kMaxBuckets];   // entries of this tile per bucket
   __shared__ uint32_t soff[kMaxBuckets];   // exclusive prefix of hist (staging offsets)
-  __shared__ uint32_t gbase[kMaxBuckets];  // position of this tile's run inside the bucket
+  __shared__ uint32_t delta[kMaxBuckets];  // (entry position in the frame's ent array) - (staging position)
   __shared__ uint2 stage[kBinTile];
   __shared__ uint32_t warp_sums[33];
+  __shared__ uint32_t s_overflow;
 
   const int f = blockIdx.y;
-  const HvFrame& fr = batch.f[f];
+  const int n = batch.f[f].n;
   const int tid = threadIdx.x;
   const int tile0 = blockIdx.x * kBinTile;
-  if (tile0 >= fr.n) return;
-  // all row loads of the thread are issued before any arithmetic: one exposed DRAM latency per
-  // tile (the per-point division has a slow-path branch the compiler will not hoist loads over)
-  float px[kBinPerThread], py[kBinPerThread], pz[kBinPerThread];
-  const float qnan = __int_as_float(0x7FC00000);
+  if (tile0 >= n) return;
+  // All row loads of the thread are issued before any arithmetic: one exposed DRAM latency per
+  // tile.  ax/ay/az end up holding p - range_min.
+  float ax[kBinPerThread], ay[kBinPerThread], az[kBinPerThread];
+  {
+    const float* __restrict__ p = batch.f[f].pts + (size_t)(tile0 + tid) * c;
+    const int stride = kBinThreads * c;
+    if (tile0 + kBinTile <= n) {
 #pragma unroll
-  for (int k = 0; k < kBinPerThread; ++k) {
-    const int i = tile0 + k * kBinThreads + tid;
-    px[k] = qnan;  // past the end: NaN fails every range test
-    py[k] = qnan;
-    pz[k] = qnan;
-    if (i < fr.n) load_xyz(fr.pts, i, c, px[k], py[k], pz[k]);
+      for (int k = 0; k < kBinPerThread; ++k) {
+        ax[k] = __ldg(p + k * stride);
+        ay[k] = __ldg(p + k * stride + 1);
+        az[k] = __ldg(p + k * stride + 2);
+      }
+    } else {
+      const float qnan = __int_as_float(0x7FC00000);  // past the end: NaN fails every range test
+#pragma unroll
+      for (int k = 0; k < kBinPerThread; ++k) {
+        const bool in = tile0 + tid + k * kBinThreads < n;
+        ax[k] = in ? __ldg(p + k * stride) : qnan;
+        ay[k] = in ? __ldg(p + k * stride + 1) : qnan;
+        az[k] = in ? __ldg(p + k * stride + 2) : qnan;
+      }
+    }
   }
   for (int b = tid; b < w.nb; b += kBinThreads) hist[b] = 0;
+  if (tid == 0) s_overflow = 0u;
   __syncthreads();
 
-  const FastAxes fa = make_fast_axes(g);
+  // cell keys.  One branch per thread, not per point: when every difference of the thread is
+  // inside the guard of the hoisted-reciprocal division (pcfe_common.cuh) the eight keys are
+  // computed without any control flow; otherwise all eight take the plain IEEE divide.
   uint32_t key[kBinPerThread];
-  uint32_t rank[kBinPerThread];
+  bool guard_ok = use_fast_div != 0;
+#pragma unroll
+  for (int k = 0; k < kBinPerThread; ++k) {
+    ax[k] = __fsub_rn(ax[k], g.x0);
+    ay[k] = __fsub_rn(ay[k], g.y0);
+    az[k] = __fsub_rn(az[k], g.z0);
+    guard_ok = guard_ok & fast_div_guard(ax[k]) & fast_div_guard(ay[k]) & fast_div_guard(az[k]);
+  }
+  if (guard_ok) {
+    const FastAxes fa = make_fast_axes(g);
+#pragma unroll
+    for (int k = 0; k < kBinPerThread; ++k) {
+      const float qx = fast_div(ax[k], g.vx, fa.rx), qy = fast_div(ay[k], g.vy, fa.ry), qz = fast_div(az[k], g.vz, fa.rz);
+      // 0 <= q < 2^31 <=> bits(q) < bits(2^31) as unsigned; -0 and NaN cannot come out of the guard
+      const uint32_t qmax = max(max(__float_as_uint(qx), __float_as_uint(qy)), __float_as_uint(qz));
+      const int cx = __float2int_rz(qx), cy = __float2int_rz(qy), cz = __float2int_rz(qz);
+      const bool ok = (qmax < 0x4F000000u) & (cx < g.gx) & (cy < g.gy) & (cz < g.gz);
+      const uint32_t lin = ((uint32_t)cz * (uint32_t)g.gy + (uint32_t)cy) * (uint32_t)g.gx + (uint32_t)cx;
+      key[k] = ok ? lin : kEmpty;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kBinPerThread; ++k) {
+      // voxelization_cpu.cpp:23-29 on the differences (axis_cell() without its subtract)
+      const float qx = __fdiv_rn(ax[k], g.vx), qy = __fdiv_rn(ay[k], g.vy), qz = __fdiv_rn(az[k], g.vz);
+      const bool in = (qx >= 0.0f) & (qx < 2147483648.0f) & (qy >= 0.0f) & (qy < 2147483648.0f) &
+                      (qz >= 0.0f) & (qz < 2147483648.0f);
+      const int cx = in ? __float2int_rz(qx) : -1, cy = in ? __float2int_rz(qy) : -1, cz = in ? __float2int_rz(qz) : -1;
+      const bool ok = in & (cx < g.gx) & (cy < g.gy) & (cz < g.gz);
+      const uint32_t lin = ((uint32_t)cz * (uint32_t)g.gy + (uint32_t)cy) * (uint32_t)g.gx + (uint32_t)cx;
+      key[k] = ok ? lin : kEmpty;
+    }
+  }
+  // rank of every entry inside its (tile, bucket) run; rb = bucket << 16 | rank
+  uint32_t rb[kBinPerThread];
   const int shift = 32 - w.log2_nb;
 #pragma unroll
   for (int k = 0; k < kBinPerThread; ++k) {
-    key[k] = point_key_fast(px[k], py[k], pz[k], g, fa, fast_div != 0);
-    rank[k] = 0;
+    rb[k] = 0;
     if (key[k] != kEmpty) {
       const uint32_t b = w.log2_nb ? (key[k] * kGold) >> shift : 0u;
-      rank[k] = atomicAdd(&hist[b], 1u);
+      rb[k] = (b << 16) | atomicAdd(&hist[b], 1u);
     }
   }
   __syncthreads();
@@ -152,26 +204,27 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
     const uint32_t ex = block_exscan(h, warp_sums, &tot);
     if (b < w.nb) {
       soff[b] = total + ex;
-      if (gb + h > (uint32_t)w.cap) ctl[w.nb + kCtlOverflow] = 1u;  // frame takes the fallback
-      gbase[b] = gb;
+      delta[b] = (uint32_t)b * (uint32_t)w.cap + gb - (total + ex);
+      if (gb + h > (uint32_t)w.cap) {  // the frame takes the fallback; its entries are not needed
+        ctl[w.nb + kCtlOverflow] = 1u;
+        s_overflow = 1u;
+      }
     }
     total += tot;
     __syncthreads();
   }
+  if (s_overflow) return;
 #pragma unroll
   for (int k = 0; k < kBinPerThread; ++k) {
-    if (key[k] != kEmpty) {
-      const uint32_t b = w.log2_nb ? (key[k] * kGold) >> shift : 0u;
-      stage[soff[b] + rank[k]] = make_uint2(key[k], (uint32_t)(tile0 + k * kBinThreads + tid));
-    }
+    if (key[k] != kEmpty)
+      stage[soff[rb[k] >> 16] + (rb[k] & 0xFFFFu)] = make_uint2(key[k], (uint32_t)(tile0 + k * kBinThreads + tid));
   }
   __syncthreads();
   uint2* __restrict__ ent = w.ent(f);
   for (uint32_t j = tid; j < total; j += kBinThreads) {
     const uint2 e = stage[j];
     const uint32_t b = w.log2_nb ? (e.x * kGold) >> shift : 0u;
-    const uint32_t dst = gbase[b] + (j - soff[b]);
-    if (dst < (uint32_t)w.cap) ent[(size_t)b * w.cap + dst] = e;
+    ent[delta[b] + j] = e;
   }
 }
 
@@ -310,7 +363,11 @@ hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
 // the arena straight from registers: consecutive cells write consecutive ranges.
 // dynamic shared memory (words): hkey[S] | head[S] | eidx[cap] | enext[cap] (u16) | slotlist[cap] (u16)
 // ------------------------------------------------------------------------------------------
-template <int PT>
+// REC (P <= 5 only): instead of a cell record + a list in the arena, the cell is written as ONE
+// 32-byte record at the index of its first point, rec[first] = {key, len, idx1..idx4, 0, 0} (idx0 is
+// `first` itself): a full-sector write, no list offsets, no cursors, no block scan -- and no order
+// pass later, because the expansion finds the record of voxel v at rec[firsts[v]].
+template <int PT, bool REC = false>
 __global__ void __launch_bounds__(kBucketThreads)
 hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -340,25 +397,37 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
   const uint2* __restrict__ ent = w.ent(f) + (size_t)b * cap;
   const uint32_t smask = (uint32_t)S - 1u;
   const int sshift = 32 - w.log2_nb - w.log2_slots;
-  for (int e = tid; e < ne; e += kBucketThreads) {
-    const uint2 en = __ldcs(&ent[e]);
+  const uint32_t lane_lt = (1u << (tid & 31)) - 1u;
+  // warp-uniform trip count: every lane takes part in the ballot below
+  for (int e0 = 0; e0 < ne; e0 += kBucketThreads) {
+    const int e = e0 + tid;
+    const bool valid = e < ne;
+    uint2 en = make_uint2(0u, 0u);
+    if (valid) en = __ldcs(&ent[e]);
     uint32_t s = ((en.x * kGold) >> sshift) & smask;
-    while (true) {
-      uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&hkey[s]);
-      if (cur == en.x) break;
-      if (cur == kEmpty) {
-        cur = atomicCAS(&hkey[s], kEmpty, en.x);
-        if (cur == kEmpty) {
-          slotlist[atomicAdd(&s_nclaimed, 1u)] = (uint16_t)s;
-          break;
-        }
-        if (cur == en.x) break;
+    bool claimed = false;
+    if (valid) {
+      // one CAS per probe: it either claims the slot, finds the cell, or reports a collision
+      while (true) {
+        const uint32_t old = atomicCAS(&hkey[s], kEmpty, en.x);
+        claimed = old == kEmpty;
+        if (claimed || old == en.x) break;
+        s = (s + 1u) & smask;
       }
-      s = (s + 1u) & smask;
     }
-    const uint32_t prev = atomicExch(&head[s], (uint32_t)e);
-    enext[e] = (uint16_t)(prev == kEmpty ? kNil : prev);
-    eidx[e] = en.y;
+    // claimed slots are appended to the cell list with one shared-memory atomic per warp
+    const uint32_t cm = __ballot_sync(0xFFFFFFFFu, claimed);
+    if (cm) {
+      uint32_t base = 0;
+      if ((tid & 31) == __ffs(cm) - 1) base = atomicAdd(&s_nclaimed, (uint32_t)__popc(cm));
+      base = __shfl_sync(0xFFFFFFFFu, base, __ffs(cm) - 1);
+      if (claimed) slotlist[base + __popc(cm & lane_lt)] = (uint16_t)s;
+    }
+    if (valid) {
+      const uint32_t prev = atomicExch(&head[s], (uint32_t)e);
+      enext[e] = (uint16_t)(prev == kEmpty ? kNil : prev);
+      eidx[e] = en.y;
+    }
   }
   __syncthreads();
 
@@ -366,6 +435,35 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
   uint32_t* __restrict__ glst = w.lst(f);
   Cell* __restrict__ cells = w.cells(f);
   uint32_t* __restrict__ bitmask = w.bitmask(f);
+  if (REC) {
+    uint4* __restrict__ rec = w.rec(f);
+#pragma unroll 1
+    for (int j = tid; j < nv; j += kBucketThreads) {
+      uint32_t sorted[PT];
+#pragma unroll
+      for (int t = 0; t < PT; ++t) sorted[t] = kEmpty;
+      const int s = slotlist[j];
+      uint32_t cnt = 0;
+      uint32_t e = head[s];
+      while (e != kNil) {  // chain walk; the P smallest indices stay in registers, ascending
+        uint32_t v = eidx[e];
+        e = enext[e];
+        ++cnt;
+#pragma unroll
+        for (int t = 0; t < PT; ++t) {
+          const uint32_t lo = min(sorted[t], v);
+          v = max(sorted[t], v);
+          sorted[t] = lo;
+        }
+      }
+      const uint32_t len = min(cnt, (uint32_t)pe);
+      const uint32_t first = sorted[0];
+      rec[2 * (size_t)first] = make_uint4(hkey[s], len, sorted[1 % PT], sorted[2 % PT]);
+      rec[2 * (size_t)first + 1] = make_uint4(sorted[3 % PT], sorted[4 % PT], 0u, 0u);
+      atomicOr(&bitmask[first >> 5], 1u << (first & 31));
+    }
+    return;
+  }
   // kCellsPerThread cells per thread and round (cells tid, tid + T, ...): a typical bucket
   // (~370 cells) needs one round, i.e. one block scan and three barriers for the whole tail
   constexpr int kCellsPerThread = 2;
@@ -810,6 +908,166 @@ hvb_expand_pipe_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, c
   }
 }
 
+// ---- record-at-first-point variant: voxel ids -> first points, then a pipelined expansion -----------
+// firsts[v] = index of the first point of voxel v = position of the v-th set bit of the frame's
+// bitmask.  CTA (slice, frame) re-counts the bits before its slice (<= 22 KB of L2-resident words)
+// instead of waiting for a prefix, then writes the positions of its own set bits.
+constexpr int kFirstsThreads = 256;
+
+// CTA (slice, frame) owns 256 consecutive bitmask words (one per thread).  It re-counts the bits
+// before its slice (<= 22 KB of L2-resident words) instead of waiting for a prefix, expands its
+// own set bits into shared memory and writes them out as one contiguous, coalesced run (scattered
+// 4-byte stores would be partial-sector L2 writes: measured 7x slower).
+__global__ void __launch_bounds__(kFirstsThreads)
+hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
+                       int32_t* __restrict__ voxel_num) {
+  __shared__ uint32_t warp_sums[33];
+  __shared__ uint32_t stage[kFirstsThreads * 32];
+  const int f = blockIdx.y, tid = threadIdx.x;
+  if (w.ctl(f)[w.nb + kCtlOverflow]) return;
+  const uint32_t* __restrict__ bm = w.bitmask(f);
+  uint32_t* __restrict__ firsts = w.firsts(f);
+  const int lo = blockIdx.x * kFirstsThreads;
+  const int wd = lo + tid;
+  uint32_t bits = wd < words ? bm[wd] : 0u;
+  uint32_t sum = 0;
+  for (int i = tid; i < lo; i += kFirstsThreads) sum += __popc(bm[i]);
+  uint32_t before;
+  block_exscan(sum, warp_sums, &before);
+  __syncthreads();  // warp_sums is reused below
+  uint32_t total;
+  uint32_t pos = block_exscan((uint32_t)__popc(bits), warp_sums, &total);
+  while (bits) {
+    const int bit = __ffs(bits) - 1;
+    bits &= bits - 1u;
+    stage[pos++] = (uint32_t)wd * 32u + (uint32_t)bit;
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < total; i += kFirstsThreads)
+    if (before + i < (uint32_t)max_voxels) firsts[before + i] = stage[i];  // voxelization_cpu.cpp:78
+  if (blockIdx.x == gridDim.x - 1 && tid == 0)
+    voxel_num[f] = (int32_t)min(before + total, (uint32_t)max_voxels);
+}
+
+// Expansion: lane = voxel.  Three dependent round trips per tile (firsts -> record -> rows), one of
+// each kind in flight: rows of tile t, records of tile t + 1, first-point indices of tile t + 2.
+template <int C>
+__global__ void __launch_bounds__(kExpThreads)
+hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const KeyDecode kd,
+                      const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist) {
+  constexpr int PT = 5;
+  __shared__ __align__(16) float stage_all[kExpWarps * 32 * PT * C];
+  const int f = blockIdx.y;
+  if (pf_dist > 0 && f + pf_dist < frames && threadIdx.x < 32) {  // see hvb_expand_pipe_kernel
+    const HvFrame& nf = batch.f[f + pf_dist];
+    const size_t total = ((size_t)nf.n * C * 4) & ~(size_t)15;
+    const size_t slice = ((total + gridDim.x - 1) / gridDim.x + 511) & ~(size_t)511;
+    const size_t lo = (size_t)blockIdx.x * slice + (size_t)threadIdx.x * (slice / 32);
+    if (lo < total) {
+      const uint32_t bytes = (uint32_t)min(slice / 32, total - lo);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(nf.pts) + lo), "r"(bytes) : "memory");
+    }
+  }
+  if (w.ctl(f)[w.nb + kCtlOverflow]) return;
+  const HvFrame& fr = batch.f[f];
+  const int m = voxel_num[f];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* stage = stage_all + wid * (32 * PT * C);
+  const uint32_t* __restrict__ firsts = w.firsts(f);
+  const uint4* __restrict__ rec = w.rec(f);
+  const float* __restrict__ pts = fr.pts;
+  float* st = stage + lane * (PT * C);
+  const int vbase = (blockIdx.x * kExpWarps + wid) * (kPipeTiles * 32);
+  if (vbase >= m) return;  // warp-uniform
+
+  auto load_first = [&](int v0) { return v0 + lane < m ? __ldg(firsts + v0 + lane) : kEmpty; };
+  uint32_t fi_cur = load_first(vbase);
+  uint32_t fi_nxt = load_first(vbase + 32);
+  uint4 ra_cur = make_uint4(0u, 0u, kEmpty, kEmpty), rb_cur = make_uint4(kEmpty, kEmpty, 0u, 0u);
+  if (fi_cur != kEmpty) {
+    ra_cur = __ldg(rec + 2 * (size_t)fi_cur);
+    rb_cur = __ldg(rec + 2 * (size_t)fi_cur + 1);
+  }
+
+#pragma unroll 1
+  for (int it = 0; it < kPipeTiles; ++it) {
+    const int v0 = vbase + it * 32;
+    if (v0 >= m) break;  // warp-uniform
+    const int nvox = min(32, m - v0);
+    const uint32_t len = min(ra_cur.y, (uint32_t)PT);  // 0 for lanes past the end
+    uint32_t idx[PT];
+    idx[0] = fi_cur;
+    idx[1] = ra_cur.z; idx[2] = ra_cur.w; idx[3] = rb_cur.x; idx[4] = rb_cur.y;
+    // rows of this tile
+    float4 qa[PT], qb[PT];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      qa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      qb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((uint32_t)j < len) {
+        if (C == 4) {
+          qa[j] = __ldg(reinterpret_cast<const float4*>(pts) + idx[j]);
+        } else {
+          // words [5 idx, 5 idx + 5) lie inside the two aligned 16-byte chunks starting at word
+          // (5 idx) & ~3; both chunks hold a word of the row, so both are inside the allocation
+          const uint32_t w0 = idx[j] * 5u;
+          const float4* p4 = reinterpret_cast<const float4*>(pts) + (w0 >> 2);
+          qa[j] = __ldg(p4);
+          qb[j] = __ldg(p4 + 1);
+        }
+      }
+    }
+    // records of the next tile, first-point indices of the one after
+    uint4 ra_nxt = make_uint4(0u, 0u, kEmpty, kEmpty), rb_nxt = make_uint4(kEmpty, kEmpty, 0u, 0u);
+    if (fi_nxt != kEmpty) {
+      ra_nxt = __ldg(rec + 2 * (size_t)fi_nxt);
+      rb_nxt = __ldg(rec + 2 * (size_t)fi_nxt + 1);
+    }
+    const uint32_t fi_nn = load_first(v0 + 64);
+    // coordinates and count of this tile's voxels
+    if (lane < nvox) {
+      const uint32_t cz = div_small_err(ra_cur.x, kd.plane, kd.m_plane);
+      const uint32_t rem = ra_cur.x - cz * kd.plane;
+      const uint32_t cy = div_small_err(rem, kd.gx, kd.m_gx);
+      int32_t* co = fr.coors + (uint32_t)(v0 + lane) * 3u;
+      co[0] = (int32_t)cz;
+      co[1] = (int32_t)cy;
+      co[2] = (int32_t)(rem - cy * kd.gx);
+      fr.num[v0 + lane] = (int32_t)len;
+    }
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      if (C == 4) {
+        *reinterpret_cast<float4*>(st + j * 4) = qa[j];
+      } else {
+        const float4 a = qa[j], b = qb[j];
+        const uint32_t o = (idx[j] * 5u) & 3u;  // absent rows are all zeros whatever o is
+        const bool o1 = o & 1u, o2 = o & 2u;
+        const float t0 = o1 ? a.y : a.x, t1 = o1 ? a.z : a.y, t2 = o1 ? a.w : a.z, t3 = o1 ? b.x : a.w;
+        const float t4 = o1 ? b.y : b.x, t5 = o1 ? b.z : b.y, t6 = o1 ? b.w : b.z;
+        st[j * C + 0] = o2 ? t2 : t0;
+        st[j * C + 1] = o2 ? t3 : t1;
+        st[j * C + 2] = o2 ? t4 : t2;
+        st[j * C + 3] = o2 ? t5 : t3;
+        st[j * C + 4 % C] = o2 ? t6 : t4;
+      }
+    }
+    __syncwarp();
+    const uint32_t w0 = (uint32_t)v0 * (PT * C);  // % 4 == 0 because v0 % 32 == 0
+    float* __restrict__ dst = fr.voxels + w0;
+    const int nwords = nvox * (PT * C);
+    const int n4 = nwords >> 2;
+    for (int i = lane; i < n4; i += 32)
+      __stcs(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(stage)[i]);
+    for (int i = (n4 << 2) + lane; i < nwords; i += 32) dst[i] = stage[i];
+    __syncwarp();
+    fi_cur = fi_nxt;
+    fi_nxt = fi_nn;
+    ra_cur = ra_nxt;
+    rb_cur = rb_nxt;
+  }
+}
+
 template <int C>
 int launch_expand(dim3 grid, cudaStream_t st, const HvBatch& b, const HvbWork& w,
                   const GridParams& g, int c, int p, int vt, const int32_t* vn, int vec_ok) {
@@ -858,7 +1116,9 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   p->vcell_b = align256(std::max<size_t>(vmax, 1) * sizeof(Cell));
   p->word_b = align256((size_t)p->words * sizeof(uint32_t));
   p->cnt_b = align256((size_t)(p->nb + 16) * sizeof(uint32_t)) + 256;  // also covers hv_mega.cu's ctl + ticket
-  const size_t fast = p->ent_b + p->lst_b + p->cells_b + p->vcell_b;
+  p->rec_b = align256((size_t)p->npad * 32);
+  p->firsts_b = align256(std::max<size_t>(vmax, 1) * sizeof(uint32_t));
+  const size_t fast = std::max(p->ent_b + p->lst_b + p->cells_b + p->vcell_b, p->ent_b + p->rec_b + p->firsts_b);
   // the fallback reuses the frame's own region as table | lists | pslot
   const size_t slow = p->slow.table_b + p->slow.list_b + p->slow.pslot_b;
   p->region_b = std::max(fast, slow);
@@ -917,6 +1177,8 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
   w.lst_off = p.ent_b;
   w.cells_off = p.ent_b + p.lst_b;
   w.vcell_off = p.ent_b + p.lst_b + p.cells_b;
+  w.rec_off = p.ent_b;
+  w.firsts_off = p.ent_b + p.rec_b;
   const size_t zero_per = p.word_b + p.cnt_b;
   w.zero_stride = zero_per / sizeof(uint32_t);
   w.ctl_off = p.word_b / sizeof(uint32_t);
@@ -929,6 +1191,8 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)p.smem_bucket));
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)p.smem_bucket));
+  PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)p.smem_bucket));
   const int pe = std::max(max_points, 1);
   int vec_ok = 1;  // float4 tile stream / vector row loads need 16-byte aligned buffers
@@ -963,6 +1227,39 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       hvb_bin_kernel<<<grid, kBinThreads, 0, st>>>(b, w, p.g, c, fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0);
       PCFE_LAUNCH_CHECK();
     }
+    // P == 5 with 16-byte aligned rows: the record-at-first-point variant (no order pass)
+    const bool use_rec = max_points == 5 && (c == 4 || c == 5) && vec_ok && max_voxels < (1 << 24) &&
+                         g_opt_bucket_variant == 0;
+    int rc = PCFE_OK;
+    if (use_rec) {
+      {
+        ProfScope ps("hvb_bucket", st);
+        const dim3 grid((unsigned)p.nb, (unsigned)wv);
+        const size_t smem_small = (size_t)(2 * p.slots + p.cap) * 4 + (size_t)(2 * p.cap) * 2;
+        hvb_bucket_small_kernel<5, true><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
+        PCFE_LAUNCH_CHECK();
+      }
+      {
+        ProfScope ps("hvb_scan_firsts", st);
+        hvb_scan_firsts_kernel<<<dim3((unsigned)((wnpad / 32 + kFirstsThreads - 1) / kFirstsThreads), (unsigned)wv), kFirstsThreads, 0, st>>>(w, wnpad / 32, max_voxels, voxel_num + f0);
+        PCFE_LAUNCH_CHECK();
+      }
+      {
+        ProfScope ps("hvb_expand", st);
+        KeyDecode kd;
+        kd.plane = (uint32_t)p.g.gx * (uint32_t)p.g.gy;
+        kd.gx = (uint32_t)p.g.gx;
+        kd.m_plane = (uint32_t)(0x100000000ull / kd.plane);
+        kd.m_gx = (uint32_t)(0x100000000ull / kd.gx);
+        const int64_t vmax = std::max<int64_t>(std::min<int64_t>(max_voxels, wn_max), 1);
+        const int pper = kExpWarps * kPipeTiles * 32;
+        const dim3 pgrid((unsigned)((vmax + pper - 1) / pper), (unsigned)wv);
+        const int32_t* vn = voxel_num + f0;
+        if (c == 4) hvb_expand_rec_kernel<4><<<pgrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch);
+        else hvb_expand_rec_kernel<5><<<pgrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch);
+        PCFE_LAUNCH_CHECK();
+      }
+    } else {
     {
       ProfScope ps("hvb_bucket", st);
       const dim3 grid((unsigned)p.nb, (unsigned)wv);
@@ -976,7 +1273,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         hvb_bucket_kernel<<<grid, kBucketThreads, p.smem_bucket, st>>>(w, pe);
       PCFE_LAUNCH_CHECK();
     }
-    int rc = hv_launch_scan(w.zero, w.zero_stride, w.wordprefix, w.word_stride, wnpad / 32,
+    rc = hv_launch_scan(w.zero, w.zero_stride, w.wordprefix, w.word_stride, wnpad / 32,
                             max_voxels, voxel_num + f0, wv, 1, st);
     if (rc != PCFE_OK) return rc;
     {
@@ -1016,6 +1313,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       else if (c == 5) rc = launch_expand<5>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
       else rc = launch_expand<0>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
       if (rc != PCFE_OK) return rc;
+    }
     }
     rc = hvg_launch_slow(b, wv, w.zero + w.ctl_off + p.nb + kCtlOverflow, w.zero_stride,
                          g_opt_force_overflow, w.region, w.region_stride, p.slow, w.zero,

@@ -146,6 +146,7 @@ struct HvBucketPlan {
   int exp_vt;             // voxels per warp tile of the expansion kernel
   // per-frame byte sizes (256-aligned)
   size_t ent_b, lst_b, cells_b, vcell_b, word_b, cnt_b, region_b, per_frame;
+  size_t rec_b, firsts_b;  // record-at-first-point variant (P == 5): 32-byte records, voxel id -> first point
   size_t smem_bucket;     // dynamic shared memory of the bucket kernel
   // the overflow fallback (single CTA per frame) reuses the frame's own scratch region
   HvGlobalPlan slow;
