@@ -534,6 +534,114 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
 }
 
 // ------------------------------------------------------------------------------------------
+// B'': the record-at-first-point bucket kernel (P == 5).  Same grouping as B' -- open-addressing
+// table, chains, register sort -- with three changes measured on B200:
+//   * the bucket's entries arrive in shared memory with ONE TMA bulk copy (the per-thread global
+//     loads exposed a DRAM/L2 latency per loop trip: 18 % of all stall samples);
+//   * one CAS per probe (claims the slot, finds the cell or reports a collision) and a hand-written
+//     warp-aggregated append to the cell list;
+//   * every cell leaves as one 32-byte record at rec[first point]: no lists, cursors or block scan.
+// dynamic shared memory: ents[cap] (uint2) | hkey[S] | head[S] | enext[cap] (u16) | slotlist[cap] (u16)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBucketThreads)
+hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */) {
+  constexpr int PT = 5;
+  constexpr uint32_t kNil = 0xFFFFu;
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t s_nclaimed;
+
+  const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
+  const uint32_t* ctl = w.ctl(f);
+  if (ctl[w.nb + kCtlOverflow]) return;
+  const int S = w.slots, cap = w.cap;
+  uint2* ents = reinterpret_cast<uint2*>(smem);
+  uint32_t* hkey = smem + 2 * cap;
+  uint32_t* head = hkey + S;
+  uint16_t* enext = reinterpret_cast<uint16_t*>(head + S);
+  uint16_t* slotlist = enext + cap;
+
+  const int ne = (int)min(ctl[b], (uint32_t)cap);
+  if (ne == 0) return;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    const uint32_t bytes = (uint32_t)((ne + 1) & ~1) * 8u;  // 16-byte granules; cap is even
+    mbar_expect_tx(&bar, bytes);
+    bulk_g2s(ents, w.ent(f) + (size_t)b * cap, bytes, &bar);
+    s_nclaimed = 0u;
+  }
+  {
+    uint4* k4 = reinterpret_cast<uint4*>(hkey);  // hkey and head are contiguous: 2 * S words
+    for (int s = tid; s < S / 2; s += kBucketThreads) k4[s] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+  }
+  __syncthreads();  // table initialised, barrier initialised
+  mbar_wait(&bar, 0);
+
+  const uint32_t smask = (uint32_t)S - 1u;
+  const int sshift = 32 - w.log2_nb - w.log2_slots;
+  const uint32_t lane = (uint32_t)tid & 31u;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  for (int e0 = 0; e0 < ne; e0 += kBucketThreads) {  // warp-uniform trip count
+    const int e = e0 + tid;
+    const bool valid = e < ne;
+    const uint32_t key = valid ? ents[e].x : 0u;
+    uint32_t s = ((key * kGold) >> sshift) & smask;
+    bool claimed = false;
+    if (valid) {
+      while (true) {
+        const uint32_t old = atomicCAS(&hkey[s], kEmpty, key);
+        claimed = old == kEmpty;
+        if (claimed || old == key) break;
+        s = (s + 1u) & smask;
+      }
+    }
+    const uint32_t cm = __ballot_sync(0xFFFFFFFFu, claimed);
+    if (cm) {
+      const uint32_t leader = (uint32_t)__ffs(cm) - 1u;
+      uint32_t base = 0;
+      if (lane == leader)
+        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(smem_u32(&s_nclaimed)), "r"(__popc(cm)) : "memory");
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (claimed) slotlist[base + __popc(cm & lane_lt)] = (uint16_t)s;
+    }
+    if (valid) {
+      const uint32_t prev = atomicExch(&head[s], (uint32_t)e);
+      enext[e] = (uint16_t)(prev == kEmpty ? kNil : prev);
+    }
+  }
+  __syncthreads();
+
+  const int nv = (int)s_nclaimed;
+  uint32_t* __restrict__ bitmask = w.bitmask(f);
+  uint4* __restrict__ rec = w.rec(f);
+#pragma unroll 1
+  for (int j = tid; j < nv; j += kBucketThreads) {
+    uint32_t sorted[PT];
+#pragma unroll
+    for (int t = 0; t < PT; ++t) sorted[t] = kEmpty;
+    const int s = slotlist[j];
+    uint32_t cnt = 0;
+    uint32_t e = head[s];
+    while (e != kNil) {  // chain walk; the 5 smallest point indices stay in registers, ascending
+      uint32_t v = ents[e].y;
+      e = enext[e];
+      ++cnt;
+#pragma unroll
+      for (int t = 0; t < PT; ++t) {
+        const uint32_t lo = min(sorted[t], v);
+        v = max(sorted[t], v);
+        sorted[t] = lo;
+      }
+    }
+    const uint32_t len = min(cnt, (uint32_t)pe);
+    const uint32_t first = sorted[0];
+    rec[2 * (size_t)first] = make_uint4(hkey[s], len, sorted[1], sorted[2]);
+    rec[2 * (size_t)first + 1] = make_uint4(sorted[3], sorted[4], 0u, 0u);
+    atomicOr(&bitmask[first >> 5], 1u << (first & 31));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // D: voxel id of every cell = rank of its first point; vcell[vid] = cell
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -949,14 +1057,27 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
     voxel_num[f] = (int32_t)min(before + total, (uint32_t)max_voxels);
 }
 
-// Expansion: lane = voxel.  Three dependent round trips per tile (firsts -> record -> rows), one of
+// Expansion.  Three dependent round trips per tile of 32 voxels (firsts -> record -> rows), one of
 // each kind in flight: rows of tile t, records of tile t + 1, first-point indices of tile t + 2.
+// Records are fetched with lane = voxel; the rows are fetched with lane = OUTPUT WORD: word
+// w = lane + 32 k of the tile belongs to (voxel, slot) q = w / C and feature w % C, so the C
+// consecutive lanes of a row read one 4 C-byte piece of memory (one L1 wavefront per row instead of
+// two 16-byte gathers per lane) and the loaded word goes straight from its register to its final
+// place in a 128-byte coalesced store -- no shared-memory transposition of the data.  The kernel is
+// bound by L1 wavefronts (random gathers), not by DRAM: the same frames resident in L2 run no faster.
+#ifndef PCFE_EXP_REC_MINB
+#define PCFE_EXP_REC_MINB 6
+#endif
 template <int C>
-__global__ void __launch_bounds__(kExpThreads)
+__global__ void __launch_bounds__(kExpThreads, PCFE_EXP_REC_MINB)
 hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const KeyDecode kd,
-                      const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist) {
+                      const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist,
+                      const int coors_vec /* every coors buffer is 16-byte aligned */,
+                      const int skip /* timing experiments only: 1 no rows, 2 no records, 4 no firsts */) {
   constexpr int PT = 5;
-  __shared__ __align__(16) float stage_all[kExpWarps * 32 * PT * C];
+  constexpr int W = PT * C;  // output words per voxel
+  __shared__ uint32_t eff_all[kExpWarps * 32 * PT];  // point index of (voxel, slot), kEmpty if absent
+  __shared__ __align__(16) int32_t coor_all[kExpWarps * 96];  // (z, y, x) of a tile: one coalesced store
   const int f = blockIdx.y;
   if (pf_dist > 0 && f + pf_dist < frames && threadIdx.x < 32) {  // see hvb_expand_pipe_kernel
     const HvFrame& nf = batch.f[f + pf_dist];
@@ -972,19 +1093,19 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   const HvFrame& fr = batch.f[f];
   const int m = voxel_num[f];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float* stage = stage_all + wid * (32 * PT * C);
+  uint32_t* eff = eff_all + wid * (32 * PT);
+  int32_t* cstage = coor_all + wid * 96;
   const uint32_t* __restrict__ firsts = w.firsts(f);
   const uint4* __restrict__ rec = w.rec(f);
   const float* __restrict__ pts = fr.pts;
-  float* st = stage + lane * (PT * C);
   const int vbase = (blockIdx.x * kExpWarps + wid) * (kPipeTiles * 32);
   if (vbase >= m) return;  // warp-uniform
 
-  auto load_first = [&](int v0) { return v0 + lane < m ? __ldg(firsts + v0 + lane) : kEmpty; };
+  auto load_first = [&](int v0) { return v0 + lane < m ? ((skip & 4) ? (uint32_t)(v0 + lane) : __ldg(firsts + v0 + lane)) : kEmpty; };
   uint32_t fi_cur = load_first(vbase);
   uint32_t fi_nxt = load_first(vbase + 32);
   uint4 ra_cur = make_uint4(0u, 0u, kEmpty, kEmpty), rb_cur = make_uint4(kEmpty, kEmpty, 0u, 0u);
-  if (fi_cur != kEmpty) {
+  if (fi_cur != kEmpty && !(skip & 2)) {
     ra_cur = __ldg(rec + 2 * (size_t)fi_cur);
     rb_cur = __ldg(rec + 2 * (size_t)fi_cur + 1);
   }
@@ -995,71 +1116,58 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     if (v0 >= m) break;  // warp-uniform
     const int nvox = min(32, m - v0);
     const uint32_t len = min(ra_cur.y, (uint32_t)PT);  // 0 for lanes past the end
-    uint32_t idx[PT];
-    idx[0] = fi_cur;
-    idx[1] = ra_cur.z; idx[2] = ra_cur.w; idx[3] = rb_cur.x; idx[4] = rb_cur.y;
-    // rows of this tile
-    float4 qa[PT], qb[PT];
+    eff[lane * PT + 0] = len > 0u ? fi_cur : kEmpty;
+    eff[lane * PT + 1] = len > 1u ? ra_cur.z : kEmpty;
+    eff[lane * PT + 2] = len > 2u ? ra_cur.w : kEmpty;
+    eff[lane * PT + 3] = len > 3u ? rb_cur.x : kEmpty;
+    eff[lane * PT + 4] = len > 4u ? rb_cur.y : kEmpty;
+    if (lane < nvox) {  // coordinates and count of this tile's voxels
+      const uint32_t cz = div_small_err(ra_cur.x, kd.plane, kd.m_plane);
+      const uint32_t rem = ra_cur.x - cz * kd.plane;
+      const uint32_t cy = div_small_err(rem, kd.gx, kd.m_gx);
+      cstage[lane * 3 + 0] = (int32_t)cz;
+      cstage[lane * 3 + 1] = (int32_t)cy;
+      cstage[lane * 3 + 2] = (int32_t)(rem - cy * kd.gx);
+      fr.num[v0 + lane] = (int32_t)len;
+    }
+    __syncwarp();
+    // rows of this tile, lane = output word
+    float val[W];
 #pragma unroll
-    for (int j = 0; j < PT; ++j) {
-      qa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      qb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((uint32_t)j < len) {
-        if (C == 4) {
-          qa[j] = __ldg(reinterpret_cast<const float4*>(pts) + idx[j]);
-        } else {
-          // words [5 idx, 5 idx + 5) lie inside the two aligned 16-byte chunks starting at word
-          // (5 idx) & ~3; both chunks hold a word of the row, so both are inside the allocation
-          const uint32_t w0 = idx[j] * 5u;
-          const float4* p4 = reinterpret_cast<const float4*>(pts) + (w0 >> 2);
-          qa[j] = __ldg(p4);
-          qb[j] = __ldg(p4 + 1);
-        }
-      }
+    for (int k = 0; k < W; ++k) {
+      const uint32_t ow = (uint32_t)lane + 32u * (uint32_t)k;     // < 32 W <= 800
+      const uint32_t q = C == 4 ? ow >> 2 : (ow * 205u) >> 10;    // ow / 5 for ow < 1024
+      const uint32_t comp = ow - q * (uint32_t)C;
+      const uint32_t idx = eff[q];
+      val[k] = 0.0f;
+      if (idx != kEmpty && !(skip & 1)) val[k] = __ldg(pts + (size_t)idx * C + comp);
     }
     // records of the next tile, first-point indices of the one after
     uint4 ra_nxt = make_uint4(0u, 0u, kEmpty, kEmpty), rb_nxt = make_uint4(kEmpty, kEmpty, 0u, 0u);
-    if (fi_nxt != kEmpty) {
+    if (fi_nxt != kEmpty && !(skip & 2)) {
       ra_nxt = __ldg(rec + 2 * (size_t)fi_nxt);
       rb_nxt = __ldg(rec + 2 * (size_t)fi_nxt + 1);
     }
     const uint32_t fi_nn = load_first(v0 + 64);
-    // coordinates and count of this tile's voxels
-    if (lane < nvox) {
-      const uint32_t cz = div_small_err(ra_cur.x, kd.plane, kd.m_plane);
-      const uint32_t rem = ra_cur.x - cz * kd.plane;
-      const uint32_t cy = div_small_err(rem, kd.gx, kd.m_gx);
-      int32_t* co = fr.coors + (uint32_t)(v0 + lane) * 3u;
-      co[0] = (int32_t)cz;
-      co[1] = (int32_t)cy;
-      co[2] = (int32_t)(rem - cy * kd.gx);
-      fr.num[v0 + lane] = (int32_t)len;
-    }
+    float* __restrict__ dst = fr.voxels + (size_t)v0 * W;
+    if (nvox == 32) {
 #pragma unroll
-    for (int j = 0; j < PT; ++j) {
-      if (C == 4) {
-        *reinterpret_cast<float4*>(st + j * 4) = qa[j];
+      for (int k = 0; k < W; ++k) __stcs(dst + lane + 32 * k, val[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < W; ++k)
+        if (lane + 32 * k < nvox * W) __stcs(dst + lane + 32 * k, val[k]);
+    }
+    {  // coordinates: 3 * nvox words, contiguous; v0 % 32 == 0 keeps the run 16-byte aligned
+      int32_t* __restrict__ cdst = fr.coors + (size_t)v0 * 3;
+      const int cw = nvox * 3;
+      if (coors_vec) {
+        if (lane < (cw >> 2)) reinterpret_cast<int4*>(cdst)[lane] = reinterpret_cast<const int4*>(cstage)[lane];
+        if (lane < (cw & 3)) cdst[(cw & ~3) + lane] = cstage[(cw & ~3) + lane];
       } else {
-        const float4 a = qa[j], b = qb[j];
-        const uint32_t o = (idx[j] * 5u) & 3u;  // absent rows are all zeros whatever o is
-        const bool o1 = o & 1u, o2 = o & 2u;
-        const float t0 = o1 ? a.y : a.x, t1 = o1 ? a.z : a.y, t2 = o1 ? a.w : a.z, t3 = o1 ? b.x : a.w;
-        const float t4 = o1 ? b.y : b.x, t5 = o1 ? b.z : b.y, t6 = o1 ? b.w : b.z;
-        st[j * C + 0] = o2 ? t2 : t0;
-        st[j * C + 1] = o2 ? t3 : t1;
-        st[j * C + 2] = o2 ? t4 : t2;
-        st[j * C + 3] = o2 ? t5 : t3;
-        st[j * C + 4 % C] = o2 ? t6 : t4;
+        for (int i = lane; i < cw; i += 32) cdst[i] = cstage[i];
       }
     }
-    __syncwarp();
-    const uint32_t w0 = (uint32_t)v0 * (PT * C);  // % 4 == 0 because v0 % 32 == 0
-    float* __restrict__ dst = fr.voxels + w0;
-    const int nwords = nvox * (PT * C);
-    const int n4 = nwords >> 2;
-    for (int i = lane; i < n4; i += 32)
-      __stcs(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(stage)[i]);
-    for (int i = (n4 << 2) + lane; i < nwords; i += 32) dst[i] = stage[i];
     __syncwarp();
     fi_cur = fi_nxt;
     fi_nxt = fi_nn;
@@ -1194,10 +1302,14 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
                                      (int)p.smem_bucket));
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)p.smem_bucket));
+  PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2)));
   const int pe = std::max(max_points, 1);
   int vec_ok = 1;  // float4 tile stream / vector row loads need 16-byte aligned buffers
   for (int k = 0; k < num_frames && vec_ok; ++k)
     vec_ok = !(((uintptr_t)frames[k].voxels & 15) || ((uintptr_t)frames[k].points & 15));
+  int coors_vec = 1;
+  for (int k = 0; k < num_frames && coors_vec; ++k) coors_vec = !((uintptr_t)frames[k].coors & 15);
 
   int wave_idx = 0;
   for (int f0 = 0; f0 < num_frames; f0 += wave, ++wave_idx) {
@@ -1229,14 +1341,19 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     }
     // P == 5 with 16-byte aligned rows: the record-at-first-point variant (no order pass)
     const bool use_rec = max_points == 5 && (c == 4 || c == 5) && vec_ok && max_voxels < (1 << 24) &&
-                         g_opt_bucket_variant == 0;
+                         g_opt_bucket_variant != 1;
     int rc = PCFE_OK;
     if (use_rec) {
       {
         ProfScope ps("hvb_bucket", st);
         const dim3 grid((unsigned)p.nb, (unsigned)wv);
-        const size_t smem_small = (size_t)(2 * p.slots + p.cap) * 4 + (size_t)(2 * p.cap) * 2;
-        hvb_bucket_small_kernel<5, true><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
+        const size_t smem_rec = (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2;
+        if (g_opt_bucket_variant == 2) {
+          const size_t smem_small = (size_t)(2 * p.slots + p.cap) * 4 + (size_t)(2 * p.cap) * 2;
+          hvb_bucket_small_kernel<5, true><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
+        } else {
+          hvb_bucket_rec_kernel<<<grid, kBucketThreads, smem_rec, st>>>(w, pe);
+        }
         PCFE_LAUNCH_CHECK();
       }
       {
@@ -1255,8 +1372,8 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         const int pper = kExpWarps * kPipeTiles * 32;
         const dim3 pgrid((unsigned)((vmax + pper - 1) / pper), (unsigned)wv);
         const int32_t* vn = voxel_num + f0;
-        if (c == 4) hvb_expand_rec_kernel<4><<<pgrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch);
-        else hvb_expand_rec_kernel<5><<<pgrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch);
+        if (c == 4) hvb_expand_rec_kernel<4><<<pgrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip);
+        else hvb_expand_rec_kernel<5><<<pgrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip);
         PCFE_LAUNCH_CHECK();
       }
     } else {
