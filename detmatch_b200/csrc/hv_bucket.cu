@@ -49,6 +49,7 @@ int g_opt_no_fast_div = 0;      // 1: __fdiv_rn for every point (no hoisted reci
 int g_opt_expand_variant = 0;  // 1: un-pipelined fixed-P expansion kernel
 int g_opt_expand_skip = 0;      // timing experiments only (wrong output)
 int g_opt_expand_prefetch = 1;
+int g_opt_expand_ctas = 0;      // > 0: persistent expansion with this many CTAs per SM
 int g_opt_expand_pad_kb = 0;    // experiment: extra dynamic smem per expansion CTA (limits its occupancy)  // frames of L2 prefetch distance in the pipelined expansion (0 = off)
 
 namespace {
@@ -456,10 +457,13 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
           sorted[t] = lo;
         }
       }
-      const uint32_t len = min(cnt, (uint32_t)pe);
       const uint32_t first = sorted[0];
-      rec[2 * (size_t)first] = make_uint4(hkey[s], len, sorted[1 % PT], sorted[2 % PT]);
-      rec[2 * (size_t)first + 1] = make_uint4(sorted[3 % PT], sorted[4 % PT], 0u, 0u);
+      const uint32_t i1 = (cnt > 1u && pe > 1) ? sorted[1 % PT] : 0xFFFFFFu;
+      const uint32_t i2 = (cnt > 2u && pe > 2) ? sorted[2 % PT] : 0xFFFFFFu;
+      const uint32_t i3 = (cnt > 3u && pe > 3) ? sorted[3 % PT] : 0xFFFFFFu;
+      const uint32_t i4 = (cnt > 4u && pe > 4) ? sorted[4 % PT] : 0xFFFFFFu;
+      rec[2 * (size_t)first] = make_uint4(hkey[s], i1 | (i4 << 24), i2 | ((i4 >> 8) << 24), i3 | ((i4 >> 16) << 24));
+      rec[2 * (size_t)first + 1] = make_uint4(0u, 0u, 0u, 0u);
       atomicOr(&bitmask[first >> 5], 1u << (first & 31));
     }
     return;
@@ -540,9 +544,11 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
 //     loads exposed a DRAM/L2 latency per loop trip: 18 % of all stall samples);
 //   * one CAS per probe (claims the slot, finds the cell or reports a collision) and a hand-written
 //     warp-aggregated append to the cell list;
-//   * every cell leaves as one 32-byte record at rec[first point]: no lists, cursors or block scan.
+//   * every cell leaves as one 16-byte record at rec[first point]: no lists, cursors or block scan.
 // dynamic shared memory: ents[cap] (uint2) | hkey[S] | head[S] | enext[cap] (u16) | slotlist[cap] (u16)
 // ------------------------------------------------------------------------------------------
+constexpr uint32_t kRecNone = 0xFFFFFFu;  // 24-bit "no point" in a packed record
+
 __global__ void __launch_bounds__(kBucketThreads)
 hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */) {
   constexpr int PT = 5;
@@ -551,7 +557,10 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */) {
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t s_nclaimed;
 
-  const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
+  // frames in REVERSE launch order: the bin kernel wrote the entries of the last frames most
+  // recently (still in L2), and the records this kernel writes last (first frames) are the ones
+  // the expansion reads first
+  const int f = (int)(gridDim.y - 1u - blockIdx.y), b = blockIdx.x, tid = threadIdx.x;
   const uint32_t* ctl = w.ctl(f);
   if (ctl[w.nb + kCtlOverflow]) return;
   const int S = w.slots, cap = w.cap;
@@ -633,10 +642,18 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */) {
         sorted[t] = lo;
       }
     }
-    const uint32_t len = min(cnt, (uint32_t)pe);
+    // rec[first] = {key, idx1 | idx4[7:0] << 24, idx2 | idx4[15:8] << 24, idx3 | idx4[23:16] << 24}:
+    // 24-bit point indices (n < 2^24 - 1 on this path), 0xFFFFFF = no point; slots >= pe stay empty
     const uint32_t first = sorted[0];
-    rec[2 * (size_t)first] = make_uint4(hkey[s], len, sorted[1], sorted[2]);
-    rec[2 * (size_t)first + 1] = make_uint4(sorted[3], sorted[4], 0u, 0u);
+    const uint32_t i1 = (cnt > 1u && pe > 1) ? sorted[1] : kRecNone;
+    const uint32_t i2 = (cnt > 2u && pe > 2) ? sorted[2] : kRecNone;
+    const uint32_t i3 = (cnt > 3u && pe > 3) ? sorted[3] : kRecNone;
+    const uint32_t i4 = (cnt > 4u && pe > 4) ? sorted[4] : kRecNone;
+    // the record owns a whole 32-byte sector (second half unused): the two stores leave the SM as
+    // one full-sector write; a lone 16-byte store is a partial-sector L2 write (measured: +12 %
+    // kernel time)
+    rec[2 * (size_t)first] = make_uint4(hkey[s], i1 | (i4 << 24), i2 | ((i4 >> 8) << 24), i3 | ((i4 >> 16) << 24));
+    rec[2 * (size_t)first + 1] = make_uint4(0u, 0u, 0u, 0u);
     atomicOr(&bitmask[first >> 5], 1u << (first & 31));
   }
 }
@@ -1073,54 +1090,58 @@ __global__ void __launch_bounds__(kExpThreads, PCFE_EXP_REC_MINB)
 hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const KeyDecode kd,
                       const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist,
                       const int coors_vec /* every coors buffer is 16-byte aligned */,
-                      const int skip /* timing experiments only: 1 no rows, 2 no records, 4 no firsts */) {
+                      const int skip /* timing experiments only: 1 no rows, 2 no records, 4 no firsts */,
+                      const int tiles_x /* CTA-tiles per frame; the 1-D grid strides over tiles_x * frames */) {
   constexpr int PT = 5;
   constexpr int W = PT * C;  // output words per voxel
   __shared__ uint32_t eff_all[kExpWarps * 32 * PT];  // point index of (voxel, slot), kEmpty if absent
   __shared__ __align__(16) int32_t coor_all[kExpWarps * 96];  // (z, y, x) of a tile: one coalesced store
-  const int f = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t* eff = eff_all + wid * (32 * PT);
+  int32_t* cstage = coor_all + wid * 96;
+#pragma unroll 1
+  for (int wi = blockIdx.x; wi < tiles_x * frames; wi += gridDim.x) {
+  const int f = wi / tiles_x, bx = wi - f * tiles_x;
   if (pf_dist > 0 && f + pf_dist < frames && threadIdx.x < 32) {  // see hvb_expand_pipe_kernel
     const HvFrame& nf = batch.f[f + pf_dist];
     const size_t total = ((size_t)nf.n * C * 4) & ~(size_t)15;
-    const size_t slice = ((total + gridDim.x - 1) / gridDim.x + 511) & ~(size_t)511;
-    const size_t lo = (size_t)blockIdx.x * slice + (size_t)threadIdx.x * (slice / 32);
+    const size_t slice = ((total + tiles_x - 1) / tiles_x + 511) & ~(size_t)511;
+    const size_t lo = (size_t)bx * slice + (size_t)threadIdx.x * (slice / 32);
     if (lo < total) {
       const uint32_t bytes = (uint32_t)min(slice / 32, total - lo);
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(nf.pts) + lo), "r"(bytes) : "memory");
     }
   }
-  if (w.ctl(f)[w.nb + kCtlOverflow]) return;
+  if (w.ctl(f)[w.nb + kCtlOverflow]) continue;
   const HvFrame& fr = batch.f[f];
   const int m = voxel_num[f];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t* eff = eff_all + wid * (32 * PT);
-  int32_t* cstage = coor_all + wid * 96;
   const uint32_t* __restrict__ firsts = w.firsts(f);
   const uint4* __restrict__ rec = w.rec(f);
   const float* __restrict__ pts = fr.pts;
-  const int vbase = (blockIdx.x * kExpWarps + wid) * (kPipeTiles * 32);
-  if (vbase >= m) return;  // warp-uniform
+  const int vbase = (bx * kExpWarps + wid) * (kPipeTiles * 32);
+  if (vbase >= m) continue;  // warp-uniform
 
   auto load_first = [&](int v0) { return v0 + lane < m ? ((skip & 4) ? (uint32_t)(v0 + lane) : __ldg(firsts + v0 + lane)) : kEmpty; };
   uint32_t fi_cur = load_first(vbase);
   uint32_t fi_nxt = load_first(vbase + 32);
-  uint4 ra_cur = make_uint4(0u, 0u, kEmpty, kEmpty), rb_cur = make_uint4(kEmpty, kEmpty, 0u, 0u);
-  if (fi_cur != kEmpty && !(skip & 2)) {
-    ra_cur = __ldg(rec + 2 * (size_t)fi_cur);
-    rb_cur = __ldg(rec + 2 * (size_t)fi_cur + 1);
-  }
+  const uint4 rec_none = make_uint4(0u, kEmpty, kEmpty, kEmpty);  // no points besides the first
+  uint4 ra_cur = rec_none;
+  if (fi_cur != kEmpty && !(skip & 2)) ra_cur = __ldg(rec + 2 * (size_t)fi_cur);
 
 #pragma unroll 1
   for (int it = 0; it < kPipeTiles; ++it) {
     const int v0 = vbase + it * 32;
     if (v0 >= m) break;  // warp-uniform
     const int nvox = min(32, m - v0);
-    const uint32_t len = min(ra_cur.y, (uint32_t)PT);  // 0 for lanes past the end
-    eff[lane * PT + 0] = len > 0u ? fi_cur : kEmpty;
-    eff[lane * PT + 1] = len > 1u ? ra_cur.z : kEmpty;
-    eff[lane * PT + 2] = len > 2u ? ra_cur.w : kEmpty;
-    eff[lane * PT + 3] = len > 3u ? rb_cur.x : kEmpty;
-    eff[lane * PT + 4] = len > 4u ? rb_cur.y : kEmpty;
+    // unpack {key, idx1 | idx4[7:0] << 24, idx2 | idx4[15:8] << 24, idx3 | idx4[23:16] << 24}
+    const uint32_t i1 = ra_cur.y & 0xFFFFFFu, i2 = ra_cur.z & 0xFFFFFFu, i3 = ra_cur.w & 0xFFFFFFu;
+    const uint32_t i4 = (ra_cur.y >> 24) | ((ra_cur.z >> 24) << 8) | ((ra_cur.w >> 24) << 16);
+    const uint32_t len = (fi_cur != kEmpty) + (i1 != 0xFFFFFFu) + (i2 != 0xFFFFFFu) + (i3 != 0xFFFFFFu) + (i4 != 0xFFFFFFu);
+    eff[lane * PT + 0] = fi_cur;  // kEmpty for lanes past the end
+    eff[lane * PT + 1] = i1 != 0xFFFFFFu ? i1 : kEmpty;
+    eff[lane * PT + 2] = i2 != 0xFFFFFFu ? i2 : kEmpty;
+    eff[lane * PT + 3] = i3 != 0xFFFFFFu ? i3 : kEmpty;
+    eff[lane * PT + 4] = i4 != 0xFFFFFFu ? i4 : kEmpty;
     if (lane < nvox) {  // coordinates and count of this tile's voxels
       const uint32_t cz = div_small_err(ra_cur.x, kd.plane, kd.m_plane);
       const uint32_t rem = ra_cur.x - cz * kd.plane;
@@ -1143,11 +1164,8 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
       if (idx != kEmpty && !(skip & 1)) val[k] = __ldg(pts + (size_t)idx * C + comp);
     }
     // records of the next tile, first-point indices of the one after
-    uint4 ra_nxt = make_uint4(0u, 0u, kEmpty, kEmpty), rb_nxt = make_uint4(kEmpty, kEmpty, 0u, 0u);
-    if (fi_nxt != kEmpty && !(skip & 2)) {
-      ra_nxt = __ldg(rec + 2 * (size_t)fi_nxt);
-      rb_nxt = __ldg(rec + 2 * (size_t)fi_nxt + 1);
-    }
+    uint4 ra_nxt = rec_none;
+    if (fi_nxt != kEmpty && !(skip & 2)) ra_nxt = __ldg(rec + 2 * (size_t)fi_nxt);
     const uint32_t fi_nn = load_first(v0 + 64);
     float* __restrict__ dst = fr.voxels + (size_t)v0 * W;
     if (nvox == 32) {
@@ -1172,7 +1190,8 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     fi_cur = fi_nxt;
     fi_nxt = fi_nn;
     ra_cur = ra_nxt;
-    rb_cur = rb_nxt;
+  }
+  __syncwarp();
   }
 }
 
@@ -1340,7 +1359,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       PCFE_LAUNCH_CHECK();
     }
     // P == 5 with 16-byte aligned rows: the record-at-first-point variant (no order pass)
-    const bool use_rec = max_points == 5 && (c == 4 || c == 5) && vec_ok && max_voxels < (1 << 24) &&
+    const bool use_rec = max_points == 5 && (c == 4 || c == 5) && vec_ok && max_voxels < (1 << 24) && wn_max < 0xFFFFFF &&
                          g_opt_bucket_variant != 1;
     int rc = PCFE_OK;
     if (use_rec) {
@@ -1372,8 +1391,11 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         const int pper = kExpWarps * kPipeTiles * 32;
         const dim3 pgrid((unsigned)((vmax + pper - 1) / pper), (unsigned)wv);
         const int32_t* vn = voxel_num + f0;
-        if (c == 4) hvb_expand_rec_kernel<4><<<pgrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip);
-        else hvb_expand_rec_kernel<5><<<pgrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip);
+        const int tiles_x = (int)pgrid.x;
+        unsigned egrid = pgrid.x * pgrid.y;
+        if (g_opt_expand_ctas > 0) egrid = std::min<unsigned>(egrid, (unsigned)(g_opt_expand_ctas * 148));
+        if (c == 4) hvb_expand_rec_kernel<4><<<egrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x);
+        else hvb_expand_rec_kernel<5><<<egrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x);
         PCFE_LAUNCH_CHECK();
       }
     } else {
