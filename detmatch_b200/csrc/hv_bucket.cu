@@ -545,16 +545,16 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
 //   * one CAS per probe (claims the slot, finds the cell or reports a collision) and a hand-written
 //     warp-aggregated append to the cell list;
 //   * every cell leaves as one 16-byte record at rec[first point]: no lists, cursors or block scan.
-// dynamic shared memory: ents[cap] (uint2) | hkey[S] | head[S] | enext[cap] (u16) | slotlist[cap] (u16)
+// dynamic shared memory: ents[cap] (uint2) | hkey[S] | head[S] | slotlist[cap] (u16)
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kRecNone = 0xFFFFFFu;  // 24-bit "no point" in a packed record
 
 __global__ void __launch_bounds__(kBucketThreads)
-hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */) {
+hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const int spec /* entries copied before ne is known */) {
   constexpr int PT = 5;
-  constexpr uint32_t kNil = 0xFFFFu;
+  constexpr uint32_t kNil = 0xFFFFFFFFu;
   extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar[2];
   __shared__ uint32_t s_nclaimed;
 
   // frames in REVERSE launch order: the bin kernel wrote the entries of the last frames most
@@ -562,29 +562,40 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */) {
   // the expansion reads first
   const int f = (int)(gridDim.y - 1u - blockIdx.y), b = blockIdx.x, tid = threadIdx.x;
   const uint32_t* ctl = w.ctl(f);
-  if (ctl[w.nb + kCtlOverflow]) return;
-  const int S = w.slots, cap = w.cap;
-  uint2* ents = reinterpret_cast<uint2*>(smem);
+  const int cap = w.cap;
+  uint2* ents = reinterpret_cast<uint2*>(smem);  // {key, point}; .x becomes the chain link once inserted
   uint32_t* hkey = smem + 2 * cap;
-  uint32_t* head = hkey + S;
-  uint16_t* enext = reinterpret_cast<uint16_t*>(head + S);
-  uint16_t* slotlist = enext + cap;
-
-  const int ne = (int)min(ctl[b], (uint32_t)cap);
-  if (ne == 0) return;
+  const uint2* gent = w.ent(f) + (size_t)b * cap;
+  // the first `spec` entries are requested before the bucket's fill count has arrived (one global
+  // latency instead of two in front of the insert loop); the rest, if any, follows
   if (tid == 0) {
-    mbar_init(&bar, 1);
-    const uint32_t bytes = (uint32_t)((ne + 1) & ~1) * 8u;  // 16-byte granules; cap is even
-    mbar_expect_tx(&bar, bytes);
-    bulk_g2s(ents, w.ent(f) + (size_t)b * cap, bytes, &bar);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_expect_tx(&bar[0], (uint32_t)spec * 8u);
+    bulk_g2s(ents, gent, (uint32_t)spec * 8u, &bar[0]);
     s_nclaimed = 0u;
+  }
+  const uint32_t overflow = ctl[w.nb + kCtlOverflow];
+  const int ne = (int)min(ctl[b], (uint32_t)cap);
+  // table size for THIS bucket: a power of two >= 1.25 ne (the plan's `slots` covers ne == cap)
+  int S = 64;
+  while (S < ne + (ne >> 2)) S <<= 1;
+  S = min(S, w.slots);
+  uint32_t* head = hkey + S;
+  uint16_t* slotlist = reinterpret_cast<uint16_t*>(hkey + 2 * w.slots);
+  if (tid == 0 && ne > spec) {
+    const uint32_t bytes = (uint32_t)(((ne - spec) + 1) & ~1) * 8u;  // 16-byte granules; cap and spec are even
+    mbar_expect_tx(&bar[1], bytes);
+    bulk_g2s(ents + spec, gent + spec, bytes, &bar[1]);
   }
   {
     uint4* k4 = reinterpret_cast<uint4*>(hkey);  // hkey and head are contiguous: 2 * S words
     for (int s = tid; s < S / 2; s += kBucketThreads) k4[s] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
   }
-  __syncthreads();  // table initialised, barrier initialised
-  mbar_wait(&bar, 0);
+  __syncthreads();  // table and barriers initialised
+  mbar_wait(&bar[0], 0);  // always: the copy must not outlive the CTA's shared memory
+  if (overflow || ne == 0) return;
+  if (ne > spec) mbar_wait(&bar[1], 0);
 
   const uint32_t smask = (uint32_t)S - 1u;
   const int sshift = 32 - w.log2_nb - w.log2_slots;
@@ -597,7 +608,7 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */) {
     uint32_t s = ((key * kGold) >> sshift) & smask;
     bool claimed = false;
     if (valid) {
-      while (true) {
+      while (true) {  // one CAS per probe: claims the slot, finds the cell, or reports a collision
         const uint32_t old = atomicCAS(&hkey[s], kEmpty, key);
         claimed = old == kEmpty;
         if (claimed || old == key) break;
@@ -605,7 +616,7 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */) {
       }
     }
     const uint32_t cm = __ballot_sync(0xFFFFFFFFu, claimed);
-    if (cm) {
+    if (cm) {  // claimed slots join the cell list: one shared-memory atomic per warp
       const uint32_t leader = (uint32_t)__ffs(cm) - 1u;
       uint32_t base = 0;
       if (lane == leader)
@@ -613,10 +624,7 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */) {
       base = __shfl_sync(0xFFFFFFFFu, base, leader);
       if (claimed) slotlist[base + __popc(cm & lane_lt)] = (uint16_t)s;
     }
-    if (valid) {
-      const uint32_t prev = atomicExch(&head[s], (uint32_t)e);
-      enext[e] = (uint16_t)(prev == kEmpty ? kNil : prev);
-    }
+    if (valid) ents[e].x = atomicExch(&head[s], (uint32_t)e);  // link: previous head of the cell, or kNil
   }
   __syncthreads();
 
@@ -632,8 +640,9 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */) {
     uint32_t cnt = 0;
     uint32_t e = head[s];
     while (e != kNil) {  // chain walk; the 5 smallest point indices stay in registers, ascending
-      uint32_t v = ents[e].y;
-      e = enext[e];
+      const uint2 en = ents[e];
+      uint32_t v = en.y;
+      e = en.x;
       ++cnt;
 #pragma unroll
       for (int t = 0; t < PT; ++t) {
@@ -1366,12 +1375,15 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       {
         ProfScope ps("hvb_bucket", st);
         const dim3 grid((unsigned)p.nb, (unsigned)wv);
-        const size_t smem_rec = (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2;
+        const size_t smem_rec = (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)p.cap * 2;
+        // speculative first copy: the average bucket fill of the largest frame, rounded up to 64
+        // entries, never more than the region
+        const int spec = (int)std::min<int64_t>(p.cap, (((wn_max + p.nb - 1) / p.nb) + 63) / 64 * 64);
         if (g_opt_bucket_variant == 2) {
           const size_t smem_small = (size_t)(2 * p.slots + p.cap) * 4 + (size_t)(2 * p.cap) * 2;
           hvb_bucket_small_kernel<5, true><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
         } else {
-          hvb_bucket_rec_kernel<<<grid, kBucketThreads, smem_rec, st>>>(w, pe);
+          hvb_bucket_rec_kernel<<<grid, kBucketThreads, smem_rec, st>>>(w, pe, spec);
         }
         PCFE_LAUNCH_CHECK();
       }
