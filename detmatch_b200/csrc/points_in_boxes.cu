@@ -114,8 +114,19 @@ struct __align__(16) PBox {
 };
 static_assert(sizeof(PBox) == 32, "PBox must be 32 bytes");
 
+// Conservative reject data: a point with |x - cx| > r or |y - cy| > r is outside whatever the
+// rotation.  r = 1.0001 * sqrt(hl^2 + hw^2) rounded up: an inside point has computed
+// lx^2 + ly^2 < hl^2 + hw^2, and the float rotation changes the norm of (sx, sy) by less than 1e-6
+// relative, so |sx| > r or |sy| > r implies the exact test fails.  NaN compares false (no reject),
+// r = NaN / Inf never rejects: the exact test decides.  99.5 % of the point-box pairs of a LiDAR
+// frame are rejected with 2 subtractions and 2 comparisons instead of the 20-instruction test.
+struct __align__(16) RBox {
+  float cx, cy, r, pad;
+};
+static_assert(sizeof(RBox) == 16, "RBox must be 16 bytes");
+
 __global__ void pib_prepare_kernel(const float* __restrict__ boxes, int64_t nboxes,
-                                   PBox* __restrict__ out) {
+                                   PBox* __restrict__ out, RBox* __restrict__ rout) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nboxes) return;
   const float* b = boxes + i * 7;
@@ -137,6 +148,18 @@ __global__ void pib_prepare_kernel(const float* __restrict__ boxes, int64_t nbox
   p.cosa = glibc_sin_or_cos(rot, 1);
   p.sina = glibc_sin_or_cos(rot, 0);
   out[i] = p;
+  RBox r;
+  r.cx = cx;
+  r.cy = cy;
+  const double hl = (double)p.hl, hw = (double)p.hw;
+  r.r = __double2float_ru(__dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(hl, hl), __dmul_rn(hw, hw))), 1.0001));
+  r.pad = 0.0f;
+  rout[i] = r;
+}
+
+// true: the pair cannot be inside (see RBox); false: run the exact test
+__device__ __forceinline__ bool xy_reject(float x, float y, const RBox& r) {
+  return (fabsf(__fsub_rn(x, r.cx)) > r.r) | (fabsf(__fsub_rn(y, r.cy)) > r.r);
 }
 
 // points_in_boxes_cpu.cpp:25-40, float32, no contraction.
@@ -158,62 +181,84 @@ __device__ __forceinline__ int in_box(float x, float y, float z, const PBox& b) 
 // TMA bulk copy of the prepared boxes of one frame into shared memory
 // ------------------------------------------------------------------------------------------
 
-// Loads `count` prepared boxes (32 B each, 16-B aligned source) into sboxes.  All threads call.
-__device__ __forceinline__ void stage_boxes(PBox* sboxes, const PBox* gboxes, int count,
-                                            uint64_t* bar, uint32_t parity) {
+// Loads `count` prepared boxes (32 B each) and their reject records (16 B each) into shared
+// memory; 16-byte aligned sources.  All threads call.
+__device__ __forceinline__ void stage_boxes(PBox* sboxes, RBox* srej, const PBox* gboxes,
+                                            const RBox* grej, int count, uint64_t* bar, uint32_t parity) {
   if (threadIdx.x == 0) {
     const uint32_t bytes = (uint32_t)count * (uint32_t)sizeof(PBox);
-    mbar_expect_tx(bar, bytes);
+    const uint32_t rbytes = (uint32_t)count * (uint32_t)sizeof(RBox);
+    mbar_expect_tx(bar, bytes + rbytes);
     bulk_g2s(sboxes, gboxes, bytes, bar);
+    bulk_g2s(srej, grej, rbytes, bar);
   }
   mbar_wait(bar, parity);
 }
 
-constexpr int kBoxChunk = 1024;  // boxes staged per pass (32 KB of static shared memory)
+constexpr int kBoxChunk = 1024;   // boxes per frame the point-major kernel keeps in shared memory
+constexpr int kPointChunk = 512;  // boxes staged per pass by the thread-per-point kernels (24 KB static)
+constexpr int kPibThreads = 256;
 
 // ------------------------------------------------------------------------------------------
-// points_in_boxes_batch: out (b, m, t), point-major.  Thread = VEC consecutive boxes (kept in
-// registers) x a strided set of points; the T flags of one point are written by T/VEC
-// neighbouring threads as one contiguous run.
+// points_in_boxes_batch: out (b, m, t), point-major, t <= kBoxChunk.
+// Thread = one point against all t boxes (boxes broadcast from shared memory, staged by TMA): the
+// conservative xy reject keeps the exact test off 99.5 % of the pairs, the flags are collected as
+// bits (one word per 32 boxes) and staged in shared memory; then every warp writes the t int32
+// flags of each of its 32 points as contiguous 128-byte (or 512-byte, VEC4) streaming stores.
+// dynamic shared memory: PBox[t] | RBox[t] | masks[ceil(t / 32)][256]
 // ------------------------------------------------------------------------------------------
-template <int VEC>
-__global__ void __launch_bounds__(1024)
-pib_all_kernel(const PBox* __restrict__ pboxes, const float* __restrict__ points, int t,
-               long long m, int pts_per_cta, int32_t* __restrict__ out) {
+template <bool VEC4>
+__global__ void __launch_bounds__(kPibThreads)
+pib_all_kernel(const PBox* __restrict__ pboxes, const RBox* __restrict__ rboxes,
+               const float* __restrict__ points, const int t, const long long m,
+               int32_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint64_t bar;
+  __shared__ __align__(8) uint64_t bar;
   PBox* sboxes = reinterpret_cast<PBox*>(smem_raw);
-  float* spts = reinterpret_cast<float*>(smem_raw + (size_t)t * sizeof(PBox));
+  RBox* srej = reinterpret_cast<RBox*>(smem_raw + (size_t)t * sizeof(PBox));
+  uint32_t* masks = reinterpret_cast<uint32_t*>(smem_raw + (size_t)t * (sizeof(PBox) + sizeof(RBox)));
 
-  const int b = blockIdx.y;
-  const long long m0 = (long long)blockIdx.x * pts_per_cta;
-  const int npts = (int)min((long long)pts_per_cta, m - m0);
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * kPibThreads;
+  const long long p = m0 + tid;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (p < m) {
+    const float* gp = points + ((size_t)b * m + p) * 3;
+    x = __ldg(gp); y = __ldg(gp + 1); z = __ldg(gp + 2);
+  }
+  if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
-  stage_boxes(sboxes, pboxes + (size_t)b * t, t, &bar, 0);
-  const float* gp = points + ((size_t)b * m + m0) * 3;
-  for (int i = threadIdx.x; i < npts * 3; i += blockDim.x) spts[i] = __ldg(gp + i);
-  __syncthreads();
+  stage_boxes(sboxes, srej, pboxes + (size_t)b * t, rboxes + (size_t)b * t, t, &bar, 0);
 
-  const int groups = t / VEC;                 // threads per point
-  const int q = threadIdx.x % groups;         // my box group
-  const int prow = threadIdx.x / groups;      // my first point
-  const int pstep = blockDim.x / groups;      // blockDim.x is a multiple of groups
-  PBox bx[VEC];
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) bx[v] = sboxes[q * VEC + v];
-  int32_t* obase = out + ((size_t)b * m + m0) * t + (size_t)q * VEC;
-  for (int p = prow; p < npts; p += pstep) {
-    const float x = spts[p * 3], y = spts[p * 3 + 1], z = spts[p * 3 + 2];
-    int32_t r[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) r[v] = in_box(x, y, z, bx[v]);
-    int32_t* o = obase + (size_t)p * t;
-    if (VEC == 4) {
-      __stcs(reinterpret_cast<int4*>(o), make_int4(r[0], r[1], r[2], r[3]));
+  const int nw = (t + 31) >> 5;
+  for (int j = 0; j < nw; ++j) {
+    uint32_t word = 0;
+    const int kend = min(32, t - j * 32);
+#pragma unroll 8
+    for (int bit = 0; bit < kend; ++bit) {
+      const int k = j * 32 + bit;
+      if (!xy_reject(x, y, srej[k])) word |= (uint32_t)in_box(x, y, z, sboxes[k]) << bit;
+    }
+    masks[j * kPibThreads + tid] = word;
+  }
+  __syncwarp();  // a warp writes the points it tested itself
+
+  const int lane = tid & 31, wbase = tid & ~31;
+  for (int pl = 0; pl < 32; ++pl) {
+    const long long pp = m0 + wbase + pl;
+    if (pp >= m) break;  // warp-uniform
+    int32_t* __restrict__ row = out + ((size_t)b * m + pp) * t;
+    const uint32_t* mrow = masks + wbase + pl;
+    if (VEC4) {  // t % 4 == 0 and out is 16-byte aligned: lane writes flags [4 i, 4 i + 4)
+      for (int i = lane; i * 4 < t; i += 32) {
+        const uint32_t wv = mrow[(i >> 3) * kPibThreads] >> ((i & 7) * 4);
+        __stcs(reinterpret_cast<int4*>(row) + i, make_int4(wv & 1u, (wv >> 1) & 1u, (wv >> 2) & 1u, (wv >> 3) & 1u));
+      }
     } else {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) __stcs(o + v, r[v]);
+      for (int k0 = 0; k0 < t; k0 += 32) {
+        const uint32_t wv = mrow[(k0 >> 5) * kPibThreads];
+        if (k0 + lane < t) __stcs(row + k0 + lane, (int32_t)((wv >> lane) & 1u));
+      }
     }
   }
 }
@@ -223,7 +268,7 @@ pib_all_kernel(const PBox* __restrict__ pboxes, const float* __restrict__ points
 __global__ void __launch_bounds__(256)
 pib_all_generic_kernel(const PBox* __restrict__ pboxes, const float* __restrict__ points, int t,
                        long long m, int32_t* __restrict__ out) {
-  __shared__ __align__(16) PBox sboxes[kBoxChunk / 8];
+  __shared__ __align__(16) PBox sboxes[128];
   const int b = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float x = 0.f, y = 0.f, z = 0.f;
@@ -231,7 +276,7 @@ pib_all_generic_kernel(const PBox* __restrict__ pboxes, const float* __restrict_
     const float* gp = points + ((size_t)b * m + p) * 3;
     x = __ldg(gp); y = __ldg(gp + 1); z = __ldg(gp + 2);
   }
-  constexpr int chunk = kBoxChunk / 8;
+  constexpr int chunk = 128;
   for (int t0 = 0; t0 < t; t0 += chunk) {
     const int cnt = min(chunk, t - t0);
     __syncthreads();
@@ -247,14 +292,16 @@ pib_all_generic_kernel(const PBox* __restrict__ pboxes, const float* __restrict_
 // ------------------------------------------------------------------------------------------
 // points_in_boxes_gpu: out (b, m) = lowest containing box index or -1
 // points_in_boxes_cpu layout: out (t, n) box-major 0/1   (BOXMAJOR = true, b == 1)
-// Thread = one point; boxes broadcast from shared memory, staged by TMA in chunks.
+// Thread = one point; boxes broadcast from shared memory, staged by TMA in chunks; conservative
+// xy reject in front of the exact test.
 // ------------------------------------------------------------------------------------------
 template <bool BOXMAJOR>
 __global__ void __launch_bounds__(256)
-pib_point_kernel(const PBox* __restrict__ pboxes, const float* __restrict__ points, int t,
-                 long long m, int32_t* __restrict__ out) {
-  __shared__ __align__(16) PBox sboxes[kBoxChunk];
-  __shared__ uint64_t bar;
+pib_point_kernel(const PBox* __restrict__ pboxes, const RBox* __restrict__ rboxes,
+                 const float* __restrict__ points, int t, long long m, int32_t* __restrict__ out) {
+  __shared__ __align__(16) PBox sboxes[kPointChunk];
+  __shared__ __align__(16) RBox srej[kPointChunk];
+  __shared__ __align__(8) uint64_t bar;
   const int b = blockIdx.y;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float x = 0.f, y = 0.f, z = 0.f;
@@ -266,17 +313,23 @@ pib_point_kernel(const PBox* __restrict__ pboxes, const float* __restrict__ poin
   __syncthreads();
   int first = -1;
   uint32_t parity = 0;
-  for (int t0 = 0; t0 < t; t0 += kBoxChunk) {
-    const int cnt = min(kBoxChunk, t - t0);
+  for (int t0 = 0; t0 < t; t0 += kPointChunk) {
+    const int cnt = min(kPointChunk, t - t0);
     if (t0 > 0) __syncthreads();  // everyone is done with the previous chunk
-    stage_boxes(sboxes, pboxes + (size_t)b * t + t0, cnt, &bar, parity);
+    stage_boxes(sboxes, srej, pboxes + (size_t)b * t + t0, rboxes + (size_t)b * t + t0, cnt, &bar, parity);
     parity ^= 1u;
     if (p < m) {
       if (BOXMAJOR) {
-        for (int k = 0; k < cnt; ++k) __stcs(out + (size_t)(t0 + k) * m + p, in_box(x, y, z, sboxes[k]));
-      } else if (first < 0) {
+#pragma unroll 4
         for (int k = 0; k < cnt; ++k) {
-          if (in_box(x, y, z, sboxes[k])) {
+          int32_t r = 0;
+          if (!xy_reject(x, y, srej[k])) r = in_box(x, y, z, sboxes[k]);
+          __stcs(out + (size_t)(t0 + k) * m + p, r);
+        }
+      } else if (first < 0) {
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+          if (!xy_reject(x, y, srej[k]) && in_box(x, y, z, sboxes[k])) {
             first = t0 + k;  // points_in_boxes_cuda.cu:71-75: first hit wins
             break;
           }
@@ -311,8 +364,13 @@ int check_common(const float* boxes, const float* points, const int32_t* out, in
   return PCFE_OK;
 }
 
-int prepare(const float* boxes, int64_t nboxes, PBox* pb, cudaStream_t st) {
-  pib_prepare_kernel<<<(unsigned)((nboxes + 127) / 128), 128, 0, st>>>(boxes, nboxes, pb);
+// workspace layout: PBox[nboxes] | (256-byte aligned) RBox[nboxes]
+inline RBox* rbox_base(void* ws, int64_t nboxes) {
+  return reinterpret_cast<RBox*>((char*)ws + align256((size_t)nboxes * sizeof(PBox)));
+}
+
+int prepare(const float* boxes, int64_t nboxes, void* ws, cudaStream_t st) {
+  pib_prepare_kernel<<<(unsigned)((nboxes + 127) / 128), 128, 0, st>>>(boxes, nboxes, (PBox*)ws, rbox_base(ws, nboxes));
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
@@ -324,7 +382,7 @@ using namespace pcfe;
 
 extern "C" size_t pcfe_points_in_boxes_workspace_bytes(int b, int t) {
   if (b <= 0 || t <= 0) return 256;
-  return align256((size_t)b * (size_t)t * sizeof(PBox));
+  return align256((size_t)b * (size_t)t * sizeof(PBox)) + align256((size_t)b * (size_t)t * sizeof(RBox));
 }
 
 extern "C" int pcfe_points_in_boxes_part_f32(const float* boxes, const float* points, int b, int t,
@@ -342,9 +400,9 @@ extern "C" int pcfe_points_in_boxes_part_f32(const float* boxes, const float* po
     return PCFE_OK;
   }
   PBox* pb = (PBox*)ws;
-  if ((rc = prepare(boxes, (int64_t)b * t, pb, st)) != PCFE_OK) return rc;
+  if ((rc = prepare(boxes, (int64_t)b * t, ws, st)) != PCFE_OK) return rc;
   dim3 grid((unsigned)((m + 255) / 256), (unsigned)b);
-  pib_point_kernel<false><<<grid, 256, 0, st>>>(pb, points, t, (long long)m, out);
+  pib_point_kernel<false><<<grid, 256, 0, st>>>(pb, rbox_base(ws, (int64_t)b * t), points, t, (long long)m, out);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
@@ -359,9 +417,9 @@ extern "C" int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float
   PCFE_CUDA_TRY(guard.err);
   cudaStream_t st = (cudaStream_t)stream;
   PBox* pb = (PBox*)ws;
-  if ((rc = prepare(boxes, t, pb, st)) != PCFE_OK) return rc;
+  if ((rc = prepare(boxes, t, ws, st)) != PCFE_OK) return rc;
   dim3 grid((unsigned)((n + 255) / 256), 1);
-  pib_point_kernel<true><<<grid, 256, 0, st>>>(pb, points, t, (long long)n, out);
+  pib_point_kernel<true><<<grid, 256, 0, st>>>(pb, rbox_base(ws, t), points, t, (long long)n, out);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
@@ -375,25 +433,19 @@ extern "C" int pcfe_points_in_boxes_all_f32(const float* boxes, const float* poi
   PCFE_CUDA_TRY(guard.err);
   cudaStream_t st = (cudaStream_t)stream;
   PBox* pb = (PBox*)ws;
-  if ((rc = prepare(boxes, (int64_t)b * t, pb, st)) != PCFE_OK) return rc;
+  if ((rc = prepare(boxes, (int64_t)b * t, ws, st)) != PCFE_OK) return rc;
 
-  // fast path: all boxes of a frame in shared memory, VEC boxes per thread in registers
-  const bool vec4 = (t % 4 == 0) && (((uintptr_t)out & 15) == 0);
-  const int vec = vec4 ? 4 : 1;
-  const int groups = t / vec;
-  if (groups <= 1024 && t <= kBoxChunk) {
-    const int ppi = 1024 / groups;                         // points per block iteration
-    const int threads = ppi * groups;                      // <= 1024, multiple of groups
-    const int iters = 16;
-    const int pts_per_cta = ppi * iters;
-    const size_t smem = (size_t)t * sizeof(PBox) + (size_t)pts_per_cta * 3 * sizeof(float);
-    dim3 grid((unsigned)((m + pts_per_cta - 1) / pts_per_cta), (unsigned)b);
+  if (t <= kBoxChunk) {  // all boxes of a frame in shared memory
+    const bool vec4 = (t % 4 == 0) && (((uintptr_t)out & 15) == 0);
+    const size_t smem = (size_t)t * (sizeof(PBox) + sizeof(RBox)) + (size_t)((t + 31) / 32) * kPibThreads * sizeof(uint32_t);
+    dim3 grid((unsigned)((m + kPibThreads - 1) / kPibThreads), (unsigned)b);
+    const RBox* rb = rbox_base(ws, (int64_t)b * t);
     if (vec4) {
-      PCFE_CUDA_TRY(cudaFuncSetAttribute(pib_all_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      pib_all_kernel<4><<<grid, threads, smem, st>>>(pb, points, t, (long long)m, pts_per_cta, out);
+      PCFE_CUDA_TRY(cudaFuncSetAttribute(pib_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pib_all_kernel<true><<<grid, kPibThreads, smem, st>>>(pb, rb, points, t, (long long)m, out);
     } else {
-      PCFE_CUDA_TRY(cudaFuncSetAttribute(pib_all_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      pib_all_kernel<1><<<grid, threads, smem, st>>>(pb, points, t, (long long)m, pts_per_cta, out);
+      PCFE_CUDA_TRY(cudaFuncSetAttribute(pib_all_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      pib_all_kernel<false><<<grid, kPibThreads, smem, st>>>(pb, rb, points, t, (long long)m, out);
     }
     PCFE_LAUNCH_CHECK();
   } else {

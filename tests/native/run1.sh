@@ -1,3 +1,2 @@
-B="python bench.py --no-cpu-baseline --no-e2e"
-P='import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d["ms_per_step"], d["roofline"]["frac"], {k:v["ms_per_step"] for k,v in d["kernels"].items()})'
-for a in 400 512 700 1024 1400; do echo -n "bucket avg $a: "; $B --steps 100 --warmup 3 --hv-bucket-avg $a 2>&1 | tail -1 | python -c "$P"; done
+timeout 900 python -m pytest tests/test_gpu_pib.py -m gpu -x -q 2>&1 | tail -3
+python tests/native/bench_ops.py 2>&1 | grep -E "points_in_boxes"
