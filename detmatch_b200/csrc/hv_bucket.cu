@@ -667,6 +667,254 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
   }
 }
 
+// Ascending bitonic sort of N = 256 E keys held E per thread (thread t: elements t E .. t E + E - 1).
+// Comparator distances below E stay in registers, below 32 E they are warp shuffles; only the
+// remaining log2(N / (32 E)) (log2(N / (32 E)) + 1) / 2 stages go through shared memory (K, N words)
+// with block barriers -- 6 of the 55 stages for N = 1024.  All comparators point the same way: the
+// first stage of every merge pairs i with its mirror image inside the block (i ^ (kk - 1)), the
+// following ones pair i with i ^ d.
+template <int E>
+__device__ __forceinline__ void bitonic_sort_256(uint32_t (&v)[E], uint32_t* K, const int tid) {
+  constexpr int N = kBucketThreads * E;
+#pragma unroll
+  for (int kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+    for (int d = kk >> 1; d > 0; d >>= 1) {
+      const bool flip = d == (kk >> 1);
+      if (flip ? (kk <= E) : (d < E)) {  // both elements in this thread
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const int q = flip ? (r ^ (kk - 1)) : (r ^ d);
+          if (r < q) {
+            const uint32_t a = v[r], b = v[q];
+            v[r] = min(a, b);
+            v[q] = max(a, b);
+          }
+        }
+      } else if (flip ? (kk <= 32 * E) : (d < 32 * E)) {  // partner in another lane of this warp
+        const int lmask = flip ? (kk / E - 1) : (d / E);
+        const bool lower = flip ? !(tid & (kk / 2 / E)) : !(tid & (d / E));
+        uint32_t o[E];
+#pragma unroll
+        for (int r = 0; r < E; ++r) o[r] = __shfl_xor_sync(0xFFFFFFFFu, v[flip ? E - 1 - r : r], lmask);
+#pragma unroll
+        for (int r = 0; r < E; ++r) v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
+      } else {  // partner in another warp: through shared memory
+#pragma unroll
+        for (int r = 0; r < E; ++r) K[tid * E + r] = v[r];
+        __syncthreads();
+        const int pt = flip ? (tid ^ (kk / E - 1)) : (tid ^ (d / E));
+        const bool lower = tid < pt;
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+          const uint32_t o = K[pt * E + (flip ? E - 1 - r : r)];
+          v[r] = lower ? min(v[r], o) : max(v[r], o);
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// B3: general max_points (pillars: P = 64).  No chains, no atomicMin lists, nothing whose cost depends
+// on how the points are spread over the cells: every entry finds its cell's slot (one CAS per probe)
+// and bumps the cell's count; a block scan over the cells (claim order) turns the counts into
+// segment offsets; then the bucket's entries are SORTED as 32-bit keys (cell number << 21 | point
+// index) by a bitonic network in shared memory.  Sorted position - segment offset is the entry's
+// rank inside its cell: ranks < P are kept.  A 260-point pillar costs exactly as much as 260
+// one-point cells (per-entry rank counting spent 82 % of its instructions on such pillars, at 12
+// active lanes; atomicMin lists serialise on them).
+// dynamic shared memory: ents[cap] (uint2: TMA destination; once the entries are in registers the
+// same words hold the sort keys, then the output lists) | hkey[S] | hcell[S] (count, then cell
+// number) | ccnt | coff | loff | slotlist (u16 x cap each)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBucketThreads)
+hvb_bucket_rank_kernel(const HvbWork w, const int pe /* max(max_points, 1) */, const int spec,
+                       const int slots /* table allocation: power of two > cap */) {
+  constexpr int kPer = kMaxCap / kBucketThreads;  // entries per thread, at most
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t warp_sums[33];
+  __shared__ uint32_t s_nclaimed, s_list_base, s_cell_base;
+
+  const int f = (int)(gridDim.y - 1u - blockIdx.y), b = blockIdx.x, tid = threadIdx.x;
+  uint32_t* ctl = w.ctl(f);
+  const int cap = w.cap;
+  uint2* ents = reinterpret_cast<uint2*>(smem);
+  uint32_t* K = smem;  // sort keys, then the output lists (valid after pass 1)
+  uint32_t* hkey = smem + 2 * cap;
+  uint32_t* hcell = hkey + slots;
+  uint16_t* ccnt = reinterpret_cast<uint16_t*>(hcell + slots);
+  uint16_t* coff = ccnt + cap;
+  uint16_t* loff = coff + cap;
+  uint16_t* slotlist = loff + cap;
+  const uint2* gent = w.ent(f) + (size_t)b * cap;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_expect_tx(&bar[0], (uint32_t)spec * 8u);
+    bulk_g2s(ents, gent, (uint32_t)spec * 8u, &bar[0]);
+    s_nclaimed = 0u;
+  }
+  const uint32_t overflow = ctl[w.nb + kCtlOverflow];
+  const int ne = (int)min(ctl[b], (uint32_t)cap);
+  int S = 64;
+  while (S < ne + (ne >> 2)) S <<= 1;
+  S = min(S, slots);
+  if (tid == 0 && ne > spec) {
+    const uint32_t bytes = (uint32_t)(((ne - spec) + 1) & ~1) * 8u;
+    mbar_expect_tx(&bar[1], bytes);
+    bulk_g2s(ents + spec, gent + spec, bytes, &bar[1]);
+  }
+  for (int s = tid; s < S; s += kBucketThreads) {
+    hkey[s] = kEmpty;
+    hcell[s] = 0u;
+  }
+  __syncthreads();
+  mbar_wait(&bar[0], 0);  // always: the copy must not outlive the CTA's shared memory
+  if (overflow || ne == 0) return;
+  if (ne > spec) mbar_wait(&bar[1], 0);
+
+  // pass 1: slot of the entry's cell (one CAS per probe), arrival rank inside the cell
+  const uint32_t smask = (uint32_t)S - 1u;
+  const int sshift = 32 - w.log2_nb - w.log2_slots;
+  const uint32_t lane = (uint32_t)tid & 31u;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  uint32_t myidx[kPer], mysr[kPer];
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    myidx[k] = 0u;
+    mysr[k] = 0u;
+    if (k * kBucketThreads < ne) {  // block-uniform: every lane takes part in the ballot
+      const int e = k * kBucketThreads + tid;
+      const bool valid = e < ne;
+      uint2 en = make_uint2(0u, 0u);
+      if (valid) en = ents[e];
+      uint32_t s = ((en.x * kGold) >> sshift) & smask;
+      bool claimed = false;
+      if (valid) {
+        while (true) {
+          const uint32_t old = atomicCAS(&hkey[s], kEmpty, en.x);
+          claimed = old == kEmpty;
+          if (claimed || old == en.x) break;
+          s = (s + 1u) & smask;
+        }
+      }
+      const uint32_t cm = __ballot_sync(0xFFFFFFFFu, claimed);
+      if (cm) {
+        const uint32_t leader = (uint32_t)__ffs(cm) - 1u;
+        uint32_t base = 0;
+        if (lane == leader)
+          asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(smem_u32(&s_nclaimed)), "r"(__popc(cm)) : "memory");
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (claimed) slotlist[base + __popc(cm & lane_lt)] = (uint16_t)s;
+      }
+      if (valid) {
+        const uint32_t r = atomicAdd(&hcell[s], 1u);
+        myidx[k] = en.y;
+        mysr[k] = s | (r << 16);
+      }
+    }
+  }
+  __syncthreads();
+
+  // per cell, in claim order: count -> offset of its entries in the regrouped array (low half) and
+  // of its output list (high half: min(count, P) entries), both from ONE packed block scan
+  const int nv = (int)s_nclaimed;
+  uint32_t run = 0;
+#pragma unroll 1
+  for (int j0 = 0; j0 < nv; j0 += kBucketThreads) {
+    const int j = j0 + tid;
+    uint32_t cnt = 0;
+    int s = 0;
+    if (j < nv) {
+      s = slotlist[j];
+      cnt = hcell[s];
+    }
+    const uint32_t pack = (min(cnt, (uint32_t)pe) << 16) | cnt;
+    uint32_t tot;
+    const uint32_t ex = run + block_exscan(pack, warp_sums, &tot);
+    if (j < nv) {
+      ccnt[j] = (uint16_t)cnt;
+      coff[j] = (uint16_t)(ex & 0xFFFFu);
+      loff[j] = (uint16_t)(ex >> 16);
+      hcell[s] = (uint32_t)j;
+    }
+    run += tot;
+    __syncthreads();  // warp_sums is reused by the next chunk; hcell / coff visible below
+  }
+  const uint32_t total_list = run >> 16;
+  if (tid == 0) {
+    s_list_base = atomicAdd(&ctl[w.nb + kCtlList], total_list);
+    s_cell_base = atomicAdd(&ctl[w.nb + kCtlCell], (uint32_t)nv);
+  }
+
+  // pass 2: sort keys (cell number << 21 | point index), padded to a power of two with kEmpty
+  int N = kBucketThreads;
+  while (N < ne) N <<= 1;  // <= 2048 = kMaxCap words: fits the entry buffer (2 cap words, cap >= 832)
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int e = k * kBucketThreads + tid;
+    if (e < N) K[e] = e < ne ? ((hcell[mysr[k] & 0xFFFFu] << 21) | myidx[k]) : kEmpty;
+  }
+  __syncthreads();
+  const uint32_t list_base = s_list_base, cell_base = s_cell_base;
+  if (list_base + total_list > w.arena_cap || cell_base + (uint32_t)nv > w.arena_cap) {
+    if (tid == 0) ctl[w.nb + kCtlOverflow] = 1u;  // cannot happen: arenas hold one entry per point
+    return;
+  }
+  // sort: thread t takes elements t E .. t E + E - 1 (N = 256 E), see bitonic_sort_256
+  uint32_t kv[kPer];
+  const int E = N / kBucketThreads;  // 1, 2, 4 or 8 (block-uniform)
+#pragma unroll
+  for (int r = 0; r < kPer; ++r) kv[r] = r < E ? K[tid * E + r] : kEmpty;
+  __syncthreads();  // the network reuses K
+  if (E == 1) {
+    uint32_t v[1] = {kv[0]};
+    bitonic_sort_256<1>(v, K, tid);
+    kv[0] = v[0];
+  } else if (E == 2) {
+    uint32_t v[2] = {kv[0], kv[1]};
+    bitonic_sort_256<2>(v, K, tid);
+    kv[0] = v[0]; kv[1] = v[1];
+  } else if (E == 4) {
+    uint32_t v[4] = {kv[0], kv[1], kv[2], kv[3]};
+    bitonic_sort_256<4>(v, K, tid);
+    kv[0] = v[0]; kv[1] = v[1]; kv[2] = v[2]; kv[3] = v[3];
+  } else {
+    bitonic_sort_256<8>(kv, K, tid);
+  }
+  // pass 3: sorted position i of cell j is rank i - coff[j]; the first P of every cell are kept
+  // (the network's last barrier is behind us: K is free for the lists)
+#pragma unroll
+  for (int r = 0; r < kPer; ++r) {
+    const int i = tid * E + r;
+    if (r < E && i < ne) {
+      const uint32_t j = kv[r] >> 21;
+      const uint32_t rank = (uint32_t)i - coff[j];
+      if (rank < (uint32_t)pe) K[loff[j] + rank] = kv[r] & 0x1FFFFFu;
+    }
+  }
+  __syncthreads();
+
+  // emit: the CTA's lists are contiguous in shared memory in claim order, so the list arena gets
+  // one coalesced copy; every cell becomes one 16-byte record; first points are flagged
+  uint32_t* __restrict__ glst = w.lst(f) + list_base;
+  for (uint32_t i = tid; i < total_list; i += kBucketThreads) glst[i] = K[i];
+  Cell* __restrict__ cells = w.cells(f) + cell_base;
+  uint32_t* __restrict__ bitmask = w.bitmask(f);
+  for (int j = tid; j < nv; j += kBucketThreads) {
+    Cell cl;
+    cl.key = hkey[slotlist[j]];
+    cl.len = min((uint32_t)ccnt[j], (uint32_t)pe);  // >= 1: every claimed cell has a point and pe >= 1
+    cl.list_off = list_base + loff[j];
+    cl.first = K[loff[j]];  // lists are ascending: entry 0 is the cell's first point
+    cells[j] = cl;
+    atomicOr(&bitmask[cl.first >> 5], 1u << (cl.first & 31));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // D: voxel id of every cell = rank of its first point; vcell[vid] = cell
 // ------------------------------------------------------------------------------------------
@@ -1420,8 +1668,20 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         hvb_bucket_small_kernel<5><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
       else if (pe <= 8 && g_opt_bucket_variant != 1)
         hvb_bucket_small_kernel<8><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
-      else
+      else if (g_opt_bucket_variant == 1 || wn_max >= (1 << 21)) {  // sort keys hold 21-bit point indices
         hvb_bucket_kernel<<<grid, kBucketThreads, p.smem_bucket, st>>>(w, pe);
+      } else {
+        // table: the smallest power of two above cap (the plan's `slots` keeps the load under 0.8
+        // even for a full bucket of distinct cells; here a full bucket is allowed to probe longer
+        // in exchange for one more resident CTA)
+        int rslots = 64;
+        while (rslots <= p.cap) rslots <<= 1;
+        rslots = std::min(rslots, p.slots);
+        const size_t smem_rank = (size_t)p.cap * 16 + (size_t)rslots * 8;
+        const int spec = (int)std::min<int64_t>(p.cap, (((wn_max + p.nb - 1) / p.nb) + 63) / 64 * 64);
+        PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rank));
+        hvb_bucket_rank_kernel<<<grid, kBucketThreads, smem_rank, st>>>(w, pe, spec, rslots);
+      }
       PCFE_LAUNCH_CHECK();
     }
     rc = hv_launch_scan(w.zero, w.zero_stride, w.wordprefix, w.word_stride, wnpad / 32,

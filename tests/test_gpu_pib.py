@@ -75,6 +75,45 @@ def test_faces_edges_corners_and_special_values():
     _all_three(pts, bxs, "faces")
 
 
+def test_reject_margin_adversarial():
+    """The kernels skip the exact test when |x - cx| or |y - cy| exceeds 1.0001 * sqrt(hl^2 + hw^2).
+    Points are placed on the world axes through each box centre at distances swept finely around
+    that radius (where a box corner can lie), for yaws that put a corner on or next to an axis, for
+    tiny / huge / degenerate / non-finite boxes: every flag must still equal the CPU op's."""
+    rng = np.random.default_rng(20240607)
+    T = 96
+    bxs = np.zeros((T, 7), dtype=np.float32)
+    bxs[:, 0:2] = rng.uniform(-30, 30, (T, 2))
+    bxs[:, 2] = -1.0
+    bxs[:, 3] = rng.uniform(0.3, 3.0, T)      # w
+    bxs[:, 4] = rng.uniform(0.3, 6.0, T)      # l
+    bxs[:, 5] = 2.0
+    # yaw such that the corner (+hl, +hw) points along +x, +y, -x, -y (plus a little noise)
+    corner = np.arctan2(bxs[:, 3], bxs[:, 4])
+    bxs[:, 6] = (-np.pi / 2 - corner + (np.arange(T) % 4) * (np.pi / 2) + rng.normal(0, 1e-4, T)).astype(np.float32)
+    bxs[90, 3:5] = [1e-3, 2e-3]
+    bxs[91, 3:5] = [900.0, 1200.0]
+    bxs[92, 3:5] = [0.0, 2.0]
+    bxs[93, 3:5] = [-1.0, 2.0]
+    bxs[94, 3:5] = [np.nan, 2.0]
+    bxs[95, 3:5] = [np.inf, 2.0]
+    rho = np.sqrt((bxs[:, 3].astype(np.float64) / 2) ** 2 + (bxs[:, 4].astype(np.float64) / 2) ** 2)
+    rho = np.nan_to_num(rho, nan=1.0, posinf=1e6)
+    f = np.concatenate([1.0 + np.linspace(-3e-4, 3e-4, 25), [0.5, 0.999, 1.001, 2.0]])
+    pts = []
+    for k in range(T):
+        for sx, sy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+            d = (rho[k] * f).astype(np.float64)
+            p = np.zeros((len(f), 3))
+            p[:, 0] = bxs[k, 0] + sx * d
+            p[:, 1] = bxs[k, 1] + sy * d
+            p[:, 2] = 0.0
+            pts.append(p)
+    pts = np.concatenate(pts).astype(np.float32)
+    inside = _all_three(pts[None], bxs[None], "reject margin")
+    assert inside > 0
+
+
 def test_c3_frame_vs_oracle():
     """BASELINE config C3 shape: 120k points x 200 boxes (2 of the 16 frames against the oracle,
     every frame for cross-op consistency)."""
