@@ -66,7 +66,8 @@ struct HvbWork {
   size_t region_stride;  // bytes
   size_t lst_off, cells_off, vcell_off;  // byte offsets inside a frame region
   size_t rec_off, firsts_off;            // record-at-first-point variant: ent | rec | firsts
-  uint32_t* zero;        // [W] per-frame zeroed block: bitmask[words] | ctl
+  uint32_t* zero;        // [W] per-frame zeroed block: bitmask[2 * words] | ctl  (the record path keeps a
+                         // second bit per point, "its cell has more points", in 64-bit words)
   size_t zero_stride;    // words
   size_t ctl_off;        // words: ctl = bucket_cnt[nb] | list_cursor | cell_cursor | overflow
   uint32_t* wordprefix;  // [W][2 * words]  {bitmask word, exclusive popcount prefix} pairs
@@ -364,11 +365,7 @@ hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
 // the arena straight from registers: consecutive cells write consecutive ranges.
 // dynamic shared memory (words): hkey[S] | head[S] | eidx[cap] | enext[cap] (u16) | slotlist[cap] (u16)
 // ------------------------------------------------------------------------------------------
-// REC (P <= 5 only): instead of a cell record + a list in the arena, the cell is written as ONE
-// 32-byte record at the index of its first point, rec[first] = {key, len, idx1..idx4, 0, 0} (idx0 is
-// `first` itself): a full-sector write, no list offsets, no cursors, no block scan -- and no order
-// pass later, because the expansion finds the record of voxel v at rec[firsts[v]].
-template <int PT, bool REC = false>
+template <int PT>
 __global__ void __launch_bounds__(kBucketThreads)
 hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -436,38 +433,6 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
   uint32_t* __restrict__ glst = w.lst(f);
   Cell* __restrict__ cells = w.cells(f);
   uint32_t* __restrict__ bitmask = w.bitmask(f);
-  if (REC) {
-    uint4* __restrict__ rec = w.rec(f);
-#pragma unroll 1
-    for (int j = tid; j < nv; j += kBucketThreads) {
-      uint32_t sorted[PT];
-#pragma unroll
-      for (int t = 0; t < PT; ++t) sorted[t] = kEmpty;
-      const int s = slotlist[j];
-      uint32_t cnt = 0;
-      uint32_t e = head[s];
-      while (e != kNil) {  // chain walk; the P smallest indices stay in registers, ascending
-        uint32_t v = eidx[e];
-        e = enext[e];
-        ++cnt;
-#pragma unroll
-        for (int t = 0; t < PT; ++t) {
-          const uint32_t lo = min(sorted[t], v);
-          v = max(sorted[t], v);
-          sorted[t] = lo;
-        }
-      }
-      const uint32_t first = sorted[0];
-      const uint32_t i1 = (cnt > 1u && pe > 1) ? sorted[1 % PT] : 0xFFFFFFu;
-      const uint32_t i2 = (cnt > 2u && pe > 2) ? sorted[2 % PT] : 0xFFFFFFu;
-      const uint32_t i3 = (cnt > 3u && pe > 3) ? sorted[3 % PT] : 0xFFFFFFu;
-      const uint32_t i4 = (cnt > 4u && pe > 4) ? sorted[4 % PT] : 0xFFFFFFu;
-      rec[2 * (size_t)first] = make_uint4(hkey[s], i1 | (i4 << 24), i2 | ((i4 >> 8) << 24), i3 | ((i4 >> 16) << 24));
-      rec[2 * (size_t)first + 1] = make_uint4(0u, 0u, 0u, 0u);
-      atomicOr(&bitmask[first >> 5], 1u << (first & 31));
-    }
-    return;
-  }
   // kCellsPerThread cells per thread and round (cells tid, tid + T, ...): a typical bucket
   // (~370 cells) needs one round, i.e. one block scan and three barriers for the whole tail
   constexpr int kCellsPerThread = 2;
@@ -544,11 +509,10 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
 //     loads exposed a DRAM/L2 latency per loop trip: 18 % of all stall samples);
 //   * one CAS per probe (claims the slot, finds the cell or reports a collision) and a hand-written
 //     warp-aggregated append to the cell list;
-//   * every cell leaves as one 16-byte record at rec[first point]: no lists, cursors or block scan.
+//   * every cell with more than one point leaves as one record at rec[first point]: no lists,
+//     cursors or block scan.
 // dynamic shared memory: ents[cap] (uint2) | hkey[S] | head[S] | slotlist[cap] (u16)
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kRecNone = 0xFFFFFFu;  // 24-bit "no point" in a packed record
-
 __global__ void __launch_bounds__(kBucketThreads)
 hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const int spec /* entries copied before ne is known */) {
   constexpr int PT = 5;
@@ -629,7 +593,7 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
   __syncthreads();
 
   const int nv = (int)s_nclaimed;
-  uint32_t* __restrict__ bitmask = w.bitmask(f);
+  unsigned long long* __restrict__ bm64 = reinterpret_cast<unsigned long long*>(w.bitmask(f));
   uint4* __restrict__ rec = w.rec(f);
 #pragma unroll 1
   for (int j = tid; j < nv; j += kBucketThreads) {
@@ -651,19 +615,21 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
         sorted[t] = lo;
       }
     }
-    // rec[first] = {key, idx1 | idx4[7:0] << 24, idx2 | idx4[15:8] << 24, idx3 | idx4[23:16] << 24}:
-    // 24-bit point indices (n < 2^24 - 1 on this path), 0xFFFFFF = no point; slots >= pe stay empty
+    // A cell with one kept point needs no record at all: bit `first` of the low mask word says
+    // "first point of a voxel", the same bit of the high word says "the voxel has more points, see
+    // rec[first]" -- one 64-bit atomic sets both.  rec[first] = {idx1, idx2, idx3, idx4} (kEmpty =
+    // no point; slots >= pe stay empty) owns a whole 32-byte sector: the two stores leave the SM as
+    // one full-sector write (a lone 16-byte store is a partial-sector L2 write, measured +12 %).
+    // The voxel's coordinates are recomputed from its first point by the expansion.
     const uint32_t first = sorted[0];
-    const uint32_t i1 = (cnt > 1u && pe > 1) ? sorted[1] : kRecNone;
-    const uint32_t i2 = (cnt > 2u && pe > 2) ? sorted[2] : kRecNone;
-    const uint32_t i3 = (cnt > 3u && pe > 3) ? sorted[3] : kRecNone;
-    const uint32_t i4 = (cnt > 4u && pe > 4) ? sorted[4] : kRecNone;
-    // the record owns a whole 32-byte sector (second half unused): the two stores leave the SM as
-    // one full-sector write; a lone 16-byte store is a partial-sector L2 write (measured: +12 %
-    // kernel time)
-    rec[2 * (size_t)first] = make_uint4(hkey[s], i1 | (i4 << 24), i2 | ((i4 >> 8) << 24), i3 | ((i4 >> 16) << 24));
-    rec[2 * (size_t)first + 1] = make_uint4(0u, 0u, 0u, 0u);
-    atomicOr(&bitmask[first >> 5], 1u << (first & 31));
+    const bool more = cnt > 1u && pe > 1;
+    if (more) {
+      rec[2 * (size_t)first] = make_uint4(sorted[1], (cnt > 2u && pe > 2) ? sorted[2] : kEmpty,
+                                          (cnt > 3u && pe > 3) ? sorted[3] : kEmpty,
+                                          (cnt > 4u && pe > 4) ? sorted[4] : kEmpty);
+      rec[2 * (size_t)first + 1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    atomicOr(&bm64[first >> 5], (1ull << (first & 31)) | (more ? (1ull << (32 + (first & 31))) : 0ull));
   }
 }
 
@@ -1307,13 +1273,15 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
   __shared__ uint32_t stage[kFirstsThreads * 32];
   const int f = blockIdx.y, tid = threadIdx.x;
   if (w.ctl(f)[w.nb + kCtlOverflow]) return;
-  const uint32_t* __restrict__ bm = w.bitmask(f);
+  // 64-bit mask words: low half = "first point of a voxel", high half = "that voxel has more points"
+  const uint2* __restrict__ bm = reinterpret_cast<const uint2*>(w.bitmask(f));
   uint32_t* __restrict__ firsts = w.firsts(f);
   const int lo = blockIdx.x * kFirstsThreads;
   const int wd = lo + tid;
-  uint32_t bits = wd < words ? bm[wd] : 0u;
+  const uint2 mine = wd < words ? bm[wd] : make_uint2(0u, 0u);
+  uint32_t bits = mine.x;
   uint32_t sum = 0;
-  for (int i = tid; i < lo; i += kFirstsThreads) sum += __popc(bm[i]);
+  for (int i = tid; i < lo; i += kFirstsThreads) sum += __popc(bm[i].x);
   uint32_t before;
   block_exscan(sum, warp_sums, &before);
   __syncthreads();  // warp_sums is reused below
@@ -1322,7 +1290,8 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
   while (bits) {
     const int bit = __ffs(bits) - 1;
     bits &= bits - 1u;
-    stage[pos++] = (uint32_t)wd * 32u + (uint32_t)bit;
+    // firsts[v] = first point of voxel v | "has a record" << 31
+    stage[pos++] = ((uint32_t)wd * 32u + (uint32_t)bit) | (((mine.y >> bit) & 1u) << 31);
   }
   __syncthreads();
   for (uint32_t i = tid; i < total; i += kFirstsThreads)
@@ -1344,7 +1313,8 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
 #endif
 template <int C>
 __global__ void __launch_bounds__(kExpThreads, PCFE_EXP_REC_MINB)
-hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const KeyDecode kd,
+hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
+                      const int use_fast_div,
                       const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist,
                       const int coors_vec /* every coors buffer is 16-byte aligned */,
                       const int skip /* timing experiments only: 1 no rows, 2 no records, 4 no firsts */,
@@ -1378,34 +1348,36 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   const int vbase = (bx * kExpWarps + wid) * (kPipeTiles * 32);
   if (vbase >= m) continue;  // warp-uniform
 
+  // firsts[v] = first point of voxel v | (the voxel has more points: see rec[first]) << 31
   auto load_first = [&](int v0) { return v0 + lane < m ? ((skip & 4) ? (uint32_t)(v0 + lane) : __ldg(firsts + v0 + lane)) : kEmpty; };
+  auto load_rec = [&](uint32_t fi) {
+    uint4 r = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);  // no points besides the first
+    if (fi != kEmpty && (fi >> 31) && !(skip & 2)) r = __ldg(rec + 2 * (size_t)(fi & 0x7FFFFFFFu));
+    return r;
+  };
+  const FastAxes fa = make_fast_axes(g);
   uint32_t fi_cur = load_first(vbase);
   uint32_t fi_nxt = load_first(vbase + 32);
-  const uint4 rec_none = make_uint4(0u, kEmpty, kEmpty, kEmpty);  // no points besides the first
-  uint4 ra_cur = rec_none;
-  if (fi_cur != kEmpty && !(skip & 2)) ra_cur = __ldg(rec + 2 * (size_t)fi_cur);
+  uint4 ra_cur = load_rec(fi_cur);
 
 #pragma unroll 1
   for (int it = 0; it < kPipeTiles; ++it) {
     const int v0 = vbase + it * 32;
     if (v0 >= m) break;  // warp-uniform
     const int nvox = min(32, m - v0);
-    // unpack {key, idx1 | idx4[7:0] << 24, idx2 | idx4[15:8] << 24, idx3 | idx4[23:16] << 24}
-    const uint32_t i1 = ra_cur.y & 0xFFFFFFu, i2 = ra_cur.z & 0xFFFFFFu, i3 = ra_cur.w & 0xFFFFFFu;
-    const uint32_t i4 = (ra_cur.y >> 24) | ((ra_cur.z >> 24) << 8) | ((ra_cur.w >> 24) << 16);
-    const uint32_t len = (fi_cur != kEmpty) + (i1 != 0xFFFFFFu) + (i2 != 0xFFFFFFu) + (i3 != 0xFFFFFFu) + (i4 != 0xFFFFFFu);
-    eff[lane * PT + 0] = fi_cur;  // kEmpty for lanes past the end
-    eff[lane * PT + 1] = i1 != 0xFFFFFFu ? i1 : kEmpty;
-    eff[lane * PT + 2] = i2 != 0xFFFFFFu ? i2 : kEmpty;
-    eff[lane * PT + 3] = i3 != 0xFFFFFFu ? i3 : kEmpty;
-    eff[lane * PT + 4] = i4 != 0xFFFFFFu ? i4 : kEmpty;
-    if (lane < nvox) {  // coordinates and count of this tile's voxels
-      const uint32_t cz = div_small_err(ra_cur.x, kd.plane, kd.m_plane);
-      const uint32_t rem = ra_cur.x - cz * kd.plane;
-      const uint32_t cy = div_small_err(rem, kd.gx, kd.m_gx);
-      cstage[lane * 3 + 0] = (int32_t)cz;
-      cstage[lane * 3 + 1] = (int32_t)cy;
-      cstage[lane * 3 + 2] = (int32_t)(rem - cy * kd.gx);
+    const bool have = fi_cur != kEmpty;  // false for lanes past the end
+    const uint32_t first = fi_cur & 0x7FFFFFFFu;
+    const uint32_t len = (have ? 1u : 0u) + (ra_cur.x != kEmpty) + (ra_cur.y != kEmpty) + (ra_cur.z != kEmpty) + (ra_cur.w != kEmpty);
+    eff[lane * PT + 0] = have ? first : kEmpty;
+    eff[lane * PT + 1] = ra_cur.x;
+    eff[lane * PT + 2] = ra_cur.y;
+    eff[lane * PT + 3] = ra_cur.z;
+    eff[lane * PT + 4] = ra_cur.w;
+    // the voxel's coordinates are the cell of its first point (recomputed: no key is stored)
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (have) {
+      const float* __restrict__ fp = pts + (size_t)first * C;
+      px = __ldg(fp); py = __ldg(fp + 1); pz = __ldg(fp + 2);
       fr.num[v0 + lane] = (int32_t)len;
     }
     __syncwarp();
@@ -1421,9 +1393,21 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
       if (idx != kEmpty && !(skip & 1)) val[k] = __ldg(pts + (size_t)idx * C + comp);
     }
     // records of the next tile, first-point indices of the one after
-    uint4 ra_nxt = rec_none;
-    if (fi_nxt != kEmpty && !(skip & 2)) ra_nxt = __ldg(rec + 2 * (size_t)fi_nxt);
+    const uint4 ra_nxt = load_rec(fi_nxt);
     const uint32_t fi_nn = load_first(v0 + 64);
+    if (have) {  // voxelization_cpu.cpp:23-29 (the point is in range: it produced a cell key)
+      const float ax = __fsub_rn(px, g.x0), ay = __fsub_rn(py, g.y0), az = __fsub_rn(pz, g.z0);
+      float qx, qy, qz;
+      if (use_fast_div && fast_div_guard(ax) && fast_div_guard(ay) && fast_div_guard(az)) {
+        qx = fast_div(ax, g.vx, fa.rx); qy = fast_div(ay, g.vy, fa.ry); qz = fast_div(az, g.vz, fa.rz);
+      } else {
+        qx = __fdiv_rn(ax, g.vx); qy = __fdiv_rn(ay, g.vy); qz = __fdiv_rn(az, g.vz);
+      }
+      cstage[lane * 3 + 0] = __float2int_rz(qz);
+      cstage[lane * 3 + 1] = __float2int_rz(qy);
+      cstage[lane * 3 + 2] = __float2int_rz(qx);
+    }
+    __syncwarp();
     float* __restrict__ dst = fr.voxels + (size_t)v0 * W;
     if (nvox == 32) {
 #pragma unroll
@@ -1506,7 +1490,7 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   // the fallback reuses the frame's own region as table | lists | pslot
   const size_t slow = p->slow.table_b + p->slow.list_b + p->slow.pslot_b;
   p->region_b = std::max(fast, slow);
-  p->per_frame = p->region_b + 3 * p->word_b + p->cnt_b;  // bitmask + {bits, prefix} pairs
+  p->per_frame = p->region_b + 4 * p->word_b + p->cnt_b;  // bitmask (2 words per 32 points) + {bits, prefix} pairs
   // expansion tile: voxels per warp such that a tile fits the per-warp stage
   if ((int64_t)std::max(max_points, 1) * c > kExpStageWords) return PCFE_ERR_TOO_LARGE;
   p->exp_vt = 32;
@@ -1563,9 +1547,9 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
   w.vcell_off = p.ent_b + p.lst_b + p.cells_b;
   w.rec_off = p.ent_b;
   w.firsts_off = p.ent_b + p.rec_b;
-  const size_t zero_per = p.word_b + p.cnt_b;
+  const size_t zero_per = 2 * p.word_b + p.cnt_b;
   w.zero_stride = zero_per / sizeof(uint32_t);
-  w.ctl_off = p.word_b / sizeof(uint32_t);
+  w.ctl_off = 2 * p.word_b / sizeof(uint32_t);
   w.word_stride = 2 * p.word_b / sizeof(uint32_t);
   w.nb = p.nb; w.log2_nb = p.log2_nb; w.cap = p.cap; w.slots = p.slots; w.log2_slots = p.log2_slots;
   w.arena_cap = (uint32_t)p.npad;
@@ -1575,8 +1559,6 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)p.smem_bucket));
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)p.smem_bucket));
-  PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)p.smem_bucket));
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2)));
@@ -1627,12 +1609,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         // speculative first copy: the average bucket fill of the largest frame, rounded up to 64
         // entries, never more than the region
         const int spec = (int)std::min<int64_t>(p.cap, (((wn_max + p.nb - 1) / p.nb) + 63) / 64 * 64);
-        if (g_opt_bucket_variant == 2) {
-          const size_t smem_small = (size_t)(2 * p.slots + p.cap) * 4 + (size_t)(2 * p.cap) * 2;
-          hvb_bucket_small_kernel<5, true><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
-        } else {
-          hvb_bucket_rec_kernel<<<grid, kBucketThreads, smem_rec, st>>>(w, pe, spec);
-        }
+        hvb_bucket_rec_kernel<<<grid, kBucketThreads, smem_rec, st>>>(w, pe, spec);
         PCFE_LAUNCH_CHECK();
       }
       {
@@ -1642,11 +1619,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       }
       {
         ProfScope ps("hvb_expand", st);
-        KeyDecode kd;
-        kd.plane = (uint32_t)p.g.gx * (uint32_t)p.g.gy;
-        kd.gx = (uint32_t)p.g.gx;
-        kd.m_plane = (uint32_t)(0x100000000ull / kd.plane);
-        kd.m_gx = (uint32_t)(0x100000000ull / kd.gx);
+        const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
         const int64_t vmax = std::max<int64_t>(std::min<int64_t>(max_voxels, wn_max), 1);
         const int pper = kExpWarps * kPipeTiles * 32;
         const dim3 pgrid((unsigned)((vmax + pper - 1) / pper), (unsigned)wv);
@@ -1654,8 +1627,8 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         const int tiles_x = (int)pgrid.x;
         unsigned egrid = pgrid.x * pgrid.y;
         if (g_opt_expand_ctas > 0) egrid = std::min<unsigned>(egrid, (unsigned)(g_opt_expand_ctas * 148));
-        if (c == 4) hvb_expand_rec_kernel<4><<<egrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x);
-        else hvb_expand_rec_kernel<5><<<egrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x);
+        if (c == 4) hvb_expand_rec_kernel<4><<<egrid, kExpThreads, 0, st>>>(b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x);
+        else hvb_expand_rec_kernel<5><<<egrid, kExpThreads, 0, st>>>(b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x);
         PCFE_LAUNCH_CHECK();
       }
     } else {
