@@ -26,10 +26,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = "C4"
-# DRAM traffic per 64-frame step from the committed ncu capture (profiles/r01_v4_ncu_summary.txt):
-# hvb_bin 293.8 MB + hvb_bucket 177.7 MB + hv_scan 1.5 MB + hvb_order 147.0 MB + hvb_expand 1025.8 MB
-NCU_TRAFFIC_BYTES_PER_STEP = {"C4": 1_645_800_000}
-NCU_EXPAND_TRAFFIC = {"C4": 1_025_800_000}
+# DRAM traffic per 64-frame step from the committed ncu capture (profiles/r01_v10_ncu_summary.txt):
+# hvb_bin 295.3 MB + hvb_bucket_rec 143.3 MB + hvb_scan_firsts 3.0 MB + hvb_expand_rec 1063.6 MB
+NCU_TRAFFIC_BYTES_PER_STEP = {"C4": 1_505_200_000}
+NCU_EXPAND_TRAFFIC = {"C4": 1_063_600_000}
+NCU_PROFILE = "profiles/r01_v10_ncu_summary.txt"
 KEPT_POINTS_PER_FRAME = {"C4": 156_000}  # points surviving the max_points cap (oracle, seed 4000)
 METRIC = "hard_voxelize_throughput"
 UNIT = "Mpoints/s"
@@ -349,17 +350,17 @@ def run_ours(args):
     achieved = algo / (ms_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_BYTES_PER_STEP.get(args.workload),
-                "kernel": "hard-voxelize launch sequence per GPU (hvb_bin, hvb_bucket, hv_scan_flags, hvb_order, "
-                          "hvb_expand); achieved = algorithmic bytes of the step / CUDA-event step time",
+                "kernel": "hard-voxelize launch sequence per GPU (" + ", ".join(k for k in (kernels or {})) + "); "
+                          "achieved = algorithmic bytes of the step / CUDA-event step time",
                 "algorithmic_bytes_per_step": algo, "peak_source": peak_src + " (of measured)",
-                "traffic_source": "sum of dram__bytes_read+write over the step's kernels, ncu --set full, "
-                                  "profiles/r01_v4_ncu_summary.txt",
+                "traffic_source": "sum of dram__bytes_read+write over the step's kernels, ncu --set full, " + NCU_PROFILE,
                 "mean_voxels_per_frame": round(sum(m_list) / len(m_list), 1)}
     if kernels and "hvb_expand" in kernels:
-        # dominant kernel: writes every returned element once, reads the kept rows and the cell records
+        # dominant kernel (the expansion): writes every returned element once, reads the kept rows and
+        # one first-point index per voxel (the records of multi-point voxels are not counted)
         kept = KEPT_POINTS_PER_FRAME.get(args.workload)
         m_tot = sum(m_list)
-        k_bytes = m_tot * (P * C * 4 + 16) + m_tot * 16 + (kept * F * (C * 4 + 4) if kept else 0)
+        k_bytes = m_tot * (P * C * 4 + 16) + m_tot * 4 + (kept * F * C * 4 if kept else 0)
         k_ms = kernels["hvb_expand"]["ms_per_step"]
         roofline["dominant_kernel"] = {"name": "hvb_expand", "ms_per_launch": k_ms,
                                        "algorithmic_bytes_per_launch": k_bytes,
