@@ -56,7 +56,8 @@ def test_workspace_sizing(lib):
     assert auto % one == 0 and one <= auto <= 2 * 64 * one
     # empty grid -> 0 (error)
     assert lib.pcfe_hard_voxelize_workspace_bytes(10, 1, 1, vs, _cabi.f6([0, 0, 0, 0, 0, 0]), 5, 10) == 0
-    assert lib.pcfe_points_in_boxes_workspace_bytes(16, 200) == 16 * 200 * 32
+    # prepared boxes (32 B) + conservative-reject records (16 B) per box
+    assert lib.pcfe_points_in_boxes_workspace_bytes(16, 200) == 16 * 200 * (32 + 16)
 
 
 def test_argument_errors_without_gpu(lib):
