@@ -1309,7 +1309,7 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
 // place in a 128-byte coalesced store -- no shared-memory transposition of the data.  The kernel is
 // bound by L1 wavefronts (random gathers), not by DRAM: the same frames resident in L2 run no faster.
 #ifndef PCFE_EXP_REC_MINB
-#define PCFE_EXP_REC_MINB 6
+#define PCFE_EXP_REC_MINB 8
 #endif
 template <int C>
 __global__ void __launch_bounds__(kExpThreads, PCFE_EXP_REC_MINB)
