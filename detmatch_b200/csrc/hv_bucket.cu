@@ -49,6 +49,7 @@ int g_opt_no_fast_div = 0;      // 1: __fdiv_rn for every point (no hoisted reci
 int g_opt_expand_variant = 0;  // 1: un-pipelined fixed-P expansion kernel
 int g_opt_expand_skip = 0;      // timing experiments only (wrong output)
 int g_opt_expand_prefetch = 1;
+int g_opt_pdl = 1;              // programmatic dependent launch between the record path's kernels
 int g_opt_expand_ctas = 0;      // > 0: persistent expansion with this many CTAs per SM
 int g_opt_expand_pad_kb = 0;    // experiment: extra dynamic smem per expansion CTA (limits its occupancy)  // frames of L2 prefetch distance in the pipelined expansion (0 = off)
 
@@ -112,6 +113,7 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
   __shared__ uint32_t warp_sums[33];
   __shared__ uint32_t s_overflow;
 
+  pdl_trigger();  // the bucket kernel may start launching; it waits for this grid before reading
   const int f = blockIdx.y;
   const int n = batch.f[f].n;
   const int tid = threadIdx.x;
@@ -539,6 +541,10 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+  }
+  pdl_wait();     // everything below reads what the bin kernel wrote
+  pdl_trigger();
+  if (tid == 0) {
     mbar_expect_tx(&bar[0], (uint32_t)spec * 8u);
     bulk_g2s(ents, gent, (uint32_t)spec * 8u, &bar[0]);
     s_nclaimed = 0u;
@@ -1276,6 +1282,8 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
   __shared__ uint32_t warp_sums[33];
   __shared__ uint32_t stage[kFirstsThreads * 32];
   const int f = blockIdx.y, tid = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   if (w.ctl(f)[w.nb + kCtlOverflow]) return;
   // 64-bit mask words: low half = "first point of a voxel", high half = "that voxel has more points"
   const uint2* __restrict__ bm = reinterpret_cast<const uint2*>(w.bitmask(f));
@@ -1343,6 +1351,8 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(nf.pts) + lo), "r"(bytes) : "memory");
     }
   }
+  pdl_wait();  // (the prefetch above only touches the caller's input rows)
+  pdl_trigger();
   if (w.ctl(f)[w.nb + kCtlOverflow]) continue;
   const HvFrame& fr = batch.f[f];
   const int m = voxel_num[f];
@@ -1613,12 +1623,13 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         // speculative first copy: the average bucket fill of the largest frame, rounded up to 64
         // entries, never more than the region
         const int spec = (int)std::min<int64_t>(p.cap, (((wn_max + p.nb - 1) / p.nb) + 63) / 64 * 64);
-        hvb_bucket_rec_kernel<<<grid, kBucketThreads, smem_rec, st>>>(w, pe, spec);
+        PCFE_CUDA_TRY(launch_pdl(hvb_bucket_rec_kernel, grid, dim3(kBucketThreads), smem_rec, st, g_opt_pdl != 0, w, pe, spec));
         PCFE_LAUNCH_CHECK();
       }
       {
         ProfScope ps("hvb_scan_firsts", st);
-        hvb_scan_firsts_kernel<<<dim3((unsigned)((wnpad / 32 + kFirstsThreads - 1) / kFirstsThreads), (unsigned)wv), kFirstsThreads, 0, st>>>(w, wnpad / 32, max_voxels, voxel_num + f0);
+        PCFE_CUDA_TRY(launch_pdl(hvb_scan_firsts_kernel, dim3((unsigned)((wnpad / 32 + kFirstsThreads - 1) / kFirstsThreads), (unsigned)wv),
+                                 dim3(kFirstsThreads), 0, st, g_opt_pdl != 0, w, wnpad / 32, max_voxels, voxel_num + f0));
         PCFE_LAUNCH_CHECK();
       }
       {
@@ -1631,8 +1642,8 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         const int tiles_x = (int)pgrid.x;
         unsigned egrid = pgrid.x * pgrid.y;
         if (g_opt_expand_ctas > 0) egrid = std::min<unsigned>(egrid, (unsigned)(g_opt_expand_ctas * 148));
-        if (c == 4) hvb_expand_rec_kernel<4><<<egrid, kExpThreads, 0, st>>>(b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x);
-        else hvb_expand_rec_kernel<5><<<egrid, kExpThreads, 0, st>>>(b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x);
+        if (c == 4) PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<4>, dim3(egrid), dim3(kExpThreads), 0, st, g_opt_pdl != 0, b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x));
+        else PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<5>, dim3(egrid), dim3(kExpThreads), 0, st, g_opt_pdl != 0, b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x));
         PCFE_LAUNCH_CHECK();
       }
     } else {

@@ -1,3 +1,4 @@
 B="python bench.py --no-cpu-baseline --no-e2e"
-P='import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d["ms_per_step"], d["roofline"]["frac"], {k:v["ms_per_step"] for k,v in d["kernels"].items() if "bucket" in k})'
-for v in libpcfe libpcfe_t2 libpcfe_t075; do echo -n "$v: "; PCFE_LIB=$PWD/detmatch_b200/lib/$v.so $B --steps 200 --warmup 3 2>&1 | tail -1 | python -c "$P"; done
+P='import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d["ms_per_step"], d["roofline"]["frac"])'
+timeout 600 python -m pytest tests/test_gpu_voxel.py -m gpu -x -q -k "bucket and not general and not exhaustive" 2>&1 | tail -2
+for v in 1 0 1 0; do echo -n "pdl $v: "; $B --steps 300 --warmup 5 --debug hv_pdl=$v 2>&1 | tail -1 | python -c "$P"; done
