@@ -250,6 +250,7 @@ hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, const uint32_t* __r
   // one frame per CTA)
   __shared__ uint32_t warp_sums[33];
   __shared__ uint32_t carry;
+  pdl_wait();  // launched as a programmatic dependent of the expansion kernel
   for (int f = blockIdx.x; f < frames; f += ring) {
   if (!force && overflow[(size_t)f * overflow_stride] == 0) continue;
   const HvFrame& fr = batch.f[f];
@@ -348,9 +349,9 @@ int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size
                     uint32_t* bitmask, size_t bitmask_stride, uint32_t* prefix, size_t prefix_stride,
                     int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st) {
   ProfScope ps("hv_slow_fallback", st);
-  hvg_slow_frame_kernel<<<frames, kSlowThreads, 0, st>>>(
-      b, overflow, overflow_stride, force, scratch_base, scratch_stride, p, bitmask, bitmask_stride,
-      prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, frames);
+  PCFE_CUDA_TRY(launch_pdl(hvg_slow_frame_kernel, dim3((unsigned)frames), dim3(kSlowThreads), 0, st, true, b, overflow,
+                           overflow_stride, force, scratch_base, scratch_stride, p, bitmask, bitmask_stride,
+                           prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, frames));
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
