@@ -552,9 +552,8 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
   const uint32_t overflow = ctl[w.nb + kCtlOverflow];
   const int ne = (int)min(ctl[b], (uint32_t)cap);
   // table size for THIS bucket: a power of two >= 2 ne, at most the plan's `slots` (>= 1.25 cap)
-  int S = 64;
-  while (S < PCFE_TABLE_NUM * ne / PCFE_TABLE_DEN) S <<= 1;
-  S = min(S, w.slots);
+  const int want = max(PCFE_TABLE_NUM * ne / PCFE_TABLE_DEN, 64);
+  const int S = min(1 << (32 - __clz(want - 1)), w.slots);  // next power of two
   uint32_t* head = hkey + S;
   uint16_t* slotlist = reinterpret_cast<uint16_t*>(hkey + 2 * w.slots);
   if (tid == 0 && ne > spec) {
@@ -590,10 +589,12 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
       }
     }
     const uint32_t cm = __ballot_sync(0xFFFFFFFFu, claimed);
-    if (cm) {  // claimed slots join the cell list: one shared-memory atomic per warp
-      const uint32_t leader = (uint32_t)__ffs(cm) - 1u;
+    if (cm) {  // claimed slots join the cell list: one shared-memory atomic per warp, issued by the
+               // lane elect.sync picks (ptxas re-aggregates an atomic under an ordinary predicate)
+      uint32_t leader, is_leader;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync %0|p, 0xffffffff;\n\tselp.u32 %1, 1, 0, p;\n\t}" : "=r"(leader), "=r"(is_leader));
       uint32_t base = 0;
-      if (lane == leader)
+      if (is_leader)
         asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(smem_u32(&s_nclaimed)), "r"(__popc(cm)) : "memory");
       base = __shfl_sync(0xFFFFFFFFu, base, leader);
       if (claimed) slotlist[base + __popc(cm & lane_lt)] = (uint16_t)s;
@@ -778,10 +779,11 @@ hvb_bucket_rank_kernel(const HvbWork w, const int pe /* max(max_points, 1) */, c
         }
       }
       const uint32_t cm = __ballot_sync(0xFFFFFFFFu, claimed);
-      if (cm) {
-        const uint32_t leader = (uint32_t)__ffs(cm) - 1u;
+      if (cm) {  // see hvb_bucket_rec_kernel
+        uint32_t leader, is_leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync %0|p, 0xffffffff;\n\tselp.u32 %1, 1, 0, p;\n\t}" : "=r"(leader), "=r"(is_leader));
         uint32_t base = 0;
-        if (lane == leader)
+        if (is_leader)
           asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(smem_u32(&s_nclaimed)), "r"(__popc(cm)) : "memory");
         base = __shfl_sync(0xFFFFFFFFu, base, leader);
         if (claimed) slotlist[base + __popc(cm & lane_lt)] = (uint16_t)s;
