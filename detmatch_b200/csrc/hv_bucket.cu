@@ -239,6 +239,9 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
 #define PCFE_BUCKET_THREADS 256
 #endif
 constexpr int kBucketThreads = PCFE_BUCKET_THREADS;
+#ifndef PCFE_REC_STRIDE
+#define PCFE_REC_STRIDE 1  // uint4 units per record slot (2 = one 32-byte sector per slot)
+#endif
 #ifndef PCFE_TABLE_NUM
 #define PCFE_TABLE_NUM 2  // table slots >= 2 x entries of the bucket (measured: 1.25x costs +8 % in probe retries)
 #define PCFE_TABLE_DEN 1
@@ -635,10 +638,10 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
     const uint32_t first = sorted[0];
     const bool more = cnt > 1u && pe > 1;
     if (more) {
-      rec[2 * (size_t)first] = make_uint4(sorted[1], (cnt > 2u && pe > 2) ? sorted[2] : kEmpty,
+      rec[PCFE_REC_STRIDE * (size_t)first] = make_uint4(sorted[1], (cnt > 2u && pe > 2) ? sorted[2] : kEmpty,
                                           (cnt > 3u && pe > 3) ? sorted[3] : kEmpty,
                                           (cnt > 4u && pe > 4) ? sorted[4] : kEmpty);
-      rec[2 * (size_t)first + 1] = make_uint4(0u, 0u, 0u, 0u);
+      if (PCFE_REC_STRIDE == 2) rec[2 * (size_t)first + 1] = make_uint4(0u, 0u, 0u, 0u);
     }
     atomicOr(&bm64[first >> 5], (1ull << (first & 31)) | (more ? (1ull << (32 + (first & 31))) : 0ull));
   }
@@ -1368,7 +1371,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   auto load_first = [&](int v0) { return v0 + lane < m ? ((skip & 4) ? (uint32_t)(v0 + lane) : __ldg(firsts + v0 + lane)) : kEmpty; };
   auto load_rec = [&](uint32_t fi) {
     uint4 r = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);  // no points besides the first
-    if (fi != kEmpty && (fi >> 31) && !(skip & 2)) r = __ldg(rec + 2 * (size_t)(fi & 0x7FFFFFFFu));
+    if (fi != kEmpty && (fi >> 31) && !(skip & 2)) r = __ldg(rec + PCFE_REC_STRIDE * (size_t)(fi & 0x7FFFFFFFu));
     return r;
   };
   const FastAxes fa = make_fast_axes(g);
@@ -1500,7 +1503,7 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   p->vcell_b = align256(std::max<size_t>(vmax, 1) * sizeof(Cell));
   p->word_b = align256((size_t)p->words * sizeof(uint32_t));
   p->cnt_b = align256((size_t)(p->nb + 16) * sizeof(uint32_t)) + 256;  // also covers hv_mega.cu's ctl + ticket
-  p->rec_b = align256((size_t)p->npad * 32);
+  p->rec_b = align256((size_t)p->npad * 16 * PCFE_REC_STRIDE);
   p->firsts_b = align256(std::max<size_t>(vmax, 1) * sizeof(uint32_t));
   const size_t fast = std::max(p->ent_b + p->lst_b + p->cells_b + p->vcell_b, p->ent_b + p->rec_b + p->firsts_b);
   // the fallback reuses the frame's own region as table | lists | pslot
