@@ -49,6 +49,7 @@ int g_opt_no_fast_div = 0;      // 1: __fdiv_rn for every point (no hoisted reci
 int g_opt_expand_variant = 0;  // 1: un-pipelined fixed-P expansion kernel
 int g_opt_expand_skip = 0;      // timing experiments only (wrong output)
 int g_opt_expand_prefetch = 1;
+int g_opt_expand_vpw = 4;       // long-voxel expansion: voxels per warp
 int g_opt_pdl = 1;              // programmatic dependent launch between the record path's kernels
 int g_opt_expand_ctas = 0;      // > 0: persistent expansion with this many CTAs per SM
 int g_opt_expand_pad_kb = 0;    // experiment: extra dynamic smem per expansion CTA (limits its occupancy)  // frames of L2 prefetch distance in the pipelined expansion (0 = off)
@@ -1455,6 +1456,61 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   }
 }
 
+// ---- expansion for long voxels (pillars: P * C = 320 words, a multiple of 4) -----------------------
+// A warp writes one voxel after the other as float4 streaming stores: lane i owns words 4 i .. 4 i + 3
+// (+ 128 per trip); only the float4s below len * C carry data -- word w belongs to slot w / C,
+// feature w % C -- everything else is stored as zeros directly: no shared memory, no zero-fill
+// pass.  The next voxel's record is fetched while the current one is written.  C == 0: features per
+// point at run time.  Needs 16-byte aligned voxel buffers.
+template <int C>
+__global__ void __launch_bounds__(kExpThreads)
+hvb_expand_words_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
+                        const int c_rt, const int max_points, const int vpw /* voxels per warp */,
+                        const int32_t* __restrict__ voxel_num) {
+  const int f = blockIdx.y;
+  pdl_wait();
+  if (w.ctl(f)[w.nb + kCtlOverflow]) return;
+  const HvFrame& fr = batch.f[f];
+  const int c = C > 0 ? C : c_rt;
+  const int m = voxel_num[f];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int W = max_points * c, W4 = W >> 2;  // W % 4 == 0
+  const uint4* __restrict__ vcell = reinterpret_cast<const uint4*>(w.vcell(f));
+  const uint32_t* __restrict__ lst = w.lst(f);
+  const float* __restrict__ pts = fr.pts;
+  const int v0 = (blockIdx.x * kExpWarps + wid) * vpw;
+  if (v0 >= m) return;
+  const int v1 = min(v0 + vpw, m);
+  uint4 cl = __ldg(vcell + v0);  // key, len, list_off, first (same address for the whole warp)
+#pragma unroll 1
+  for (int v = v0; v < v1; ++v) {
+    const uint4 cur = cl;
+    if (v + 1 < v1) cl = __ldg(vcell + v + 1);
+    const uint32_t len = min(cur.y, (uint32_t)max_points);
+    const int nreal = (int)len * c;
+    float4* __restrict__ dst = reinterpret_cast<float4*>(fr.voxels + (size_t)v * W);
+    if (lane == 0) {
+      decode_key(cur.x, g, fr.coors + (size_t)v * 3);
+      fr.num[v] = (int32_t)len;
+    }
+    for (int i4 = lane; i4 < W4; i4 += 32) {
+      float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const int ow = i4 * 4;
+      if (ow < nreal) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (ow + t < nreal) {
+            const int sl = (ow + t) / c;
+            const uint32_t idx = __ldg(lst + cur.z + sl);
+            o[t] = __ldg(pts + (size_t)idx * c + (ow + t - sl * c));
+          }
+        }
+      }
+      __stcs(dst + i4, make_float4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
 template <int C>
 int launch_expand(dim3 grid, cudaStream_t st, const HvBatch& b, const HvbWork& w,
                   const GridParams& g, int c, int p, int vt, const int32_t* vn, int vec_ok) {
@@ -1712,6 +1768,14 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
           else hvb_expand_pipe_kernel<5, 5><<<pgrid, kExpThreads, pad, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, g_opt_expand_skip);
         } else if (c == 4) hvb_expand_fixed_kernel<4, 5><<<fgrid, kExpThreads, 0, st>>>(b, w, kd, vn, vec_ok);
         else hvb_expand_fixed_kernel<5, 5><<<fgrid, kExpThreads, 0, st>>>(b, w, kd, vn, vec_ok);
+        PCFE_LAUNCH_CHECK();
+      } else if (max_points * c >= 64 && (max_points * c) % 4 == 0 && vec_ok && g_opt_expand_variant == 0) {
+        // long voxels: lane = output word, one voxel after the other per warp
+        const int vpw = g_opt_expand_vpw;
+        const dim3 wgrid((unsigned)((vmax + kExpWarps * vpw - 1) / (kExpWarps * vpw)), (unsigned)wv);
+        if (c == 4) hvb_expand_words_kernel<4><<<wgrid, kExpThreads, 0, st>>>(b, w, p.g, c, max_points, vpw, vn);
+        else if (c == 5) hvb_expand_words_kernel<5><<<wgrid, kExpThreads, 0, st>>>(b, w, p.g, c, max_points, vpw, vn);
+        else hvb_expand_words_kernel<0><<<wgrid, kExpThreads, 0, st>>>(b, w, p.g, c, max_points, vpw, vn);
         PCFE_LAUNCH_CHECK();
       } else if (c == 4) rc = launch_expand<4>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
       else if (c == 5) rc = launch_expand<5>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);

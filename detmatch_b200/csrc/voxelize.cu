@@ -51,6 +51,7 @@ extern int g_opt_expand_variant;
 extern int g_opt_expand_pad_kb;
 extern int g_opt_expand_ctas;
 extern int g_opt_pdl;
+extern int g_opt_expand_vpw;
 extern int g_opt_no_fast_div;
 extern int g_opt_expand_prefetch;
 extern int g_opt_expand_skip;
@@ -324,6 +325,7 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_expand_prefetch")) g_opt_expand_prefetch = value;
   else if (!strcmp(name, "hv_no_fast_div")) g_opt_no_fast_div = value;
   else if (!strcmp(name, "hv_expand_pad_kb")) g_opt_expand_pad_kb = value;
+  else if (!strcmp(name, "hv_expand_vpw")) g_opt_expand_vpw = value > 0 ? value : 4;
   else if (!strcmp(name, "hv_pdl")) g_opt_pdl = value;
   else if (!strcmp(name, "hv_expand_ctas")) g_opt_expand_ctas = value;
   else if (!strcmp(name, "hv_expand_skip")) g_opt_expand_skip = value;
