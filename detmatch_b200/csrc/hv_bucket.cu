@@ -104,6 +104,11 @@ constexpr int kBinPerThread = PCFE_BIN_PER_THREAD;
 constexpr int kBinTile = kBinThreads * kBinPerThread;  // 4096 points
 constexpr int kMaxBuckets = 1024;
 
+__global__ void hvb_zero_kernel(uint4* __restrict__ p, const size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void __launch_bounds__(kBinThreads, 3)
 hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
                const int c, const int use_fast_div) {
@@ -114,7 +119,6 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
   __shared__ uint32_t warp_sums[33];
   __shared__ uint32_t s_overflow;
 
-  pdl_trigger();  // the bucket kernel may start launching; it waits for this grid before reading
   const int f = blockIdx.y;
   const int n = batch.f[f].n;
   const int tid = threadIdx.x;
@@ -198,6 +202,7 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
   }
   __syncthreads();
   // reserve a run in every bucket this tile contributes to; scan hist for the staging offsets
+  pdl_wait();  // the counters are zeroed by the previous kernel of the stream (rows are caller input)
   uint32_t* ctl = w.ctl(f);
   uint32_t total = 0;
   for (int b0 = 0; b0 < w.nb; b0 += kBinThreads) {
@@ -1664,14 +1669,22 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     }
     {
       ProfScope ps("memset_ctl", st);
-      PCFE_CUDA_TRY(cudaMemsetAsync(zero_base, 0, (size_t)wv * zero_per, st));
-      count_launch();
+      if (g_opt_pdl) {  // a kernel instead of a memset node, so that the bin kernel can be its
+                        // programmatic dependent (zero_per is a multiple of 256 bytes)
+        const size_t n16 = (size_t)wv * zero_per / 16;
+        hvb_zero_kernel<<<(unsigned)std::min<size_t>((n16 + 255) / 256, 1184), 256, 0, st>>>(reinterpret_cast<uint4*>(zero_base), n16);
+        PCFE_LAUNCH_CHECK();
+      } else {
+        PCFE_CUDA_TRY(cudaMemsetAsync(zero_base, 0, (size_t)wv * zero_per, st));
+        count_launch();
+      }
     }
     const int wnpad = std::max((int)((wn_max + 31) / 32 * 32), 32);
     {
       ProfScope ps("hvb_bin", st);
       const dim3 grid((unsigned)((wn_max + kBinTile - 1) / kBinTile), (unsigned)wv);
-      hvb_bin_kernel<<<grid, kBinThreads, 0, st>>>(b, w, p.g, c, fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0);
+      PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c,
+                               fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0));
       PCFE_LAUNCH_CHECK();
     }
     // P == 5 with 16-byte aligned rows: the record-at-first-point variant (no order pass)
