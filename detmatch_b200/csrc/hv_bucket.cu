@@ -1346,10 +1346,11 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
                       const int tiles_x /* CTA-tiles per frame; the 1-D grid strides over tiles_x * frames */) {
   constexpr int PT = 5;
   constexpr int W = PT * C;  // output words per voxel
-  __shared__ uint32_t eff_all[kExpWarps * 32 * PT];  // point index of (voxel, slot), kEmpty if absent
+  // source word (point index * C + feature) of every output word of a warp's tile, kEmpty = zero
+  __shared__ uint32_t eff_all[kExpWarps * 32 * W];
   __shared__ __align__(16) int32_t coor_all[kExpWarps * 96];  // (z, y, x) of a tile: one coalesced store
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t* eff = eff_all + wid * (32 * PT);
+  uint32_t* eff = eff_all + wid * (32 * W);
   int32_t* cstage = coor_all + wid * 96;
 #pragma unroll 1
   for (int wi = blockIdx.x; wi < tiles_x * frames; wi += gridDim.x) {
@@ -1395,11 +1396,15 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     const bool have = fi_cur != kEmpty;  // false for lanes past the end
     const uint32_t first = fi_cur & 0x7FFFFFFFu;
     const uint32_t len = (have ? 1u : 0u) + (ra_cur.x != kEmpty) + (ra_cur.y != kEmpty) + (ra_cur.z != kEmpty) + (ra_cur.w != kEmpty);
-    eff[lane * PT + 0] = have ? first : kEmpty;
-    eff[lane * PT + 1] = ra_cur.x;
-    eff[lane * PT + 2] = ra_cur.y;
-    eff[lane * PT + 3] = ra_cur.z;
-    eff[lane * PT + 4] = ra_cur.w;
+    {  // lane = voxel: the 25 (20) source words of its output, slot by slot
+      const uint32_t idx5[PT] = {have ? first : kEmpty, ra_cur.x, ra_cur.y, ra_cur.z, ra_cur.w};
+#pragma unroll
+      for (int j = 0; j < PT; ++j) {
+        const uint32_t b0 = idx5[j] * (uint32_t)C;
+#pragma unroll
+        for (int q = 0; q < C; ++q) eff[lane * W + j * C + q] = idx5[j] != kEmpty ? b0 + (uint32_t)q : kEmpty;
+      }
+    }
     // the voxel's coordinates are the cell of its first point (recomputed: no key is stored)
     float px = 0.f, py = 0.f, pz = 0.f;
     if (have) {
@@ -1412,12 +1417,9 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     float val[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) {
-      const uint32_t ow = (uint32_t)lane + 32u * (uint32_t)k;     // < 32 W <= 800
-      const uint32_t q = C == 4 ? ow >> 2 : (ow * 205u) >> 10;    // ow / 5 for ow < 1024
-      const uint32_t comp = ow - q * (uint32_t)C;
-      const uint32_t idx = eff[q];
+      const uint32_t src = eff[lane + 32 * k];  // word lane + 32 k of the tile
       val[k] = 0.0f;
-      if (idx != kEmpty && !(skip & 1)) val[k] = __ldg(pts + (size_t)idx * C + comp);
+      if (src != kEmpty && !(skip & 1)) val[k] = __ldg(pts + src);
     }
     // records of the next tile, first-point indices of the one after
     const uint4 ra_nxt = load_rec(fi_nxt);
