@@ -109,9 +109,12 @@ __global__ void hvb_zero_kernel(uint4* __restrict__ p, const size_t n16) {
     p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// CT = features per point at compile time (row loads become base + immediate), 0 = run time
+template <int CT>
 __global__ void __launch_bounds__(kBinThreads, 3)
 hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
-               const int c, const int use_fast_div) {
+               const int c_rt, const int use_fast_div) {
+  const int c = CT > 0 ? CT : c_rt;
   __shared__ uint32_t hist[kMaxBuckets];   // entries of this tile per bucket
   __shared__ uint32_t soff[kMaxBuckets];   // exclusive prefix of hist (staging offsets)
   __shared__ uint32_t delta[kMaxBuckets];  // (entry position in the frame's ent array) - (staging position)
@@ -1685,8 +1688,10 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     {
       ProfScope ps("hvb_bin", st);
       const dim3 grid((unsigned)((wn_max + kBinTile - 1) / kBinTile), (unsigned)wv);
-      PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c,
-                               fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0));
+      const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
+      if (c == 4) PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<4>, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c, fdiv));
+      else if (c == 5) PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<5>, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c, fdiv));
+      else PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<0>, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c, fdiv));
       PCFE_LAUNCH_CHECK();
     }
     // P == 5 with 16-byte aligned rows: the record-at-first-point variant (no order pass)

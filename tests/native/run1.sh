@@ -1,4 +1,4 @@
 B="python bench.py --no-cpu-baseline --no-e2e"
-P='import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d["ms_per_step"], d["roofline"]["frac"])'
+P='import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d["ms_per_step"], d["roofline"]["frac"], {k:v["ms_per_step"] for k,v in d["kernels"].items()})'
 timeout 600 python -m pytest tests/test_gpu_voxel.py -m gpu -x -q -k "not exhaustive" 2>&1 | tail -2
-for v in 1 0 1; do echo -n "pdl $v: "; $B --steps 500 --warmup 5 --debug hv_pdl=$v 2>&1 | tail -1 | python -c "$P"; done
+$B --steps 500 --warmup 5 2>&1 | tail -1 | python -c "$P"
