@@ -554,7 +554,8 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
   }
-  pdl_wait();     // everything below reads what the bin kernel wrote
+  __syncthreads();  // barrier objects initialised before any use (also keeps racecheck quiet)
+  pdl_wait();       // everything below reads what the bin kernel wrote
   pdl_trigger();
   if (tid == 0) {
     mbar_expect_tx(&bar[0], (uint32_t)spec * 8u);
@@ -742,6 +743,9 @@ hvb_bucket_rank_kernel(const HvbWork w, const int pe /* max(max_points, 1) */, c
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+  }
+  __syncthreads();  // barrier objects initialised before any use
+  if (tid == 0) {
     mbar_expect_tx(&bar[0], (uint32_t)spec * 8u);
     bulk_g2s(ents, gent, (uint32_t)spec * 8u, &bar[0]);
     s_nclaimed = 0u;

@@ -1,4 +1,4 @@
 B="python bench.py --no-cpu-baseline --no-e2e"
 P='import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d["ms_per_step"], d["roofline"]["frac"], {k:v["ms_per_step"] for k,v in d["kernels"].items()})'
-timeout 600 python -m pytest tests/test_gpu_voxel.py -m gpu -x -q -k "not exhaustive" 2>&1 | tail -2
+timeout 600 compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 7 python -m pytest tests/test_gpu_voxel.py -m gpu -x -q -k "test_caps and (bucket-3-150 or bucket-5-100000 or bucket-64-50 or pipeline-5-100000)" 2>&1 | tail -4
 $B --steps 500 --warmup 5 2>&1 | tail -1 | python -c "$P"
