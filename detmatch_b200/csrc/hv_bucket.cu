@@ -627,7 +627,25 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
     const int s = slotlist[j];
     uint32_t cnt = 0;
     uint32_t e = head[s];
-    while (e != kNil) {  // chain walk; the 5 smallest point indices stay in registers, ascending
+    // chain walk; the 5 smallest point indices stay in registers, ascending.  The first 5 steps are
+    // peeled: step k inserts into a sorted prefix of k entries (k compare-exchanges instead of 5).
+#pragma unroll
+    for (int step = 0; step < PT; ++step) {
+      if (e != kNil) {
+        const uint2 en = ents[e];
+        uint32_t v = en.y;
+        e = en.x;
+        ++cnt;
+#pragma unroll
+        for (int t = 0; t < step; ++t) {
+          const uint32_t lo = min(sorted[t], v);
+          v = max(sorted[t], v);
+          sorted[t] = lo;
+        }
+        sorted[step] = v;
+      }
+    }
+    while (e != kNil) {  // more than 5 points: full insertion, the largest of the six drops out
       const uint2 en = ents[e];
       uint32_t v = en.y;
       e = en.x;
