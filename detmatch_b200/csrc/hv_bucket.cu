@@ -47,12 +47,10 @@ int g_opt_bucket_avg = 1024;  // target points per bucket (tunable through pcfe_
 int g_opt_bucket_variant = 0;  // 1: always use the general (count + atomicMin lists) bucket kernel
 int g_opt_no_fast_div = 0;      // 1: __fdiv_rn for every point (no hoisted reciprocal)
 int g_opt_expand_variant = 0;  // 1: un-pipelined fixed-P expansion kernel
-int g_opt_expand_skip = 0;      // timing experiments only (wrong output)
 int g_opt_expand_prefetch = 1;
 int g_opt_expand_vpw = 4;       // long-voxel expansion: voxels per warp
 int g_opt_pdl = 1;              // programmatic dependent launch between the record path's kernels
 int g_opt_expand_ctas = 0;      // > 0: persistent expansion with this many CTAs per SM
-int g_opt_expand_pad_kb = 0;    // experiment: extra dynamic smem per expansion CTA (limits its occupancy)  // frames of L2 prefetch distance in the pipelined expansion (0 = off)
 
 namespace {
 
@@ -1183,8 +1181,7 @@ constexpr int kPipeTiles = PCFE_EXP_PIPE_TILES;
 template <int C, int PT>
 __global__ void __launch_bounds__(kExpThreads)
 hvb_expand_pipe_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const KeyDecode kd,
-                       const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist,
-                       const int skip /* timing experiments only: 1 no row loads, 2 no list loads */) {
+                       const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist) {
   __shared__ __align__(16) float stage_all[kExpWarps * 32 * PT * C];
   const int f = blockIdx.y;
   // The row gathers below are random 32-byte sector reads; served from DRAM they waste most of
@@ -1223,7 +1220,7 @@ hvb_expand_pipe_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, c
   {
     const uint32_t len = min(cl_cur.y, (uint32_t)PT);
 #pragma unroll
-    for (int j = 0; j < PT; ++j) idx_cur[j] = ((uint32_t)j < len && !(skip & 2)) ? __ldg(lst + cl_cur.z + j) : kEmpty;
+    for (int j = 0; j < PT; ++j) idx_cur[j] = (uint32_t)j < len ? __ldg(lst + cl_cur.z + j) : kEmpty;
   }
 
 #pragma unroll 1
@@ -1237,7 +1234,7 @@ hvb_expand_pipe_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, c
     for (int j = 0; j < PT; ++j) {
       ra[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx_cur[j] != kEmpty && !(skip & 1)) {
+      if (idx_cur[j] != kEmpty) {
         if (C == 4) {
           ra[j] = __ldg(reinterpret_cast<const float4*>(pts) + idx_cur[j]);
         } else {
@@ -1256,7 +1253,7 @@ hvb_expand_pipe_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, c
     {
       const uint32_t len = min(cl_nxt.y, (uint32_t)PT);
 #pragma unroll
-      for (int j = 0; j < PT; ++j) idx_nxt[j] = ((uint32_t)j < len && !(skip & 2)) ? __ldg(lst + cl_nxt.z + j) : kEmpty;
+      for (int j = 0; j < PT; ++j) idx_nxt[j] = (uint32_t)j < len ? __ldg(lst + cl_nxt.z + j) : kEmpty;
     }
     const uint4 cl_nn = load_cell(v0 + 64);
     // coordinates and count of this tile's voxels
@@ -1367,7 +1364,6 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
                       const int use_fast_div,
                       const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist,
                       const int coors_vec /* every coors buffer is 16-byte aligned */,
-                      const int skip /* timing experiments only: 1 no rows, 2 no records, 4 no firsts */,
                       const int tiles_x /* CTA-tiles per frame; the 1-D grid strides over tiles_x * frames */) {
   constexpr int PT = 5;
   constexpr int W = PT * C;  // output words per voxel
@@ -1402,10 +1398,10 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   if (vbase >= m) continue;  // warp-uniform
 
   // firsts[v] = first point of voxel v | (the voxel has more points: see rec[first]) << 31
-  auto load_first = [&](int v0) { return v0 + lane < m ? ((skip & 4) ? (uint32_t)(v0 + lane) : __ldg(firsts + v0 + lane)) : kEmpty; };
+  auto load_first = [&](int v0) { return v0 + lane < m ? __ldg(firsts + v0 + lane) : kEmpty; };
   auto load_rec = [&](uint32_t fi) {
     uint4 r = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);  // no points besides the first
-    if (fi != kEmpty && (fi >> 31) && !(skip & 2)) r = __ldg(rec + PCFE_REC_STRIDE * (size_t)(fi & 0x7FFFFFFFu));
+    if (fi != kEmpty && (fi >> 31)) r = __ldg(rec + PCFE_REC_STRIDE * (size_t)(fi & 0x7FFFFFFFu));
     return r;
   };
   const FastAxes fa = make_fast_axes(g);
@@ -1444,7 +1440,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     for (int k = 0; k < W; ++k) {
       const uint32_t src = eff[lane + 32 * k];  // word lane + 32 k of the tile
       val[k] = 0.0f;
-      if (src != kEmpty && !(skip & 1)) val[k] = __ldg(pts + src);
+      if (src != kEmpty) val[k] = __ldg(pts + src);
     }
     // records of the next tile, first-point indices of the one after
     const uint4 ra_nxt = load_rec(fi_nxt);
@@ -1747,8 +1743,8 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         const int tiles_x = (int)pgrid.x;
         unsigned egrid = pgrid.x * pgrid.y;
         if (g_opt_expand_ctas > 0) egrid = std::min<unsigned>(egrid, (unsigned)(g_opt_expand_ctas * 148));
-        if (c == 4) PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<4>, dim3(egrid), dim3(kExpThreads), 0, st, g_opt_pdl != 0, b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x));
-        else PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<5>, dim3(egrid), dim3(kExpThreads), 0, st, g_opt_pdl != 0, b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, g_opt_expand_skip, tiles_x));
+        if (c == 4) PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<4>, dim3(egrid), dim3(kExpThreads), 0, st, g_opt_pdl != 0, b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, tiles_x));
+        else PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<5>, dim3(egrid), dim3(kExpThreads), 0, st, g_opt_pdl != 0, b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, tiles_x));
         PCFE_LAUNCH_CHECK();
       }
     } else {
@@ -1803,13 +1799,8 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         const int pper = kExpWarps * kPipeTiles * 32;
         const dim3 pgrid((unsigned)((vmax + pper - 1) / pper), (unsigned)wv);
         if (vec_ok && g_opt_expand_variant == 0) {
-          const size_t pad = (size_t)g_opt_expand_pad_kb << 10;
-          if (pad) {
-            PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_expand_pipe_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
-            PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_expand_pipe_kernel<5, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
-          }
-          if (c == 4) hvb_expand_pipe_kernel<4, 5><<<pgrid, kExpThreads, pad, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, g_opt_expand_skip);
-          else hvb_expand_pipe_kernel<5, 5><<<pgrid, kExpThreads, pad, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch, g_opt_expand_skip);
+          if (c == 4) hvb_expand_pipe_kernel<4, 5><<<pgrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch);
+          else hvb_expand_pipe_kernel<5, 5><<<pgrid, kExpThreads, 0, st>>>(b, w, kd, vn, wv, g_opt_expand_prefetch);
         } else if (c == 4) hvb_expand_fixed_kernel<4, 5><<<fgrid, kExpThreads, 0, st>>>(b, w, kd, vn, vec_ok);
         else hvb_expand_fixed_kernel<5, 5><<<fgrid, kExpThreads, 0, st>>>(b, w, kd, vn, vec_ok);
         PCFE_LAUNCH_CHECK();

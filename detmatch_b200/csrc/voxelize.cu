@@ -48,13 +48,11 @@ int g_opt_hv_wave = 0;
 extern int g_opt_bucket_avg;
 extern int g_opt_bucket_variant;
 extern int g_opt_expand_variant;
-extern int g_opt_expand_pad_kb;
 extern int g_opt_expand_ctas;
 extern int g_opt_pdl;
 extern int g_opt_expand_vpw;
 extern int g_opt_no_fast_div;
 extern int g_opt_expand_prefetch;
-extern int g_opt_expand_skip;
 extern int g_opt_mega_d1, g_opt_mega_d2, g_opt_mega_d3, g_opt_mega_ring, g_opt_mega_ctas, g_opt_mega_stats;
 
 namespace {
@@ -311,9 +309,14 @@ extern "C" int pcfe_debug_axis_sweep(float lo, float vs, float hi, uint64_t* out
   return PCFE_OK;
 }
 
-// Test / tuning knobs: "hv_path" (0 auto, 1 global-memory path, 2 bucket path),
-// "hv_force_overflow" (1: every frame also runs the overflow fallback), "hv_bucket_avg"
-// (target points per bucket).  Returns PCFE_ERR_SHAPE for an unknown name.
+// Test / tuning knobs (every setting computes the same, bit-exact results; they select code paths
+// and launch parameters): "hv_path" (0 auto, 1 global-memory path, 2 bucket path, 3 persistent
+// pipeline), "hv_force_overflow" (1: every frame also runs the overflow fallback), "hv_bucket_avg"
+// (target points per bucket), "hv_wave" (frames per launch sequence), "hv_bucket_variant" (1: general
+// kernels instead of the record path), "hv_expand_variant" (1: un-pipelined expansion kernels),
+// "hv_expand_prefetch" (frames of L2 prefetch distance), "hv_no_fast_div", "hv_pdl",
+// "hv_expand_ctas" (persistent expansion), "hv_expand_vpw", "mega_*" (pipeline offsets / ring /
+// CTAs / stage statistics).  Returns PCFE_ERR_SHAPE for an unknown name.
 extern "C" int pcfe_debug_set(const char* name, int value) {
   if (!name) return PCFE_ERR_NULL;
   if (!strcmp(name, "hv_path")) g_opt_hv_path = value;
@@ -324,11 +327,9 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_expand_variant")) g_opt_expand_variant = value;
   else if (!strcmp(name, "hv_expand_prefetch")) g_opt_expand_prefetch = value;
   else if (!strcmp(name, "hv_no_fast_div")) g_opt_no_fast_div = value;
-  else if (!strcmp(name, "hv_expand_pad_kb")) g_opt_expand_pad_kb = value;
   else if (!strcmp(name, "hv_expand_vpw")) g_opt_expand_vpw = value > 0 ? value : 4;
   else if (!strcmp(name, "hv_pdl")) g_opt_pdl = value;
   else if (!strcmp(name, "hv_expand_ctas")) g_opt_expand_ctas = value;
-  else if (!strcmp(name, "hv_expand_skip")) g_opt_expand_skip = value;
   else if (!strcmp(name, "mega_d1")) g_opt_mega_d1 = value;
   else if (!strcmp(name, "mega_d2")) g_opt_mega_d2 = value;
   else if (!strcmp(name, "mega_d3")) g_opt_mega_d3 = value;
