@@ -896,7 +896,7 @@ hvb_bucket_rank_kernel(const HvbWork w, const int pe /* max(max_points, 1) */, c
     bitonic_sort_256<4>(v, K, tid);
     kv[0] = v[0]; kv[1] = v[1]; kv[2] = v[2]; kv[3] = v[3];
   } else {
-#if PCFE_BUCKET_THREADS <= 256
+#if PCFE_BUCKET_THREADS == 256
     bitonic_sort_256<8>(kv, K, tid);
 #endif
   }
