@@ -2,32 +2,38 @@
 //
 // Behaviour reproduced bit for bit: mmdet3d/ops/voxel/src/voxelization_cpu.cpp:43-99.
 //
-// Measured on B200 (tests/native/microbench.cu): random L2 atomics 135 Gops/s, shared-memory
-// atomics 1500 Gops/s chip-wide.  So points are first partitioned by a hash of their cell key into
-// NB buckets per frame (streaming, coalesced), and all grouping work -- cell de-duplication,
-// per-cell point counts, per-cell sorted lists of the first P point indices -- happens in the
-// shared memory of the one CTA that owns a bucket.  Only two things are global per frame: the
-// bit-per-point "is first point of its voxel" mask whose popcount prefix gives voxel ids in
-// first-occurrence order, and the voxel-id -> record map the final expansion pass reads.
+// Measured on B200 (tests/native/microbench.cu, mb_emit.cu): random L2 atomics 135 Gops/s,
+// shared-memory atomics 1500 Gops/s chip-wide, partial-sector scattered L2 writes 3-7x the cost of
+// full sectors.  So points are first partitioned by a hash of their cell key into NB buckets per
+// frame (streaming, coalesced), all grouping work -- cell de-duplication, the first P point indices
+// of every cell in ascending order -- happens in the shared memory of the one CTA that owns a
+// bucket, and nothing is ever scattered by voxel id.  The only frame-wide structure is a bit per
+// point, "is the first point of its voxel": the popcount rank of that bit IS the voxel id
+// (first-occurrence order without sorting).
 //
-//   A  hvb_bin      rows -> cell key -> bucket = top hash bits; a 4096-point tile is counting-
-//                   sorted by bucket in shared memory and written as contiguous runs of
-//                   (key, point index) entries into the per-bucket regions (one L2 atomicAdd
-//                   per (tile, bucket)).
-//   B  hvb_bucket   one CTA per (frame, bucket): smem open-addressing table of the bucket's
-//                   cells; pass 1 counts points per cell; a block scan sizes per-cell lists
-//                   (min(count, P) entries); pass 2 inserts point indices into the sorted lists
-//                   (smem atomicMin chains); then each cell is emitted as a variable-length record
-//                   {key, len, idx[len]} plus a directory entry, and its first point is flagged
-//                   in the bitmask.
-//   C  hv_scan_flags popcount prefix of the bitmask per frame; voxel_num = min(#cells, V).
-//   D  hvb_order    directory entry -> voxel id = rank of the cell's first point;
-//                   order[vid] = record offset.
-//   E  hvb_expand   voxel-id order: a warp resolves the source points of 32 consecutive output rows
-//                   and moves them with transposed, fully coalesced stores (data + zero padding);
-//                   plus coors and counts.
-//   F  fallback     (hv_global.cu, one CTA per frame) for frames whose bucket regions overflowed
-//                   (heavy duplication / adversarial keys); a no-op launch otherwise.
+// Record path (max_points == 5, C = 4 or 5, 16-byte aligned buffers: KITTI / Waymo voxels):
+//   hvb_zero          counters and mask words of the wave
+//   hvb_bin           rows -> cell key (hoisted-reciprocal exact division) -> bucket = top hash
+//                     bits; a 4096-point tile is counting-sorted by bucket in shared memory and
+//                     written as contiguous runs of (key, point index) entries (one L2 atomicAdd
+//                     per (tile, bucket))
+//   hvb_bucket_rec    one CTA per (frame, bucket): TMA-staged entries, open-addressing table, one
+//                     chain per cell, register sort of the 5 smallest indices; a cell with more
+//                     than one point writes ONE 16-byte record at rec[first point]; one 64-bit
+//                     atomicOr sets "first point" and "has a record"
+//   hvb_scan_firsts   voxel id -> first point index (+ has-record bit): coalesced compaction of the
+//                     mask; voxel_num = min(#cells, V)
+//   hvb_expand_rec    voxel-id order, pipelined over 32-voxel tiles (firsts -> records -> rows),
+//                     lane = output word, 128-byte coalesced streaming stores, coordinates
+//                     recomputed from the first point
+//   fallback          (hv_global.cu, one CTA per frame) for frames whose bucket regions overflowed
+//                     (heavy duplication / adversarial keys); a no-op launch otherwise
+// The launches after hvb_zero are programmatic dependents of their predecessor.
+//
+// General path (any max_points / C / alignment): hvb_bin -> hvb_bucket_small<5|8> (P <= 8: chains +
+// register sort) or hvb_bucket_rank (any P: bitonic sort of (cell, point) keys) or hvb_bucket (the
+// first version: counts + atomicMin lists, kept as a cross-check) -> cells + list arena ->
+// hv_scan_flags -> hvb_order (cell -> voxel-id order) -> hvb_expand / _fixed / _pipe / _words.
 #include <algorithm>
 #include <mutex>
 
@@ -44,10 +50,10 @@ int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size
                     int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st);
 
 int g_opt_bucket_avg = 1024;  // target points per bucket (tunable through pcfe_debug_set)
-int g_opt_bucket_variant = 0;  // 1: always use the general (count + atomicMin lists) bucket kernel
+int g_opt_bucket_variant = 0;  // 1: general path with the first-version (atomicMin lists) bucket kernel
 int g_opt_no_fast_div = 0;      // 1: __fdiv_rn for every point (no hoisted reciprocal)
 int g_opt_expand_variant = 0;  // 1: un-pipelined fixed-P expansion kernel
-int g_opt_expand_prefetch = 1;
+int g_opt_expand_prefetch = 1;  // frames of L2 prefetch distance in the expansion (0 = off)
 int g_opt_expand_vpw = 4;       // long-voxel expansion: voxels per warp
 int g_opt_pdl = 1;              // programmatic dependent launch between the record path's kernels
 int g_opt_expand_ctas = 0;      // > 0: persistent expansion with this many CTAs per SM
