@@ -111,6 +111,38 @@ def test_caps(p, v):
     _check_hard(pts, [0.5, 0.5, 0.5], KITTI, p, v, f"caps P={p} V={v}")
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_small_configs(seed):
+    """Randomised frames, grids and caps (seeded): sizes around the tile / warp / bucket boundaries,
+    duplicated points, points on cell faces, out-of-range and non-finite rows, every row length the
+    kernels specialise on -- against the CPU op on every hard-voxelize path."""
+    rng = np.random.default_rng(7700 + seed)
+    n = int(rng.choice([1, 2, 33, 257, 4095, 4096, 4097, 9000, 30011]))
+    c = int(rng.choice([3, 4, 5, 6]))
+    p = int(rng.choice([1, 2, 5, 5, 5, 8, 9, 35]))
+    vs = [float(rng.choice([0.05, 0.1, 0.25, 0.5, 1.0])) for _ in range(2)] + [float(rng.choice([0.1, 0.5, 4.0]))]
+    lo = np.array([rng.uniform(-60, 0), rng.uniform(-40, 0), rng.uniform(-5, -1)])
+    span = np.array([rng.uniform(4, 80), rng.uniform(4, 80), 4.0])
+    rg = [float(x) for x in np.concatenate([lo, lo + span])]
+    xyz = rng.uniform(lo - 0.05 * span, lo + 1.05 * span, size=(n, 3))
+    k = n // 3
+    if k:  # duplicates (same cell, same coordinates) and points exactly on cell faces
+        xyz[rng.integers(0, n, k)] = xyz[rng.integers(0, n, k)]
+        on = rng.integers(0, n, k)
+        xyz[on] = lo + np.round((xyz[on] - lo) / np.array(vs)) * np.array(vs)
+    pts = np.concatenate([xyz, rng.uniform(0, 1, size=(n, c - 3))], axis=1).astype(np.float32)
+    if n > 40:
+        pts[7, 0] = np.nan
+        pts[11, 1] = np.inf
+        pts[13, 2] = -np.inf
+        pts[17, 0] = 3e38
+    cells = len(np.unique(oracle.dynamic_voxelize(pts, vs, rg), axis=0))
+    v = int(rng.choice([1, max(1, cells // 2), cells + 5, 200000]))
+    _check_hard(pts, vs, rg, p, v, f"random seed={seed} N={n} C={c} P={p} V={v}")
+    d = voxelization(torch.from_numpy(pts).cuda(), vs, rg, -1, -1)
+    assert_same_bits(d.cpu().numpy(), oracle.dynamic_voxelize(pts, vs, rg), "dyn")
+
+
 def test_heavy_contention_single_voxel():
     """All points in very few voxels: the sorted per-voxel lists must still come out in index order."""
     rng = np.random.default_rng(5)
