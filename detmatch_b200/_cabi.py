@@ -44,6 +44,8 @@ PROTOTYPES = {
                                        c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "pcfe_hard_voxelize_batch_f32": (c_int, [ctypes.POINTER(Frame), c_int, c_int, _f3, _f6, c_int, c_int,
                                              c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "pcfe_hard_voxelize_batch_filtered_f32": (c_int, [ctypes.POINTER(Frame), c_int, c_int, _f3, _f6, _f6, c_int, c_int,
+                                                      c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "pcfe_points_in_boxes_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pcfe_points_in_boxes_part_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
                                               c_size_t, c_int, c_void_p]),

@@ -167,6 +167,12 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
   // computed without any control flow; otherwise all eight take the plain IEEE divide.
   uint32_t key[kBinPerThread];
   bool guard_ok = use_fast_div != 0;
+  uint32_t fmask = 0xFFFFFFFFu;  // bit k: point k passes the fused PointsRangeFilter
+  if (g.filter) {
+    fmask = 0u;
+#pragma unroll
+    for (int k = 0; k < kBinPerThread; ++k) fmask |= filter_pass(ax[k], ay[k], az[k], g) ? (1u << k) : 0u;
+  }
 #pragma unroll
   for (int k = 0; k < kBinPerThread; ++k) {
     ax[k] = __fsub_rn(ax[k], g.x0);
@@ -184,7 +190,7 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
       const int cx = __float2int_rz(qx), cy = __float2int_rz(qy), cz = __float2int_rz(qz);
       const bool ok = (qmax < 0x4F000000u) & (cx < g.gx) & (cy < g.gy) & (cz < g.gz);
       const uint32_t lin = ((uint32_t)cz * (uint32_t)g.gy + (uint32_t)cy) * (uint32_t)g.gx + (uint32_t)cx;
-      key[k] = ok ? lin : kEmpty;
+      key[k] = (ok && ((fmask >> k) & 1u)) ? lin : kEmpty;
     }
   } else {
 #pragma unroll
@@ -196,7 +202,7 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
       const int cx = in ? __float2int_rz(qx) : -1, cy = in ? __float2int_rz(qy) : -1, cz = in ? __float2int_rz(qz) : -1;
       const bool ok = in & (cx < g.gx) & (cy < g.gy) & (cz < g.gz);
       const uint32_t lin = ((uint32_t)cz * (uint32_t)g.gy + (uint32_t)cy) * (uint32_t)g.gx + (uint32_t)cx;
-      key[k] = ok ? lin : kEmpty;
+      key[k] = (ok && ((fmask >> k) & 1u)) ? lin : kEmpty;
     }
   }
   // rank of every entry inside its (tile, bucket) run; rb = bucket << 16 | rank

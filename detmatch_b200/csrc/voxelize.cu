@@ -226,10 +226,10 @@ extern "C" size_t pcfe_hard_voxelize_workspace_bytes(int64_t n_max, int num_fram
   return (size_t)w * per * nbuf;
 }
 
-extern "C" int pcfe_hard_voxelize_batch_f32(const pcfe_frame_t* frames, int num_frames, int c,
-                                            const float vs[3], const float rg[6], int max_points,
-                                            int max_voxels, int32_t* voxel_num, void* workspace,
-                                            size_t workspace_bytes, int device, void* stream) {
+static int hv_batch_impl(const pcfe_frame_t* frames, int num_frames, int c, const float vs[3],
+                         const float rg[6], const float* filter /* 6 floats or NULL */, int max_points,
+                         int max_voxels, int32_t* voxel_num, void* workspace, size_t workspace_bytes,
+                         int device, void* stream) {
   if (num_frames < 0 || c < 3) return PCFE_ERR_SHAPE;
   if (num_frames == 0) return PCFE_OK;
   if (!frames || !voxel_num) return PCFE_ERR_NULL;
@@ -248,6 +248,15 @@ extern "C" int pcfe_hard_voxelize_batch_f32(const pcfe_frame_t* frames, int num_
   HvChoice ch;
   int rc = choose_path(n_max, c, vs, rg, max_points, max_voxels, &ch);
   if (rc != PCFE_OK) return rc;
+  if (filter) {  // fused PointsRangeFilter: every path reads it from its GridParams
+    for (GridParams* g : {&ch.bp.g, &ch.bp.slow.g, &ch.gp.g}) {
+      g->filter = 1;
+      for (int j = 0; j < 3; ++j) {
+        g->flo[j] = filter[j];
+        g->fhi[j] = filter[3 + j];
+      }
+    }
+  }
 
   DeviceGuard guard(device);
   PCFE_CUDA_TRY(guard.err);
@@ -280,6 +289,24 @@ extern "C" int pcfe_hard_voxelize_batch_f32(const pcfe_frame_t* frames, int num_
     return hvb_run(frames, num_frames, c, ch.bp, max_points, max_voxels, voxel_num, workspace, wave,
                    nbuf, device, st);
   return hvg_run(frames, num_frames, c, ch.gp, max_points, max_voxels, voxel_num, workspace, wave, st);
+}
+
+extern "C" int pcfe_hard_voxelize_batch_f32(const pcfe_frame_t* frames, int num_frames, int c,
+                                            const float vs[3], const float rg[6], int max_points,
+                                            int max_voxels, int32_t* voxel_num, void* workspace,
+                                            size_t workspace_bytes, int device, void* stream) {
+  return hv_batch_impl(frames, num_frames, c, vs, rg, nullptr, max_points, max_voxels, voxel_num, workspace,
+                       workspace_bytes, device, stream);
+}
+
+extern "C" int pcfe_hard_voxelize_batch_filtered_f32(const pcfe_frame_t* frames, int num_frames, int c,
+                                                     const float vs[3], const float rg[6],
+                                                     const float filter_range[6], int max_points,
+                                                     int max_voxels, int32_t* voxel_num, void* workspace,
+                                                     size_t workspace_bytes, int device, void* stream) {
+  if (!filter_range) return PCFE_ERR_NULL;
+  return hv_batch_impl(frames, num_frames, c, vs, rg, filter_range, max_points, max_voxels, voxel_num,
+                       workspace, workspace_bytes, device, stream);
 }
 
 extern "C" int pcfe_hard_voxelize_f32(const float* points, int64_t n, int c, const float vs[3],

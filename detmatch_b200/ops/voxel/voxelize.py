@@ -41,8 +41,12 @@ def voxelization(points, voxel_size, coors_range, max_points=35, max_voxels=2000
                 num_points_per_voxel[:voxel_num].to(home))
 
 
-def voxelize_batch(points, voxel_size, coors_range, max_points, max_voxels, sync=True):
+def voxelize_batch(points, voxel_size, coors_range, max_points, max_voxels, sync=True, points_range=None):
     """Hard-voxelizes a list of (N_i, C) CUDA frames in one launch sequence.
+
+    ``points_range`` (6 floats) fuses the pipeline's ``PointsRangeFilter`` in front
+    (base_points.py:223-228: strict ``lo < p < hi`` on x, y, z): the result equals filtering every
+    frame first (order kept) and voxelizing the filtered frames, without the compaction pass.
 
     Returns ``(voxels, coors, num_points, voxel_num)`` where voxels is (F, max_voxels, max_points,
     C), coors (F, max_voxels, 3), num_points (F, max_voxels) and voxel_num a device int32 (F,)
@@ -72,8 +76,13 @@ def voxelize_batch(points, voxel_size, coors_range, max_points, max_voxels, sync
         vs, rg = _cabi.f3(voxel_size), _cabi.f6(coors_range)
         need = L.pcfe_hard_voxelize_workspace_bytes(n_max, nf, 0, vs, rg, max_points, max_voxels)
         ws = workspace(dev, need)
-        rc = L.pcfe_hard_voxelize_batch_f32(frames, nf, c, vs, rg, max_points, max_voxels, ptr(voxel_num),
-                                            ptr(ws), ws.numel(), dev.index, stream_ptr(dev))
+        if points_range is None:
+            rc = L.pcfe_hard_voxelize_batch_f32(frames, nf, c, vs, rg, max_points, max_voxels, ptr(voxel_num),
+                                                ptr(ws), ws.numel(), dev.index, stream_ptr(dev))
+        else:
+            rc = L.pcfe_hard_voxelize_batch_filtered_f32(frames, nf, c, vs, rg, _cabi.f6(points_range), max_points,
+                                                         max_voxels, ptr(voxel_num), ptr(ws), ws.numel(), dev.index,
+                                                         stream_ptr(dev))
         _cabi.check(rc, "pcfe_hard_voxelize_batch_f32")
         if not sync:
             return voxels, coors, num, voxel_num
@@ -94,12 +103,13 @@ class HardVoxelizeBatchPlan:
     """
 
     def __init__(self, sizes, num_features, voxel_size, coors_range, max_points, max_voxels, device,
-                 frames_in_flight=0):
+                 frames_in_flight=0, points_range=None):
         self.device = torch.device(device)
         self.sizes = [int(n) for n in sizes]
         self.c = int(num_features)
         self.max_points, self.max_voxels = int(max_points), int(max_voxels)
         self.vs, self.rg = _cabi.f3(voxel_size), _cabi.f6(coors_range)
+        self.filter = None if points_range is None else _cabi.f6(points_range)  # fused PointsRangeFilter
         nf = len(self.sizes)
         dev = self.device
         self.voxels = torch.empty((nf, max_voxels, max_points, self.c), dtype=torch.float32, device=dev)
@@ -124,10 +134,17 @@ class HardVoxelizeBatchPlan:
         return self
 
     def run(self):
-        rc = _cabi.lib().pcfe_hard_voxelize_batch_f32(self.frames, len(self.sizes), self.c, self.vs, self.rg,
-                                                      self.max_points, self.max_voxels, ptr(self.voxel_num),
-                                                      ptr(self.ws), self.ws.numel(), self.device.index,
-                                                      stream_ptr(self.device))
+        L = _cabi.lib()
+        if self.filter is None:
+            rc = L.pcfe_hard_voxelize_batch_f32(self.frames, len(self.sizes), self.c, self.vs, self.rg,
+                                                self.max_points, self.max_voxels, ptr(self.voxel_num),
+                                                ptr(self.ws), self.ws.numel(), self.device.index,
+                                                stream_ptr(self.device))
+        else:
+            rc = L.pcfe_hard_voxelize_batch_filtered_f32(self.frames, len(self.sizes), self.c, self.vs, self.rg,
+                                                         self.filter, self.max_points, self.max_voxels,
+                                                         ptr(self.voxel_num), ptr(self.ws), self.ws.numel(),
+                                                         self.device.index, stream_ptr(self.device))
         _cabi.check(rc, "pcfe_hard_voxelize_batch_f32")
         return self.voxels, self.coors, self.num_points, self.voxel_num
 

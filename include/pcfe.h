@@ -142,6 +142,17 @@ int pcfe_hard_voxelize_batch_f32(const pcfe_frame_t* frames, int num_frames, int
                                  int max_points, int max_voxels, int32_t* voxel_num,
                                  void* workspace, size_t workspace_bytes, int device, void* stream);
 
+/* The same with PointsRangeFilter fused in front (mmdet3d/datasets/pipelines/transforms_3d.py
+ * PointsRangeFilter -> BasePoints.in_range_3d, mmdet3d/core/points/base_points.py:223-228): only
+ * points with filter_range[j] < p[j] < filter_range[3 + j] on x, y, z (strict, float32) take part.
+ * Results equal "drop the other rows (order kept), then hard_voxelize" -- voxels, coors,
+ * num_points, voxel_num bit for bit -- without the compaction pass or the filtered copy. */
+int pcfe_hard_voxelize_batch_filtered_f32(const pcfe_frame_t* frames, int num_frames, int c,
+                                          const float voxel_size[3], const float coors_range[6],
+                                          const float filter_range[6], int max_points, int max_voxels,
+                                          int32_t* voxel_num, void* workspace, size_t workspace_bytes,
+                                          int device, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * points in boxes
  * Replaces: roiaware_pool3d_ext.points_in_boxes_{gpu,batch,cpu}(boxes, points, out)

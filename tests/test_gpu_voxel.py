@@ -361,3 +361,33 @@ def test_fast_division_equals_ieee_divide_exhaustive(lo, vs, hi, hv_mode):
     assert rc == 0
     bad, first = out.cpu().tolist()
     assert bad == 0, f"{bad} coordinates disagree with the IEEE divide, first bits {first & 0xFFFFFFFF:#x}"
+
+
+@pytest.mark.parametrize("cfg_name,ci", [("C1", 1), ("C4", 4), ("C5", 5)])
+def test_fused_points_range_filter(cfg_name, ci):
+    """voxelize_batch(points_range=...) == PointsRangeFilter (base_points.py:223-228, strict on both
+    sides, float32) followed by hard voxelization of the filtered frames: bit for bit, including
+    points exactly on the filter faces, NaN rows and a filter range tighter than the voxel range."""
+    cfg = synth.CONFIGS[cfg_name]
+    rg = cfg["point_cloud_range"]
+    frames = []
+    for k in range(3):
+        p = synth.lidar_frame(20000 + 1000 * k, cfg["c"], 5000 + 10 * ci + k, cfg["r_max"]).numpy().copy()
+        p[5, 0] = rg[0]          # on the lower face: the filter drops it, plain voxelization keeps it
+        p[6, 1] = rg[4]          # on the upper face
+        p[7, 2] = np.nan
+        p[8, 0] = np.float32(rg[3]) - np.float32(1e-3)
+        frames.append(p)
+    for fr in (rg, [rg[0] + 3.0, rg[1] + 1.5, rg[2] + 0.2, rg[3] - 7.0, rg[4] - 2.5, rg[5] - 0.4]):
+        lo, hi = np.asarray(fr[:3], np.float32), np.asarray(fr[3:], np.float32)
+        P, V = cfg["max_num_points"], min(cfg["max_voxels"], 9000)
+        vox, coors, num, vnum = voxelize_batch([torch.from_numpy(p).cuda() for p in frames], cfg["voxel_size"], rg, P, V,
+                                               sync=False, points_range=fr)
+        counts = vnum.cpu().tolist()
+        for k, p in enumerate(frames):
+            keep = np.all(p[:, :3] > lo, axis=1) & np.all(p[:, :3] < hi, axis=1)
+            ev, ec, en = oracle.hard_voxelize(np.ascontiguousarray(p[keep]), cfg["voxel_size"], rg, P, V)
+            assert counts[k] == len(en)
+            assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"{cfg_name} frame {k} coors")
+            assert_same_bits(num[k, :counts[k]].cpu().numpy(), en, f"{cfg_name} frame {k} num")
+            assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"{cfg_name} frame {k} voxels")
