@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PCFE_LIB") or os.path.join(_HERE, "lib", "libpcfe.so")
 
 _lib = None
+ERR_SHAPE = -2  # PCFE_ERR_SHAPE
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
@@ -46,6 +47,9 @@ PROTOTYPES = {
                                              c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "pcfe_hard_voxelize_batch_filtered_f32": (c_int, [ctypes.POINTER(Frame), c_int, c_int, _f3, _f6, _f6, c_int, c_int,
                                                       c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "pcfe_voxel_mean_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "pcfe_hard_voxelize_mean_batch_f32": (c_int, [ctypes.POINTER(Frame), c_int, c_int, _f3, _f6, ctypes.POINTER(ctypes.c_float),
+                                                  c_int, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "pcfe_points_in_boxes_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pcfe_points_in_boxes_part_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
                                               c_size_t, c_int, c_void_p]),

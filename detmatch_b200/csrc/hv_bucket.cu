@@ -47,7 +47,7 @@ int hv_launch_scan(const uint32_t* bitmask, size_t bitmask_stride, uint32_t* pre
 int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size_t overflow_stride,
                     int force, char* scratch_base, size_t scratch_stride, const HvGlobalPlan& p,
                     uint32_t* bitmask, size_t bitmask_stride, uint32_t* prefix, size_t prefix_stride,
-                    int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st);
+                    int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st, int mean);
 
 int g_opt_bucket_avg = 1024;  // target points per bucket (tunable through pcfe_debug_set)
 int g_opt_bucket_variant = 0;  // 1: general path with the first-version (atomicMin lists) bucket kernel
@@ -1373,7 +1373,10 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
 #ifndef PCFE_EXP_REC_MINB
 #define PCFE_EXP_REC_MINB 8
 #endif
-template <int C>
+// MEAN: instead of the (P, C) rows of a voxel, the mean of its points is written (fr.voxels is a
+// (max_voxels, C) buffer): sum over the P slots in slot order (absent slots are +0, as in the
+// zero-padded tensor HardSimpleVFE sums, voxel_encoder.py:27-44), IEEE divide by the count.
+template <int C, bool MEAN>
 __global__ void __launch_bounds__(kExpThreads, PCFE_EXP_REC_MINB)
 hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
                       const int use_fast_div,
@@ -1385,6 +1388,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   // source word (point index * C + feature) of every output word of a warp's tile, kEmpty = zero
   __shared__ uint32_t eff_all[kExpWarps * 32 * W];
   __shared__ __align__(16) int32_t coor_all[kExpWarps * 96];  // (z, y, x) of a tile: one coalesced store
+  __shared__ float mean_all[MEAN ? kExpWarps * 32 * C : 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t* eff = eff_all + wid * (32 * W);
   int32_t* cstage = coor_all + wid * 96;
@@ -1473,6 +1477,25 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
       cstage[lane * 3 + 2] = __float2int_rz(qx);
     }
     __syncwarp();
+    if (MEAN) {
+      // rows back to (voxel, slot, feature) order through the tile buffer (every lane has read its
+      // source words: the __syncwarp() above), then lane = voxel sums its slots
+      float* tile = reinterpret_cast<float*>(eff);
+#pragma unroll
+      for (int k = 0; k < W; ++k) tile[lane + 32 * k] = val[k];
+      __syncwarp();
+      float* mstage = mean_all + wid * (32 * C);
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        float a = tile[lane * W + q];
+#pragma unroll
+        for (int j = 1; j < PT; ++j) a = __fadd_rn(a, tile[lane * W + j * C + q]);
+        mstage[lane * C + q] = have ? __fdiv_rn(a, (float)len) : 0.0f;
+      }
+      __syncwarp();
+      float* __restrict__ mdst = fr.voxels + (size_t)v0 * C;
+      for (int i = lane; i < nvox * C; i += 32) mdst[i] = mstage[i];
+    } else {
     float* __restrict__ dst = fr.voxels + (size_t)v0 * W;
     if (nvox == 32) {
 #pragma unroll
@@ -1481,6 +1504,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
 #pragma unroll
       for (int k = 0; k < W; ++k)
         if (lane + 32 * k < nvox * W) __stcs(dst + lane + 32 * k, val[k]);
+    }
     }
     {  // coordinates: 3 * nvox words, contiguous; v0 % 32 == 0 keeps the run 16-byte aligned
       int32_t* __restrict__ cdst = fr.coors + (size_t)v0 * 3;
@@ -1646,7 +1670,7 @@ static int get_aux(int device, AuxStreams** out) {
 
 int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPlan& p,
             int max_points, int max_voxels, int32_t* voxel_num, void* workspace, int wave,
-            int nbuf, int device, cudaStream_t user_st) {
+            int nbuf, int device, cudaStream_t user_st, int mean) {
   std::lock_guard<std::mutex> lk(g_aux_mu);
   const int nwaves = (num_frames + wave - 1) / wave;
   const bool overlap = nbuf >= 2 && nwaves >= 2;
@@ -1685,7 +1709,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
   const int pe = std::max(max_points, 1);
   int vec_ok = 1;  // float4 tile stream / vector row loads need 16-byte aligned buffers
   for (int k = 0; k < num_frames && vec_ok; ++k)
-    vec_ok = !(((uintptr_t)frames[k].voxels & 15) || ((uintptr_t)frames[k].points & 15));
+    vec_ok = !((!mean && ((uintptr_t)frames[k].voxels & 15)) || ((uintptr_t)frames[k].points & 15));
   int coors_vec = 1;
   for (int k = 0; k < num_frames && coors_vec; ++k) coors_vec = !((uintptr_t)frames[k].coors & 15);
 
@@ -1705,6 +1729,10 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       b.f[k] = HvFrame{fr.points, fr.voxels, fr.coors, fr.num_points, (int)fr.n, 0};
       wn_max = std::max(wn_max, fr.n);
     }
+    // the mean epilogue exists on the record path only (P == 5, C = 4 / 5, aligned buffers)
+    if (mean && !(max_points == 5 && (c == 4 || c == 5) && vec_ok && max_voxels < (1 << 24) && wn_max < 0xFFFFFF &&
+                  g_opt_bucket_variant != 1))
+      return PCFE_ERR_SHAPE;
     {
       ProfScope ps("memset_ctl", st);
       if (g_opt_pdl) {  // a kernel instead of a memset node, so that the bin kernel can be its
@@ -1758,8 +1786,15 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         const int tiles_x = (int)pgrid.x;
         unsigned egrid = pgrid.x * pgrid.y;
         if (g_opt_expand_ctas > 0) egrid = std::min<unsigned>(egrid, (unsigned)(g_opt_expand_ctas * 148));
-        if (c == 4) PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<4>, dim3(egrid), dim3(kExpThreads), 0, st, g_opt_pdl != 0, b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, tiles_x));
-        else PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<5>, dim3(egrid), dim3(kExpThreads), 0, st, g_opt_pdl != 0, b, w, p.g, fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, tiles_x));
+        const bool pdl = g_opt_pdl != 0;
+#define PCFE_LAUNCH_EXPAND_REC(CC, MM)                                                                          \
+  PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<CC, MM>, dim3(egrid), dim3(kExpThreads), 0, st, pdl, b, w, p.g, fdiv, \
+                           vn, wv, g_opt_expand_prefetch, coors_vec, tiles_x))
+        if (c == 4 && mean) PCFE_LAUNCH_EXPAND_REC(4, true);
+        else if (c == 4) PCFE_LAUNCH_EXPAND_REC(4, false);
+        else if (mean) PCFE_LAUNCH_EXPAND_REC(5, true);
+        else PCFE_LAUNCH_EXPAND_REC(5, false);
+#undef PCFE_LAUNCH_EXPAND_REC
         PCFE_LAUNCH_CHECK();
       }
     } else {
@@ -1836,7 +1871,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     rc = hvg_launch_slow(b, wv, w.zero + w.ctl_off + p.nb + kCtlOverflow, w.zero_stride,
                          g_opt_force_overflow, w.region, w.region_stride, p.slow, w.zero,
                          w.zero_stride, w.wordprefix, w.word_stride, c, max_points, max_voxels,
-                         voxel_num + f0, st);
+                         voxel_num + f0, st, mean);
     if (rc != PCFE_OK) return rc;
   }
   if (overlap) {

@@ -245,7 +245,7 @@ hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, const uint32_t* __r
                       uint32_t* __restrict__ bitmask_base, const size_t bitmask_stride,
                       uint32_t* __restrict__ prefix_base, const size_t prefix_stride, const int c,
                       const int max_points, const int max_voxels, int32_t* __restrict__ voxel_num,
-                      const int frames, const int ring) {
+                      const int frames, const int ring, const int mean) {
   // CTA r serves frames r, r + ring, ... one after the other in scratch region r (ring == frames:
   // one frame per CTA)
   __shared__ uint32_t warp_sums[33];
@@ -326,8 +326,25 @@ hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, const uint32_t* __r
       sorted_insert<true>(idxlist + (size_t)vid * max_points, max_points, (uint32_t)i);
   }
   __syncthreads();
-  // phase 5: rows + counts
+  // phase 5: rows + counts (mean: the per-voxel mean of the kept points instead of the rows --
+  // slot-order sum over all max_points slots, absent ones being +0, then an IEEE divide)
   const long long rows = (long long)m * max_points;
+  if (mean) {
+    for (long long e = tid; e < (long long)m * c; e += kSlowThreads) {
+      const long long v = e / c;
+      const int j = (int)(e - v * c);
+      const uint32_t* lst = idxlist + (size_t)v * max_points;
+      float a = 0.0f;
+      int cnt = 0;
+      for (int sl = 0; sl < max_points; ++sl) {
+        const uint32_t idx = __ldcg(&lst[sl]);
+        const float x = (idx != kEmpty) ? __ldg(fr.pts + (size_t)idx * c + j) : 0.0f;
+        a = sl == 0 ? x : __fadd_rn(a, x);
+        cnt += (idx != kEmpty) ? 1 : 0;
+      }
+      fr.voxels[e] = __fdiv_rn(a, (float)cnt);
+    }
+  } else
   for (long long r = tid; r < rows; r += kSlowThreads) {
     const uint32_t idx = __ldcg(&idxlist[r]);
     float* dst = fr.voxels + (size_t)r * c;
@@ -347,11 +364,11 @@ hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, const uint32_t* __r
 int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size_t overflow_stride,
                     int force, char* scratch_base, size_t scratch_stride, const HvGlobalPlan& p,
                     uint32_t* bitmask, size_t bitmask_stride, uint32_t* prefix, size_t prefix_stride,
-                    int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st) {
+                    int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st, int mean) {
   ProfScope ps("hv_slow_fallback", st);
   PCFE_CUDA_TRY(launch_pdl(hvg_slow_frame_kernel, dim3((unsigned)frames), dim3(kSlowThreads), 0, st, true, b, overflow,
                            overflow_stride, force, scratch_base, scratch_stride, p, bitmask, bitmask_stride,
-                           prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, frames));
+                           prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, frames, mean));
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
@@ -365,7 +382,7 @@ int hvg_launch_slow_ring(const HvBatch& b, int frames, int ring, const uint32_t*
   ProfScope ps("hv_slow_fallback", st);
   hvg_slow_frame_kernel<<<std::min(frames, ring), kSlowThreads, 0, st>>>(
       b, overflow, overflow_stride, force, scratch_base, scratch_stride, p, bitmask, bitmask_stride,
-      prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, ring);
+      prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, ring, 0);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }

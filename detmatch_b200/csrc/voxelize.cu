@@ -229,7 +229,7 @@ extern "C" size_t pcfe_hard_voxelize_workspace_bytes(int64_t n_max, int num_fram
 static int hv_batch_impl(const pcfe_frame_t* frames, int num_frames, int c, const float vs[3],
                          const float rg[6], const float* filter /* 6 floats or NULL */, int max_points,
                          int max_voxels, int32_t* voxel_num, void* workspace, size_t workspace_bytes,
-                         int device, void* stream) {
+                         int device, void* stream, int mean = 0) {
   if (num_frames < 0 || c < 3) return PCFE_ERR_SHAPE;
   if (num_frames == 0) return PCFE_OK;
   if (!frames || !voxel_num) return PCFE_ERR_NULL;
@@ -277,6 +277,11 @@ static int hv_batch_impl(const pcfe_frame_t* frames, int num_frames, int c, cons
     nbuf = 1;
     wave = (int)std::min<size_t>(wave, fit);
   }
+  if (mean) {  // fused mean epilogue: record path of the bucket launch sequence only
+    if (!ch.bucket || g_opt_hv_path == 3) return PCFE_ERR_SHAPE;
+    return hvb_run(frames, num_frames, c, ch.bp, max_points, max_voxels, voxel_num, workspace, wave, nbuf,
+                   device, st, 1);
+  }
   if (ch.bucket && g_opt_hv_path == 3) {
     // experimental: the persistent frame pipeline (hv_mega.cu); measured slower than the launch
     // sequence on B200 (0.73 vs 0.56 ms per C4 step: dependency waits + register-limited occupancy)
@@ -307,6 +312,54 @@ extern "C" int pcfe_hard_voxelize_batch_filtered_f32(const pcfe_frame_t* frames,
   if (!filter_range) return PCFE_ERR_NULL;
   return hv_batch_impl(frames, num_frames, c, vs, rg, filter_range, max_points, max_voxels, voxel_num,
                        workspace, workspace_bytes, device, stream);
+}
+
+extern "C" int pcfe_hard_voxelize_mean_batch_f32(const pcfe_frame_t* frames, int num_frames, int c,
+                                                 const float vs[3], const float rg[6],
+                                                 const float* filter_range, int max_points, int max_voxels,
+                                                 int32_t* voxel_num, void* workspace, size_t workspace_bytes,
+                                                 int device, void* stream) {
+  if (max_points != 5 || (c != 4 && c != 5)) return PCFE_ERR_SHAPE;
+  return hv_batch_impl(frames, num_frames, c, vs, rg, filter_range, max_points, max_voxels, voxel_num,
+                       workspace, workspace_bytes, device, stream, 1);
+}
+
+// One thread per output element; a warp's loads of slot s cover 32 consecutive words of at most
+// ceil(32 / c) + 1 voxels, the remaining words of those sectors are used by the next slots (L1).
+__global__ void __launch_bounds__(256)
+voxel_mean_kernel(const float* __restrict__ voxels, const int32_t* __restrict__ num_points,
+                  const int32_t* __restrict__ voxel_num, const long long m_cap, const int max_points,
+                  const int c, float* __restrict__ out) {
+  const long long m = voxel_num ? min((long long)__ldg(voxel_num), m_cap) : m_cap;
+  const long long total = m * c;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long v = e / c;
+    const int q = (int)(e - v * c);
+    const float* src = voxels + (size_t)v * max_points * c + q;
+    float a = __ldg(src);
+    for (int sl = 1; sl < max_points; ++sl) a = __fadd_rn(a, __ldg(src + (size_t)sl * c));
+    out[e] = __fdiv_rn(a, (float)__ldg(num_points + v));
+  }
+}
+
+extern "C" int pcfe_voxel_mean_f32(const float* voxels, const int32_t* num_points, const int32_t* voxel_num,
+                                   int64_t m, int max_points, int c, float* out, int device, void* stream) {
+  if (m < 0 || max_points < 1 || c < 1) return PCFE_ERR_SHAPE;
+  if (m == 0) return PCFE_OK;
+  if (!voxels || !num_points || !out) return PCFE_ERR_NULL;
+  if (((uintptr_t)voxels & 3) || ((uintptr_t)num_points & 3) || ((uintptr_t)out & 3) || ((uintptr_t)voxel_num & 3))
+    return PCFE_ERR_ALIGN;
+  DeviceGuard guard(device);
+  PCFE_CUDA_TRY(guard.err);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)m * c;
+  const long long want = (total + 255) / 256;
+  const int grid = (int)std::min<long long>(want, 148ll * 8 * 16);
+  ProfScope ps("voxel_mean", st);
+  voxel_mean_kernel<<<grid, 256, 0, st>>>(voxels, num_points, voxel_num, m, max_points, c, out);
+  PCFE_LAUNCH_CHECK();
+  return PCFE_OK;
 }
 
 extern "C" int pcfe_hard_voxelize_f32(const float* points, int64_t n, int c, const float vs[3],

@@ -154,6 +154,37 @@ int pcfe_hard_voxelize_batch_filtered_f32(const pcfe_frame_t* frames, int num_fr
                                           int device, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * mean voxel feature encoder (the consumer of hard voxelization in every SECOND / PV-RCNN config)
+ * Replaces: HardSimpleVFE.forward, mmdet3d/models/voxel_encoders/voxel_encoder.py:27-44:
+ *           features[:, :, :num_features].sum(dim=1) / num_points.type_as(features).view(-1, 1)
+ * Arithmetic: float32, slot-order sum ((((s0 + s1) + s2) + ...) over all max_points slots, absent
+ * slots being +0) followed by one IEEE divide by (float)num_points.  (ATen's CPU sum picks its
+ * association from the memory layout -- it equals the slot-order sum for some shapes and differs
+ * in the last bit for others; oracle/vfe_mean.py is the restatement the tests pin bit for bit, and
+ * they bound the distance to ATen's result by 2 ulp.)
+ *
+ * pcfe_voxel_mean_f32: voxels (m, max_points, c) zero padded, num_points (m,) -> out (m, c).
+ * voxel_num (device int32, may be NULL) limits the rows to min(*voxel_num, m) so that the call can
+ * follow a batched voxelization without a host synchronisation.
+ *
+ * pcfe_hard_voxelize_mean_batch_f32: hard voxelization with the encoder fused into the expansion:
+ * frames[i].voxels is a (max_voxels, c) buffer that receives the means; the (max_voxels,
+ * max_points, c) tensor is never written (its 100 B per voxel are 3/4 of the step's compulsory
+ * bytes).  coors / num_points / voxel_num as pcfe_hard_voxelize_batch_f32.  filter_range may be
+ * NULL (no fused PointsRangeFilter).  Only max_points == 5 with c == 4 or 5 and 16-byte aligned
+ * frames (the record path); PCFE_ERR_SHAPE otherwise -- callers then run
+ * pcfe_hard_voxelize_batch_f32 + pcfe_voxel_mean_f32 (detmatch_b200.ops.voxel does).
+ * ------------------------------------------------------------------------------------------- */
+int pcfe_voxel_mean_f32(const float* voxels, const int32_t* num_points, const int32_t* voxel_num,
+                        int64_t m, int max_points, int c, float* out, int device, void* stream);
+
+int pcfe_hard_voxelize_mean_batch_f32(const pcfe_frame_t* frames, int num_frames, int c,
+                                      const float voxel_size[3], const float coors_range[6],
+                                      const float* filter_range, int max_points, int max_voxels,
+                                      int32_t* voxel_num, void* workspace, size_t workspace_bytes,
+                                      int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * points in boxes
  * Replaces: roiaware_pool3d_ext.points_in_boxes_{gpu,batch,cpu}(boxes, points, out)
  *           mmdet3d/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:40-47,126-136,

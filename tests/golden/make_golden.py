@@ -180,7 +180,38 @@ def pib_cases():
     print("pib_faces inside pairs:", int(out.sum()), "of", out.size)
 
 
+def _hard_simple_vfe(features, num_points, num_features):
+    # mmdet3d/models/voxel_encoders/voxel_encoder.py:41-44, verbatim (the module itself needs mmcv,
+    # which this image does not have; its forward is this one expression)
+    points_mean = features[:, :, :num_features].sum(dim=1, keepdim=False) / num_points.type_as(features).view(-1, 1)
+    return points_mean.contiguous()
+
+
+def vfe_cases():
+    out = {}
+    # voxelized LiDAR-like frames: the tensors HardSimpleVFE sees in the detectors
+    for tag, cfg, nfeat in (("c4", "C4", 5), ("c1", "C1", 4), ("c4_nf4", "C4", 4)):
+        c = synth.CONFIGS[cfg]
+        pts = synth.lidar_frame(6000, c["c"], synth.seed_for(9, 0), c["r_max"]).numpy()
+        vo, co, nu = _hard(pts, c["voxel_size"], c["point_cloud_range"], c["max_num_points"], c["max_voxels"])
+        if tag != "c4_nf4":  # same tensors as "c4", only the first 4 features used
+            out[tag + "_features"] = vo
+            out[tag + "_num_points"] = nu
+        out[tag + "_expected"] = _hard_simple_vfe(torch.from_numpy(vo), torch.from_numpy(nu), nfeat).numpy()
+    # tests/test_models/test_voxel_encoder/test_voxel_encoders.py:26-33 (shape reduced 240000 -> 2000)
+    gen = torch.Generator().manual_seed(5)
+    f = torch.rand([2000, 10, 5], generator=gen)
+    n = torch.randint(1, 10, [2000], generator=gen)
+    out["rand_features"], out["rand_num_points"] = f.numpy(), n.numpy().astype(np.int32)
+    out["rand_expected"] = _hard_simple_vfe(f, n, 5).numpy()
+    _save("vfe_mean", **out)
+
+
 if __name__ == "__main__":
     assert ref.available(), "run oracle/build_ref.py first"
+    if len(sys.argv) > 1 and sys.argv[1] == "vfe":
+        vfe_cases()
+        sys.exit(0)
     voxel_cases()
     pib_cases()
+    vfe_cases()

@@ -92,10 +92,49 @@ def pib():
     report(f"C3-shape points_in_boxes_cpu-layout 1x{M}x{T}", ms, M * T * 4 + M * 12, M * T, "pairs")
 
 
+def hard_mean(name):
+    """Hard voxelization + mean encoder: fused epilogue vs voxelization followed by the stand-alone kernel."""
+    import ctypes
+    from detmatch_b200.ops.voxel_encoders import hard_simple_vfe
+    cfg = synth.CONFIGS[name]
+    F, ci, c, P, V = cfg["frames"], int(name[1]), cfg["c"], cfg["max_num_points"], cfg["max_voxels"]
+    pts = [synth.lidar_frame(cfg["n"], c, synth.seed_for(ci, k), cfg["r_max"]).cuda() for k in range(F)]
+    plan = HardVoxelizeBatchPlan([cfg["n"]] * F, c, cfg["voxel_size"], cfg["point_cloud_range"], P, V, "cuda:0").bind(pts)
+    means = torch.empty((F, V, c), dtype=torch.float32, device="cuda")
+    frames = (_cabi.Frame * F)()
+    for i, t in enumerate(pts):
+        frames[i] = _cabi.Frame(t.data_ptr(), t.size(0), means[i].data_ptr(), plan.coors[i].data_ptr(),
+                                plan.num_points[i].data_ptr())
+    L, dev = _cabi.lib(), torch.device("cuda:0")
+
+    def fused():
+        _cabi.check(L.pcfe_hard_voxelize_mean_batch_f32(frames, F, c, plan.vs, plan.rg, None, P, V, ptr(plan.voxel_num),
+                                                        ptr(plan.ws), plan.ws.numel(), 0, stream_ptr(dev)), "mean")
+
+    ms_f = timeit(fused)
+    m = plan.voxel_num.cpu().tolist()
+    nb_f = sum(cfg["n"] * c * 4 + mm * (c * 4 + 16) for mm in m)
+    report(f"{name} voxelize + mean VFE, fused x{F}", ms_f, nb_f, F * cfg["n"], "pts")
+    # the detectors' flow: voxelize, concatenate the frames' voxels (openpcdet.py:69-76), one encoder call
+    plan.run()
+    vox_cat = torch.cat([plan.voxels[i, :mm] for i, mm in enumerate(m)])
+    num_cat = torch.cat([plan.num_points[i, :mm] for i, mm in enumerate(m)])
+    ms_v = timeit(lambda: hard_simple_vfe(vox_cat, num_cat))
+    report(f"{name} mean VFE kernel alone on the concatenated voxels", ms_v, sum(m) * ((P + 1) * c * 4 + 4), sum(m), "vox")
+    ms_c = timeit(lambda: torch.cat([plan.voxels[i, :mm] for i, mm in enumerate(m)]))
+    print(f"       unfused flow: voxelize {timeit(plan.run):.4f} + concatenate {ms_c:.4f} + encoder {ms_v:.4f} ms")
+    _cabi.profile(True)
+    fused()
+    torch.cuda.synchronize()
+    print("      ", {k: round(v[0], 4) for k, v in _cabi.profile_report().items()})
+    _cabi.profile(False)
+
+
 if __name__ == "__main__":
     torch.cuda.set_device(0)
     hard("C1", 16)
     dynamic()
     pib()
     hard("C4")
+    hard_mean("C4")
     hard("C5", 16)

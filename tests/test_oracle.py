@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from detmatch_b200 import synth
-from oracle import oracle, ref
+from oracle import oracle, ref, vfe_mean
 from tests.helpers import assert_same_bits, golden, golden_names
 
 
@@ -132,3 +132,25 @@ def test_grid_size_float32_rounding():
     assert oracle.grid_size([0.1, 0.1, 0.15], [-75.2, -75.2, -2, 75.2, 75.2, 4]).tolist() == [1504, 1504, 40]
     assert oracle.grid_size([0.05, 0.05, 0.1], [0, -40, -3, 70.4, 40, 1]).tolist() == [1408, 1600, 40]
     assert oracle.grid_size([0.25, 0.25, 8], [-50, -50, -5, 50, 50, 3]).tolist() == [400, 400, 1]
+
+
+@pytest.mark.parametrize("tag,nf,exact", [("c4", 5, False), ("c1", 4, True), ("c4_nf4", 4, True), ("rand", 5, False)])
+def test_vfe_mean_restatement_vs_reference_golden(tag, nf, exact):
+    """oracle/vfe_mean.py against outputs of the reference expression itself (voxel_encoder.py:41-44
+    evaluated by torch on the CPU, tests/golden/make_golden.py: vfe_cases).  ATen's association is
+    layout dependent: the slot-order restatement reproduces it bit for bit for 4 features and
+    stays within the float32 summation bound 2 (P - 1) eps sum|x| / n + 2 eps |mean| otherwise."""
+    g = golden("vfe_mean")
+    src = "c4" if tag == "c4_nf4" else tag
+    f, n, exp = g[src + "_features"], g[src + "_num_points"], g[tag + "_expected"]
+    got = vfe_mean.hard_simple_vfe(f, n, nf)
+    assert got.shape == exp.shape and got.dtype == exp.dtype
+    if exact:
+        assert_same_bits(got, exp, tag)
+        return
+    eps = 2.0 ** -24
+    mag = np.abs(f[:, :, :nf]).sum(axis=1, dtype=np.float64) / n.reshape(-1, 1)
+    bound = 2 * (f.shape[1] - 1) * eps * mag + 2 * eps * np.abs(exp.astype(np.float64))
+    err = np.abs(got.astype(np.float64) - exp.astype(np.float64))
+    assert np.all(err <= bound)
+    assert np.mean(got.view(np.uint32) == exp.view(np.uint32)) > 0.85
