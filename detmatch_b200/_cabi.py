@@ -50,6 +50,9 @@ PROTOTYPES = {
     "pcfe_voxel_mean_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
     "pcfe_hard_voxelize_mean_batch_f32": (c_int, [ctypes.POINTER(Frame), c_int, c_int, _f3, _f6, ctypes.POINTER(ctypes.c_float),
                                                   c_int, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "pcfe_hard_voxelize_packed_batch_f32": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64), c_int, c_int, _f3, _f6,
+                                                    ctypes.POINTER(ctypes.c_float), c_int, c_int, c_int, c_void_p, c_void_p,
+                                                    c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "pcfe_points_in_boxes_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pcfe_points_in_boxes_part_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
                                               c_size_t, c_int, c_void_p]),

@@ -44,10 +44,11 @@ namespace pcfe {
 int hv_launch_scan(const uint32_t* bitmask, size_t bitmask_stride, uint32_t* prefix,
                    size_t prefix_stride, int words, int max_voxels, int32_t* voxel_num, int frames,
                    int paired, cudaStream_t st);
-int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size_t overflow_stride,
+int hvg_launch_slow(const HvBatch& b, int frames, uint32_t* overflow, size_t overflow_stride,
                     int force, char* scratch_base, size_t scratch_stride, const HvGlobalPlan& p,
                     uint32_t* bitmask, size_t bitmask_stride, uint32_t* prefix, size_t prefix_stride,
-                    int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st, int mean);
+                    int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st, int mean,
+                    int stage, const int32_t* vn_all, int f_first);
 
 int g_opt_bucket_avg = 1024;  // target points per bucket (tunable through pcfe_debug_set)
 int g_opt_bucket_variant = 0;  // 1: general path with the first-version (atomicMin lists) bucket kernel
@@ -1376,13 +1377,19 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
 // MEAN: instead of the (P, C) rows of a voxel, the mean of its points is written (fr.voxels is a
 // (max_voxels, C) buffer): sum over the P slots in slot order (absent slots are +0, as in the
 // zero-padded tensor HardSimpleVFE sums, voxel_encoder.py:27-44), IEEE divide by the count.
-template <int C, bool MEAN>
+// PACK: the frames' outputs are concatenated (the detectors' torch.cat of the per-frame results,
+// openpcdet.py:69-76 / voxelnet.py:60-67): every frame's buffers are the SAME arrays, frame f writes
+// its rows at offset sum(voxel_num of the batch's earlier frames) and its coordinates as
+// (batch index, z, y, x) rows of 16 bytes.
+template <int C, bool MEAN, bool PACK>
 __global__ void __launch_bounds__(kExpThreads, PCFE_EXP_REC_MINB)
 hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
                       const int use_fast_div,
                       const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist,
                       const int coors_vec /* every coors buffer is 16-byte aligned */,
-                      const int tiles_x /* CTA-tiles per frame; the 1-D grid strides over tiles_x * frames */) {
+                      const int tiles_x /* CTA-tiles per frame; the 1-D grid strides over tiles_x * frames */,
+                      const int32_t* __restrict__ vn_all /* PACK: voxel_num of the batch's frame 0 */,
+                      const int f_first /* PACK: batch index of this launch's frame 0 */) {
   constexpr int PT = 5;
   constexpr int W = PT * C;  // output words per voxel
   // source word (point index * C + feature) of every output word of a warp's tile, kEmpty = zero
@@ -1415,6 +1422,12 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   const float* __restrict__ pts = fr.pts;
   const int vbase = (bx * kExpWarps + wid) * (kPipeTiles * 32);
   if (vbase >= m) continue;  // warp-uniform
+  size_t off = 0;  // PACK: rows of the earlier frames
+  if (PACK) {
+    int part = 0;
+    for (int k = lane; k < f_first + f; k += 32) part += __ldg(vn_all + k);
+    off = (size_t)__reduce_add_sync(0xFFFFFFFFu, part);
+  }
 
   // firsts[v] = first point of voxel v | (the voxel has more points: see rec[first]) << 31
   auto load_first = [&](int v0) { return v0 + lane < m ? __ldg(firsts + v0 + lane) : kEmpty; };
@@ -1450,7 +1463,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     if (have) {
       const float* __restrict__ fp = pts + (size_t)first * C;
       px = __ldg(fp); py = __ldg(fp + 1); pz = __ldg(fp + 2);
-      fr.num[v0 + lane] = (int32_t)len;
+      fr.num[off + v0 + lane] = (int32_t)len;
     }
     __syncwarp();
     // rows of this tile, lane = output word
@@ -1472,9 +1485,14 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
       } else {
         qx = __fdiv_rn(ax, g.vx); qy = __fdiv_rn(ay, g.vy); qz = __fdiv_rn(az, g.vz);
       }
-      cstage[lane * 3 + 0] = __float2int_rz(qz);
-      cstage[lane * 3 + 1] = __float2int_rz(qy);
-      cstage[lane * 3 + 2] = __float2int_rz(qx);
+      if (PACK) {  // one 16-byte row per lane: a 512-byte coalesced store
+        reinterpret_cast<int4*>(fr.coors)[off + v0 + lane] =
+            make_int4(f_first + f, __float2int_rz(qz), __float2int_rz(qy), __float2int_rz(qx));
+      } else {
+        cstage[lane * 3 + 0] = __float2int_rz(qz);
+        cstage[lane * 3 + 1] = __float2int_rz(qy);
+        cstage[lane * 3 + 2] = __float2int_rz(qx);
+      }
     }
     __syncwarp();
     if (MEAN) {
@@ -1493,10 +1511,10 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
         mstage[lane * C + q] = have ? __fdiv_rn(a, (float)len) : 0.0f;
       }
       __syncwarp();
-      float* __restrict__ mdst = fr.voxels + (size_t)v0 * C;
+      float* __restrict__ mdst = fr.voxels + (off + v0) * C;
       for (int i = lane; i < nvox * C; i += 32) mdst[i] = mstage[i];
     } else {
-    float* __restrict__ dst = fr.voxels + (size_t)v0 * W;
+    float* __restrict__ dst = fr.voxels + (off + v0) * W;
     if (nvox == 32) {
 #pragma unroll
       for (int k = 0; k < W; ++k) __stcs(dst + lane + 32 * k, val[k]);
@@ -1506,7 +1524,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
         if (lane + 32 * k < nvox * W) __stcs(dst + lane + 32 * k, val[k]);
     }
     }
-    {  // coordinates: 3 * nvox words, contiguous; v0 % 32 == 0 keeps the run 16-byte aligned
+    if (!PACK) {  // coordinates: 3 * nvox words, contiguous; v0 % 32 == 0 keeps the run 16-byte aligned
       int32_t* __restrict__ cdst = fr.coors + (size_t)v0 * 3;
       const int cw = nvox * 3;
       if (coors_vec) {
@@ -1670,10 +1688,12 @@ static int get_aux(int device, AuxStreams** out) {
 
 int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPlan& p,
             int max_points, int max_voxels, int32_t* voxel_num, void* workspace, int wave,
-            int nbuf, int device, cudaStream_t user_st, int mean) {
+            int nbuf, int device, cudaStream_t user_st, int mode) {
   std::lock_guard<std::mutex> lk(g_aux_mu);
+  const int mean = mode & kHvMean, pack = (mode & kHvPack) ? 1 : 0;
   const int nwaves = (num_frames + wave - 1) / wave;
-  const bool overlap = nbuf >= 2 && nwaves >= 2;
+  // (packed output: a wave places its rows behind those of the waves before it -- one stream)
+  const bool overlap = nbuf >= 2 && nwaves >= 2 && !pack;
   AuxStreams* aux = nullptr;
   if (overlap) {
     int rc = get_aux(device, &aux);
@@ -1729,8 +1749,9 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       b.f[k] = HvFrame{fr.points, fr.voxels, fr.coors, fr.num_points, (int)fr.n, 0};
       wn_max = std::max(wn_max, fr.n);
     }
-    // the mean epilogue exists on the record path only (P == 5, C = 4 / 5, aligned buffers)
-    if (mean && !(max_points == 5 && (c == 4 || c == 5) && vec_ok && max_voxels < (1 << 24) && wn_max < 0xFFFFFF &&
+    // the mean epilogue and the packed output exist on the record path only (P == 5, C = 4 / 5,
+    // aligned buffers)
+    if ((mean || pack) && !(max_points == 5 && (c == 4 || c == 5) && vec_ok && max_voxels < (1 << 24) && wn_max < 0xFFFFFF &&
                   g_opt_bucket_variant != 1))
       return PCFE_ERR_SHAPE;
     {
@@ -1776,6 +1797,12 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
                                  dim3(kFirstsThreads), 0, st, g_opt_pdl != 0, w, wnpad / 32, max_voxels, voxel_num + f0));
         PCFE_LAUNCH_CHECK();
       }
+      if (pack) {  // every frame's voxel count has to be known before the first row is placed
+        rc = hvg_launch_slow(b, wv, w.zero + w.ctl_off + p.nb + kCtlOverflow, w.zero_stride, g_opt_force_overflow,
+                             w.region, w.region_stride, p.slow, w.zero, w.zero_stride, w.wordprefix, w.word_stride,
+                             c, max_points, max_voxels, voxel_num + f0, st, mean, 1, voxel_num, f0);
+        if (rc != PCFE_OK) return rc;
+      }
       {
         ProfScope ps("hvb_expand", st);
         const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
@@ -1787,13 +1814,19 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         unsigned egrid = pgrid.x * pgrid.y;
         if (g_opt_expand_ctas > 0) egrid = std::min<unsigned>(egrid, (unsigned)(g_opt_expand_ctas * 148));
         const bool pdl = g_opt_pdl != 0;
-#define PCFE_LAUNCH_EXPAND_REC(CC, MM)                                                                          \
-  PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<CC, MM>, dim3(egrid), dim3(kExpThreads), 0, st, pdl, b, w, p.g, fdiv, \
-                           vn, wv, g_opt_expand_prefetch, coors_vec, tiles_x))
-        if (c == 4 && mean) PCFE_LAUNCH_EXPAND_REC(4, true);
-        else if (c == 4) PCFE_LAUNCH_EXPAND_REC(4, false);
-        else if (mean) PCFE_LAUNCH_EXPAND_REC(5, true);
-        else PCFE_LAUNCH_EXPAND_REC(5, false);
+#define PCFE_LAUNCH_EXPAND_REC(CC, MM, PP)                                                                      \
+  PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<CC, MM, PP>, dim3(egrid), dim3(kExpThreads), 0, st, pdl, b, w, p.g, \
+                           fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, tiles_x, (const int32_t*)voxel_num, f0))
+#define PCFE_LAUNCH_EXPAND_REC_C(CC)                                \
+  do {                                                              \
+    if (mean && pack) PCFE_LAUNCH_EXPAND_REC(CC, true, true);       \
+    else if (mean) PCFE_LAUNCH_EXPAND_REC(CC, true, false);         \
+    else if (pack) PCFE_LAUNCH_EXPAND_REC(CC, false, true);         \
+    else PCFE_LAUNCH_EXPAND_REC(CC, false, false);                  \
+  } while (0)
+        if (c == 4) PCFE_LAUNCH_EXPAND_REC_C(4);
+        else PCFE_LAUNCH_EXPAND_REC_C(5);
+#undef PCFE_LAUNCH_EXPAND_REC_C
 #undef PCFE_LAUNCH_EXPAND_REC
         PCFE_LAUNCH_CHECK();
       }
@@ -1871,7 +1904,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     rc = hvg_launch_slow(b, wv, w.zero + w.ctl_off + p.nb + kCtlOverflow, w.zero_stride,
                          g_opt_force_overflow, w.region, w.region_stride, p.slow, w.zero,
                          w.zero_stride, w.wordprefix, w.word_stride, c, max_points, max_voxels,
-                         voxel_num + f0, st, mean);
+                         voxel_num + f0, st, mean, pack ? 2 : 0, pack ? voxel_num : nullptr, f0);
     if (rc != PCFE_OK) return rc;
   }
   if (overlap) {

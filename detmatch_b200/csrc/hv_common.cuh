@@ -155,11 +155,14 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
                   int max_voxels, HvBucketPlan* p);
 // `nbuf` (1 or 2) wave buffers of wave * p.per_frame bytes each are available in `workspace`;
 // with 2 buffers and >= 2 waves consecutive waves overlap on two internal streams.
-// mean != 0: frames[i].voxels is a (max_voxels, c) buffer receiving the per-voxel mean of the kept
-// points (record path only; PCFE_ERR_SHAPE otherwise)
+// mode & kHvMean: frames[i].voxels receives (voxels, c) per-voxel means of the kept points instead
+// of (voxels, max_points, c) rows.  mode & kHvPack: every frame carries the SAME output pointers;
+// frame f writes at row offset sum(voxel_num[0 .. f)) and its coordinates as (f, z, y, x).
+// Both on the record path only (PCFE_ERR_SHAPE otherwise).
+constexpr int kHvMean = 1, kHvPack = 2;
 int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPlan& p,
             int max_points, int max_voxels, int32_t* voxel_num, void* workspace, int wave,
-            int nbuf, int device, cudaStream_t st, int mean = 0);
+            int nbuf, int device, cudaStream_t st, int mode = 0);
 
 // ---- persistent frame pipeline (hv_mega.cu): the bucket plan run as one kernel ---------------
 bool hvm_eligible(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPlan& p,

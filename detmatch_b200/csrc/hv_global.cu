@@ -238,19 +238,25 @@ int hv_launch_scan(const uint32_t* bitmask, size_t bitmask_stride, uint32_t* pre
 // ------------------------------------------------------------------------------------------
 constexpr int kSlowThreads = 1024;
 
+// stage 0: everything; stage 1: up to the per-voxel point lists and voxel_num; stage 2: the outputs
+// only (scratch, mask and prefix of stage 1 are still in place: one scratch region per frame).  The
+// split lets a packed batch (vn_all != nullptr: rows at offset sum(voxel_num of the batch's earlier
+// frames), coordinates as (batch index, z, y, x)) learn every frame's voxel count before any
+// output row is placed.
 __global__ void __launch_bounds__(kSlowThreads)
-hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, const uint32_t* __restrict__ overflow,
+hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, uint32_t* __restrict__ overflow,
                       const size_t overflow_stride, const int force, char* __restrict__ scratch_base,
                       const size_t scratch_stride, const HvGlobalPlan p,
                       uint32_t* __restrict__ bitmask_base, const size_t bitmask_stride,
                       uint32_t* __restrict__ prefix_base, const size_t prefix_stride, const int c,
                       const int max_points, const int max_voxels, int32_t* __restrict__ voxel_num,
-                      const int frames, const int ring, const int mean) {
+                      const int frames, const int ring, const int mean, const int stage,
+                      const int32_t* __restrict__ vn_all, const int f_first) {
   // CTA r serves frames r, r + ring, ... one after the other in scratch region r (ring == frames:
   // one frame per CTA)
   __shared__ uint32_t warp_sums[33];
   __shared__ uint32_t carry;
-  pdl_wait();  // launched as a programmatic dependent of the expansion kernel
+  pdl_wait();  // launched as a programmatic dependent of the kernel before it
   for (int f = blockIdx.x; f < frames; f += ring) {
   if (!force && overflow[(size_t)f * overflow_stride] == 0) continue;
   const HvFrame& fr = batch.f[f];
@@ -262,7 +268,8 @@ hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, const uint32_t* __r
   int32_t* pslot = reinterpret_cast<int32_t*>(scratch + p.table_b + p.list_b);
   uint32_t* bitmask = bitmask_base + (size_t)f * bitmask_stride;
   uint32_t* wordprefix = prefix_base + (size_t)f * prefix_stride;
-
+  int m;
+  if (stage != 2) {
   // phase 0: scratch init (table + lists are contiguous)
   {
     uint32_t* w = reinterpret_cast<uint32_t*>(scratch);
@@ -312,24 +319,52 @@ hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, const uint32_t* __r
     if (tid == 0) carry = base + total;
     __syncthreads();
   }
-  const int m = (int)min(carry, (uint32_t)max_voxels);
-  if (tid == 0) voxel_num[f] = m;
-  // phase 4: lists + coors
+  m = (int)min(carry, (uint32_t)max_voxels);
+  if (tid == 0) {
+    voxel_num[f] = m;
+    // a forced frame (test knob) is flagged like a real overflow, so that the expansion kernel
+    // that runs between the two stages leaves it alone
+    if (stage == 1 && force) overflow[(size_t)f * overflow_stride] = 1u;
+  }
+  // phase 4: lists
+  if (max_points > 0)
+    for (int i = tid; i < n; i += kSlowThreads) {
+      const int32_t s = pslot[i];
+      if (s < 0) continue;
+      const uint32_t vid = first_rank(bitmask, wordprefix, __ldcg(&table[s].y));
+      if (vid >= (uint32_t)max_voxels) continue;
+      sorted_insert<true>(idxlist + (size_t)vid * max_points, max_points, (uint32_t)i);
+    }
+  __syncthreads();  // (also: the next frame reuses `carry`)
+  if (stage == 1) continue;
+  } else {
+    m = voxel_num[f];
+  }
+  // phase 5: coordinates, rows (mean: the per-voxel mean of the kept points instead -- slot-order
+  // sum over all max_points slots, absent ones being +0, then an IEEE divide) and counts
+  size_t off = 0;
+  if (vn_all)
+    for (int k = 0; k < f_first + f; ++k) off += (size_t)vn_all[k];
   for (int i = tid; i < n; i += kSlowThreads) {
     const int32_t s = pslot[i];
     if (s < 0) continue;
     const uint2 e = __ldcg(&table[s]);
+    if (e.y != (uint32_t)i) continue;
     const uint32_t vid = first_rank(bitmask, wordprefix, e.y);
     if (vid >= (uint32_t)max_voxels) continue;
-    if (e.y == (uint32_t)i) decode_key(p.direct ? (uint32_t)s : e.x, p.g, fr.coors + (size_t)vid * 3);
-    if (max_points > 0)
-      sorted_insert<true>(idxlist + (size_t)vid * max_points, max_points, (uint32_t)i);
+    int32_t zyx[3];
+    decode_key(p.direct ? (uint32_t)s : e.x, p.g, zyx);
+    if (vn_all) {
+      int32_t* o = fr.coors + (off + vid) * 4;
+      o[0] = f_first + f; o[1] = zyx[0]; o[2] = zyx[1]; o[3] = zyx[2];
+    } else {
+      int32_t* o = fr.coors + (size_t)vid * 3;
+      o[0] = zyx[0]; o[1] = zyx[1]; o[2] = zyx[2];
+    }
   }
-  __syncthreads();
-  // phase 5: rows + counts (mean: the per-voxel mean of the kept points instead of the rows --
-  // slot-order sum over all max_points slots, absent ones being +0, then an IEEE divide)
   const long long rows = (long long)m * max_points;
   if (mean) {
+    float* out = fr.voxels + off * c;
     for (long long e = tid; e < (long long)m * c; e += kSlowThreads) {
       const long long v = e / c;
       const int j = (int)(e - v * c);
@@ -342,39 +377,44 @@ hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, const uint32_t* __r
         a = sl == 0 ? x : __fadd_rn(a, x);
         cnt += (idx != kEmpty) ? 1 : 0;
       }
-      fr.voxels[e] = __fdiv_rn(a, (float)cnt);
+      out[e] = __fdiv_rn(a, (float)cnt);
     }
-  } else
-  for (long long r = tid; r < rows; r += kSlowThreads) {
-    const uint32_t idx = __ldcg(&idxlist[r]);
-    float* dst = fr.voxels + (size_t)r * c;
-    const float* src = fr.pts + (size_t)idx * c;
-    for (int j = 0; j < c; ++j) dst[j] = (idx != kEmpty) ? __ldg(src + j) : 0.0f;
+  } else {
+    float* out = fr.voxels + off * (size_t)max_points * c;
+    for (long long r = tid; r < rows; r += kSlowThreads) {
+      const uint32_t idx = __ldcg(&idxlist[r]);
+      float* dst = out + (size_t)r * c;
+      const float* src = fr.pts + (size_t)idx * c;
+      for (int j = 0; j < c; ++j) dst[j] = (idx != kEmpty) ? __ldg(src + j) : 0.0f;
+    }
   }
   for (int v = tid; v < m; v += kSlowThreads) {
     const uint32_t* lst = idxlist + (size_t)v * max_points;
     int cnt = 0;
     for (int s = 0; s < max_points; ++s) cnt += (__ldcg(&lst[s]) != kEmpty) ? 1 : 0;
-    fr.num[v] = cnt;
+    fr.num[off + v] = cnt;
   }
   __syncthreads();  // the next frame reuses the scratch region and `carry`
   }
 }
 
-int hvg_launch_slow(const HvBatch& b, int frames, const uint32_t* overflow, size_t overflow_stride,
+// mode: bit 0 = mean epilogue; stage / vn_all / f_first: see the kernel
+int hvg_launch_slow(const HvBatch& b, int frames, uint32_t* overflow, size_t overflow_stride,
                     int force, char* scratch_base, size_t scratch_stride, const HvGlobalPlan& p,
                     uint32_t* bitmask, size_t bitmask_stride, uint32_t* prefix, size_t prefix_stride,
-                    int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st, int mean) {
+                    int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st, int mean,
+                    int stage, const int32_t* vn_all, int f_first) {
   ProfScope ps("hv_slow_fallback", st);
   PCFE_CUDA_TRY(launch_pdl(hvg_slow_frame_kernel, dim3((unsigned)frames), dim3(kSlowThreads), 0, st, true, b, overflow,
                            overflow_stride, force, scratch_base, scratch_stride, p, bitmask, bitmask_stride,
-                           prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, frames, mean));
+                           prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, frames, mean,
+                           stage, vn_all, f_first));
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
 
 // hv_mega.cu: `ring` scratch regions shared by frames f, f + ring, ...
-int hvg_launch_slow_ring(const HvBatch& b, int frames, int ring, const uint32_t* overflow,
+int hvg_launch_slow_ring(const HvBatch& b, int frames, int ring, uint32_t* overflow,
                          size_t overflow_stride, int force, char* scratch_base, size_t scratch_stride,
                          const HvGlobalPlan& p, uint32_t* bitmask, size_t bitmask_stride,
                          uint32_t* prefix, size_t prefix_stride, int c, int max_points,
@@ -382,7 +422,7 @@ int hvg_launch_slow_ring(const HvBatch& b, int frames, int ring, const uint32_t*
   ProfScope ps("hv_slow_fallback", st);
   hvg_slow_frame_kernel<<<std::min(frames, ring), kSlowThreads, 0, st>>>(
       b, overflow, overflow_stride, force, scratch_base, scratch_stride, p, bitmask, bitmask_stride,
-      prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, ring, 0);
+      prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, ring, 0, 0, nullptr, 0);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }

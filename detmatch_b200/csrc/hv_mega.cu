@@ -27,7 +27,7 @@
 
 namespace pcfe {
 
-int hvg_launch_slow_ring(const HvBatch& b, int frames, int ring, const uint32_t* overflow,
+int hvg_launch_slow_ring(const HvBatch& b, int frames, int ring, uint32_t* overflow,
                          size_t overflow_stride, int force, char* scratch_base, size_t scratch_stride,
                          const HvGlobalPlan& p, uint32_t* bitmask, size_t bitmask_stride,
                          uint32_t* prefix, size_t prefix_stride, int c, int max_points,

@@ -229,7 +229,7 @@ extern "C" size_t pcfe_hard_voxelize_workspace_bytes(int64_t n_max, int num_fram
 static int hv_batch_impl(const pcfe_frame_t* frames, int num_frames, int c, const float vs[3],
                          const float rg[6], const float* filter /* 6 floats or NULL */, int max_points,
                          int max_voxels, int32_t* voxel_num, void* workspace, size_t workspace_bytes,
-                         int device, void* stream, int mean = 0) {
+                         int device, void* stream, int mode = 0) {
   if (num_frames < 0 || c < 3) return PCFE_ERR_SHAPE;
   if (num_frames == 0) return PCFE_OK;
   if (!frames || !voxel_num) return PCFE_ERR_NULL;
@@ -277,10 +277,10 @@ static int hv_batch_impl(const pcfe_frame_t* frames, int num_frames, int c, cons
     nbuf = 1;
     wave = (int)std::min<size_t>(wave, fit);
   }
-  if (mean) {  // fused mean epilogue: record path of the bucket launch sequence only
+  if (mode) {  // mean epilogue / packed output: record path of the bucket launch sequence only
     if (!ch.bucket || g_opt_hv_path == 3) return PCFE_ERR_SHAPE;
     return hvb_run(frames, num_frames, c, ch.bp, max_points, max_voxels, voxel_num, workspace, wave, nbuf,
-                   device, st, 1);
+                   device, st, mode);
   }
   if (ch.bucket && g_opt_hv_path == 3) {
     // experimental: the persistent frame pipeline (hv_mega.cu); measured slower than the launch
@@ -321,7 +321,31 @@ extern "C" int pcfe_hard_voxelize_mean_batch_f32(const pcfe_frame_t* frames, int
                                                  int device, void* stream) {
   if (max_points != 5 || (c != 4 && c != 5)) return PCFE_ERR_SHAPE;
   return hv_batch_impl(frames, num_frames, c, vs, rg, filter_range, max_points, max_voxels, voxel_num,
-                       workspace, workspace_bytes, device, stream, 1);
+                       workspace, workspace_bytes, device, stream, kHvMean);
+}
+
+extern "C" int pcfe_hard_voxelize_packed_batch_f32(const float* const* points, const int64_t* n, int num_frames,
+                                                   int c, const float vs[3], const float rg[6],
+                                                   const float* filter_range, int max_points, int max_voxels,
+                                                   int mean, float* voxels_cat, int32_t* coors_batch,
+                                                   int32_t* num_points_cat, int64_t cap_rows, int32_t* voxel_num,
+                                                   void* workspace, size_t workspace_bytes, int device,
+                                                   void* stream) {
+  if (max_points != 5 || (c != 4 && c != 5)) return PCFE_ERR_SHAPE;
+  if (num_frames < 0 || cap_rows < 0) return PCFE_ERR_SHAPE;
+  if (num_frames == 0) return PCFE_OK;
+  if (!points || !n) return PCFE_ERR_NULL;
+  if ((uintptr_t)coors_batch & 15) return PCFE_ERR_ALIGN;
+  std::vector<pcfe_frame_t> frames((size_t)num_frames);
+  int64_t worst = 0;  // rows the batch can produce at most
+  for (int k = 0; k < num_frames; ++k) {
+    if (n[k] < 0) return PCFE_ERR_SHAPE;
+    frames[k] = pcfe_frame_t{points[k], n[k], voxels_cat, coors_batch, num_points_cat};
+    worst += std::min<int64_t>(n[k], std::max(max_voxels, 0));
+  }
+  if (cap_rows < worst) return PCFE_ERR_WORKSPACE;
+  return hv_batch_impl(frames.data(), num_frames, c, vs, rg, filter_range, max_points, max_voxels, voxel_num,
+                       workspace, workspace_bytes, device, stream, kHvPack | (mean ? kHvMean : 0));
 }
 
 // One thread per output element; a warp's loads of slot s cover 32 consecutive words of at most

@@ -1,4 +1,4 @@
 """Mirror of mmdet3d/ops/voxel/__init__.py (hot-path part)."""
-from .voxelize import HardVoxelizeBatchPlan, Voxelization, voxelization, voxelize_batch
+from .voxelize import HardVoxelizeBatchPlan, Voxelization, voxelization, voxelize_batch, voxelize_batch_packed
 
-__all__ = ["HardVoxelizeBatchPlan", "Voxelization", "voxelization", "voxelize_batch"]
+__all__ = ["HardVoxelizeBatchPlan", "Voxelization", "voxelization", "voxelize_batch", "voxelize_batch_packed"]

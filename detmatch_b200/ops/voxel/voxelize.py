@@ -95,6 +95,56 @@ def voxelize_batch(points, voxel_size, coors_range, max_points, max_voxels, sync
         return vox_cat, num_cat, coors_batch
 
 
+def voxelize_batch_packed(points, voxel_size, coors_range, max_points, max_voxels, mean=False, points_range=None):
+    """The detectors' ``voxelize()`` (openpcdet.py:59-76, voxelnet.py:50-67) as one launch sequence
+    that writes the concatenated tensors directly -- no per-frame slices, no ``torch.cat``, no host
+    synchronisation before the results exist.
+
+    Returns ``(voxels, num_points, coors_batch)`` exactly like the reference: voxels (sum M,
+    max_points, C) -- or, with ``mean=True``, the HardSimpleVFE output (sum M, C) -- num_points
+    (sum M,), coors_batch (sum M, 4) = [batch_idx, z, y, x].  The one host read (sum M, to size the
+    returned views) happens after everything is enqueued.
+    """
+    assert len(points) > 0
+    dev = points[0].device
+    c = points[0].size(1)
+    for p in points:
+        voxel_layer._check_points(p)
+        assert p.device == dev and p.size(1) == c
+    nf = len(points)
+    packed_ok = max_points == 5 and c in (4, 5) and all(p.data_ptr() % 16 == 0 for p in points)
+    if packed_ok:
+        with torch.no_grad():
+            cap = sum(min(p.size(0), max_voxels) for p in points)
+            shape = (cap, c) if mean else (cap, max_points, c)
+            voxels = torch.empty(shape, dtype=torch.float32, device=dev)
+            coors = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+            num = torch.empty((cap,), dtype=torch.int32, device=dev)
+            voxel_num = torch.empty((nf,), dtype=torch.int32, device=dev)
+            L = _cabi.lib()
+            vs, rg = _cabi.f3(voxel_size), _cabi.f6(coors_range)
+            need = L.pcfe_hard_voxelize_workspace_bytes(max(p.size(0) for p in points), nf, 0, vs, rg, max_points, max_voxels)
+            ws = workspace(dev, need)
+            pp = (ctypes.c_void_p * nf)(*[p.data_ptr() for p in points])
+            nn_ = (ctypes.c_int64 * nf)(*[p.size(0) for p in points])
+            flt = None if points_range is None else ctypes.cast(_cabi.f6(points_range), ctypes.POINTER(ctypes.c_float))
+            rc = L.pcfe_hard_voxelize_packed_batch_f32(pp, nn_, nf, c, vs, rg, flt, max_points, max_voxels, 1 if mean else 0,
+                                                       ptr(voxels), ptr(coors), ptr(num), cap, ptr(voxel_num), ptr(ws),
+                                                       ws.numel(), dev.index, stream_ptr(dev))
+            if rc == 0:
+                total = int(voxel_num.sum().item())
+                return voxels[:total], num[:total], coors[:total]
+            if rc != _cabi.ERR_SHAPE:  # ERR_SHAPE: a test knob selected a path without packed output
+                _cabi.check(rc, "pcfe_hard_voxelize_packed_batch_f32")
+    # other shapes: per-frame outputs, concatenated like the reference does
+    vox_cat, num_cat, coors_batch = voxelize_batch(points, voxel_size, coors_range, max_points, max_voxels, sync=True,
+                                                   points_range=points_range)
+    if mean:
+        from ..voxel_encoders.voxel_encoder import hard_simple_vfe
+        vox_cat = hard_simple_vfe(vox_cat, num_cat)
+    return vox_cat, num_cat, coors_batch
+
+
 class HardVoxelizeBatchPlan:
     """Pre-allocated batched hard voxelization for a fixed set of frame shapes: outputs and
     scratch are allocated once, ``run()`` only enqueues the launch sequence on the current
@@ -177,6 +227,12 @@ class Voxelization(nn.Module):
         else:
             max_voxels = self.max_voxels[1]
         return voxelization(input, self.voxel_size, self.point_cloud_range, self.max_num_points, max_voxels)
+
+    def forward_packed(self, inputs, mean=False):
+        """The detectors' voxelize() over a batch: concatenated (voxels, num_points, coors_batch)."""
+        max_voxels = self.max_voxels[0] if self.training else self.max_voxels[1]
+        return voxelize_batch_packed(inputs, self.voxel_size, self.point_cloud_range, self.max_num_points, max_voxels,
+                                     mean=mean)
 
     def forward_batch(self, inputs, sync=True):
         """All frames of a batch at once (see voxelize_batch)."""

@@ -185,6 +185,32 @@ int pcfe_hard_voxelize_mean_batch_f32(const pcfe_frame_t* frames, int num_frames
                                       int device, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * batched hard voxelization with concatenated ("packed") outputs
+ * Replaces: the detectors' voxelize(): per-frame voxel_layer + F.pad(coors, (1, 0), value=i) +
+ *           torch.cat of voxels / num_points / coors over the batch,
+ *           mmdet3d/models/detectors/openpcdet.py:59-76, voxelnet.py:50-67 (and, with mean != 0,
+ *           the HardSimpleVFE call that follows, voxel_encoder.py:27-44).
+ * points / n: HOST arrays of num_frames device pointers / row counts.  With M_f = voxel_num[f]
+ * and S_f = M_0 + ... + M_(f-1), frame f's results are rows [S_f, S_f + M_f) of
+ *   voxels_cat      (cap_rows, max_points, c)   mean == 0
+ *                   (cap_rows, c)               mean != 0 (per-voxel means, see above)
+ *   coors_batch     (cap_rows, 4) int32 = (f, z, y, x); 16-byte aligned
+ *   num_points_cat  (cap_rows,)   int32
+ * exactly the tensors the reference's torch.cat produces; rows >= S_F are not written.  No host
+ * synchronisation: the offsets are formed on the device from voxel_num (device int32[num_frames],
+ * also an output).  cap_rows >= sum_f min(n[f], max_voxels), else PCFE_ERR_WORKSPACE.
+ * filter_range may be NULL.  Record path only: max_points == 5, c == 4 or 5, 16-byte aligned
+ * frames and voxels_cat; PCFE_ERR_SHAPE otherwise (callers then concatenate the outputs of
+ * pcfe_hard_voxelize_batch_f32).  Workspace as pcfe_hard_voxelize_batch_f32.
+ * ------------------------------------------------------------------------------------------- */
+int pcfe_hard_voxelize_packed_batch_f32(const float* const* points, const int64_t* n, int num_frames, int c,
+                                        const float voxel_size[3], const float coors_range[6],
+                                        const float* filter_range, int max_points, int max_voxels, int mean,
+                                        float* voxels_cat, int32_t* coors_batch, int32_t* num_points_cat,
+                                        int64_t cap_rows, int32_t* voxel_num, void* workspace,
+                                        size_t workspace_bytes, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * points in boxes
  * Replaces: roiaware_pool3d_ext.points_in_boxes_{gpu,batch,cpu}(boxes, points, out)
  *           mmdet3d/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:40-47,126-136,
