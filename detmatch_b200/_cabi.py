@@ -60,6 +60,10 @@ PROTOTYPES = {
                                              c_size_t, c_int, c_void_p]),
     "pcfe_points_in_boxes_boxmajor_f32": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
                                                   c_size_t, c_int, c_void_p]),
+    "pcfe_pcdet_points_in_boxes_gpu_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                                   c_size_t, c_int, c_void_p]),
+    "pcfe_pcdet_points_in_boxes_cpu_f32": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
+                                                   c_size_t, c_int, c_void_p]),
     "pcfe_debug_sincosf": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "pcfe_debug_axis_sweep": (c_int, [ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p, c_int, c_void_p]),
 }

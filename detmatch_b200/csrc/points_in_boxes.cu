@@ -125,8 +125,15 @@ struct __align__(16) RBox {
 };
 static_assert(sizeof(RBox) == 16, "RBox must be 16 bytes");
 
+// pcdet == 0: mmdet3d boxes (cx, cy, cz_bottom, w, l, h, rz), points_in_boxes_cpu.cpp:16-40.
+// pcdet != 0: OpenPCDet boxes (cx, cy, cz_CENTRE, dx, dy, dz, heading) and test,
+//   thirdparty/Spconv-OpenPCDet/pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:121-140
+//   (the CUDA twin roiaware_pool3d_kernel.cu:16-37 differs in MARGIN only): rotation by -heading,
+//   |z - cz| > dz / 2.0 rejects, inside <=> |lx| < dx / 2.0 + MARGIN and |ly| < dy / 2.0 + MARGIN
+//   with the right-hand sides formed in double from the float MARGIN.
 __global__ void pib_prepare_kernel(const float* __restrict__ boxes, int64_t nboxes,
-                                   PBox* __restrict__ out, RBox* __restrict__ rout) {
+                                   PBox* __restrict__ out, RBox* __restrict__ rout, const int pcdet,
+                                   const float margin) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nboxes) return;
   const float* b = boxes + i * 7;
@@ -134,6 +141,26 @@ __global__ void pib_prepare_kernel(const float* __restrict__ boxes, int64_t nbox
   PBox p;
   p.cx = cx;
   p.cy = cy;
+  if (pcdet) {
+    p.czc = cz;
+    // float a, double T:  a > T <=> a > rd(T);  a < T <=> a < ru(T)  (no float lies strictly
+    // between T and its directed roundings; NaN / Inf propagate)
+    p.hh = __double2float_rd(__dmul_rn((double)h, 0.5));
+    p.hl = __double2float_ru(__dadd_rn(__dmul_rn((double)w, 0.5), (double)margin));  // local x <-> dx = b[3]
+    p.hw = __double2float_ru(__dadd_rn(__dmul_rn((double)l, 0.5), (double)margin));  // local y <-> dy = b[4]
+    const float rot = -rz;
+    p.cosa = glibc_sin_or_cos(rot, 1);
+    p.sina = glibc_sin_or_cos(rot, 0);
+    out[i] = p;
+    RBox r;
+    r.cx = cx;
+    r.cy = cy;
+    const double hl = (double)p.hl, hw = (double)p.hw;
+    r.r = __double2float_ru(__dmul_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(hl, hl), __dmul_rn(hw, hw))), 1.0001));
+    r.pad = 0.0f;
+    rout[i] = r;
+    return;
+  }
   // cz += h / 2.0  (double add, rounded to float; points_in_boxes_cpu.cpp:33)
   p.czc = __double2float_rn(__dadd_rn((double)cz, __dmul_rn((double)h, 0.5)));
   // The reference compares float values against the DOUBLE h/2, l/2, w/2 (:35,:37-38).  x/2 is
@@ -369,8 +396,9 @@ inline RBox* rbox_base(void* ws, int64_t nboxes) {
   return reinterpret_cast<RBox*>((char*)ws + align256((size_t)nboxes * sizeof(PBox)));
 }
 
-int prepare(const float* boxes, int64_t nboxes, void* ws, cudaStream_t st) {
-  pib_prepare_kernel<<<(unsigned)((nboxes + 127) / 128), 128, 0, st>>>(boxes, nboxes, (PBox*)ws, rbox_base(ws, nboxes));
+int prepare(const float* boxes, int64_t nboxes, void* ws, cudaStream_t st, int pcdet = 0, float margin = 0.0f) {
+  pib_prepare_kernel<<<(unsigned)((nboxes + 127) / 128), 128, 0, st>>>(boxes, nboxes, (PBox*)ws, rbox_base(ws, nboxes),
+                                                                       pcdet, margin);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
@@ -385,9 +413,8 @@ extern "C" size_t pcfe_points_in_boxes_workspace_bytes(int b, int t) {
   return align256((size_t)b * (size_t)t * sizeof(PBox)) + align256((size_t)b * (size_t)t * sizeof(RBox));
 }
 
-extern "C" int pcfe_points_in_boxes_part_f32(const float* boxes, const float* points, int b, int t,
-                                             int64_t m, int32_t* out, void* ws, size_t ws_bytes,
-                                             int device, void* stream) {
+static int part_impl(const float* boxes, const float* points, int b, int t, int64_t m, int32_t* out, void* ws,
+                     size_t ws_bytes, int device, void* stream, int pcdet, float margin) {
   int rc = check_common(boxes, points, out, b, t, m, 1, ws, ws_bytes);
   if (rc != PCFE_OK) return rc > 0 ? PCFE_OK : rc;
   DeviceGuard guard(device);
@@ -400,16 +427,27 @@ extern "C" int pcfe_points_in_boxes_part_f32(const float* boxes, const float* po
     return PCFE_OK;
   }
   PBox* pb = (PBox*)ws;
-  if ((rc = prepare(boxes, (int64_t)b * t, ws, st)) != PCFE_OK) return rc;
+  if ((rc = prepare(boxes, (int64_t)b * t, ws, st, pcdet, margin)) != PCFE_OK) return rc;
   dim3 grid((unsigned)((m + 255) / 256), (unsigned)b);
   pib_point_kernel<false><<<grid, 256, 0, st>>>(pb, rbox_base(ws, (int64_t)b * t), points, t, (long long)m, out);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }
 
-extern "C" int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float* points, int t,
-                                                 int64_t n, int32_t* out, void* ws, size_t ws_bytes,
-                                                 int device, void* stream) {
+extern "C" int pcfe_points_in_boxes_part_f32(const float* boxes, const float* points, int b, int t,
+                                             int64_t m, int32_t* out, void* ws, size_t ws_bytes,
+                                             int device, void* stream) {
+  return part_impl(boxes, points, b, t, m, out, ws, ws_bytes, device, stream, 0, 0.0f);
+}
+
+extern "C" int pcfe_pcdet_points_in_boxes_gpu_f32(const float* boxes, const float* points, int b, int t,
+                                                  int64_t m, int32_t* out, void* ws, size_t ws_bytes,
+                                                  int device, void* stream) {
+  return part_impl(boxes, points, b, t, m, out, ws, ws_bytes, device, stream, 1, 1e-5f);  // roiaware_pool3d_kernel.cu:27
+}
+
+static int boxmajor_impl(const float* boxes, const float* points, int t, int64_t n, int32_t* out, void* ws,
+                         size_t ws_bytes, int device, void* stream, int pcdet, float margin) {
   int rc = check_common(boxes, points, out, 1, t, n, t, ws, ws_bytes);
   if (rc != PCFE_OK) return rc > 0 ? PCFE_OK : rc;
   if (t == 0) return PCFE_OK;
@@ -417,11 +455,23 @@ extern "C" int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float
   PCFE_CUDA_TRY(guard.err);
   cudaStream_t st = (cudaStream_t)stream;
   PBox* pb = (PBox*)ws;
-  if ((rc = prepare(boxes, t, ws, st)) != PCFE_OK) return rc;
+  if ((rc = prepare(boxes, t, ws, st, pcdet, margin)) != PCFE_OK) return rc;
   dim3 grid((unsigned)((n + 255) / 256), 1);
   pib_point_kernel<true><<<grid, 256, 0, st>>>(pb, rbox_base(ws, t), points, t, (long long)n, out);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
+}
+
+extern "C" int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float* points, int t,
+                                                 int64_t n, int32_t* out, void* ws, size_t ws_bytes,
+                                                 int device, void* stream) {
+  return boxmajor_impl(boxes, points, t, n, out, ws, ws_bytes, device, stream, 0, 0.0f);
+}
+
+extern "C" int pcfe_pcdet_points_in_boxes_cpu_f32(const float* boxes, const float* points, int t,
+                                                  int64_t n, int32_t* out, void* ws, size_t ws_bytes,
+                                                  int device, void* stream) {
+  return boxmajor_impl(boxes, points, t, n, out, ws, ws_bytes, device, stream, 1, 1e-2f);  // roiaware_pool3d.cpp:131
 }
 
 extern "C" int pcfe_points_in_boxes_all_f32(const float* boxes, const float* points, int b, int t,

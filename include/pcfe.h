@@ -237,6 +237,26 @@ int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float* points, i
                                       int32_t* out, void* workspace, size_t workspace_bytes,
                                       int device, void* stream);
 
+/* OpenPCDet variant -- what PV-RCNN's point head calls (pcdet/models/dense_heads/
+ * point_head_template.py:82-89).
+ * Replaces: roiaware_pool3d_cuda.points_in_boxes_gpu / points_in_boxes_cpu,
+ *           thirdparty/Spconv-OpenPCDet/pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:98-118,
+ *           143-168 (bindings :175-176), roiaware_pool3d_kernel.cu:16-37,313-336;
+ *           call sites pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py:23,39.
+ * boxes = (x, y, z_CENTRE, dx, dy, dz, heading); inside <=> |z - cz| <= dz/2 and, after rotating
+ * (x - cx, y - cy) by -heading, |lx| < dx/2 + MARGIN and |ly| < dy/2 + MARGIN.  Arithmetic of
+ * check_pt_in_box3d_cpu (roiaware_pool3d.cpp:121-140) bit for bit: float32, glibc cosf / sinf, no
+ * contraction, right-hand sides in double.  MARGIN is each entry's own: 1e-5 for _gpu_ (the CUDA
+ * kernel's, :27 of the .cu), 1e-2 for _cpu_ (:131 of the .cpp).
+ * _gpu_: out (b, m) = lowest containing box index or -1, every element written.
+ * _cpu_: out (t, n) box-major 0/1.   Workspace: pcfe_points_in_boxes_workspace_bytes(b, t). */
+int pcfe_pcdet_points_in_boxes_gpu_f32(const float* boxes, const float* points, int b, int t,
+                                       int64_t m, int32_t* out, void* workspace,
+                                       size_t workspace_bytes, int device, void* stream);
+int pcfe_pcdet_points_in_boxes_cpu_f32(const float* boxes, const float* points, int t, int64_t n,
+                                       int32_t* out, void* workspace, size_t workspace_bytes,
+                                       int device, void* stream);
+
 /* Test hook: device evaluation of the glibc-exact sinf/cosf used for the boxes.
  * x, s, c are device float arrays of length n. */
 int pcfe_debug_sincosf(const float* x, int64_t n, float* s, float* c, int device, void* stream);

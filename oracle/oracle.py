@@ -46,6 +46,7 @@ def lib():
                                                     ctypes.c_int, ctypes.c_int, _f64p, _i32p, _i32p]
         L.pcfe_oracle_points_in_boxes_cpu.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int64, _i32p]
         L.pcfe_oracle_points_in_boxes_restated.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int64, _i32p]
+        L.pcfe_oracle_pcdet_points_in_boxes.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int64, ctypes.c_float, _i32p]
         L.pcfe_oracle_sincosf.argtypes = [ctypes.c_float, _f32p, _f32p]
         L.pcfe_oracle_sincosf.restype = None
         L.pcfe_oracle_host_sincosf.argtypes = [ctypes.c_float, _f32p, _f32p]
@@ -126,6 +127,31 @@ def points_in_boxes_cpu(points, boxes, restated_trig=False):
     rc = fn(_p(bx, _f32p), bx.shape[0], _p(pts, _f32p), pts.shape[0], _p(out, _i32p))
     assert rc == 1, rc
     return out
+
+
+def pcdet_points_in_boxes_cpu(points, boxes, margin=1e-2):
+    """OpenPCDet points_in_boxes_cpu (roiaware_pool3d.cpp:121-168 via roiaware_pool3d_utils.py:9-25):
+    (N,3),(T,7) -> (T,N) int32.  margin=1e-5 gives the arithmetic of the CUDA twin."""
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    bx = np.ascontiguousarray(boxes, dtype=np.float32)
+    assert bx.ndim == 2 and bx.shape[1] == 7 and pts.ndim == 2 and pts.shape[1] == 3
+    out = np.zeros((bx.shape[0], pts.shape[0]), dtype=np.int32)
+    rc = lib().pcfe_oracle_pcdet_points_in_boxes(_p(bx, _f32p), bx.shape[0], _p(pts, _f32p), pts.shape[0],
+                                                 ctypes.c_float(margin), _p(out, _i32p))
+    assert rc == 1, rc
+    return out
+
+
+def pcdet_points_in_boxes_gpu(points, boxes):
+    """(B,M,3),(B,T,7) -> (B,M) lowest containing box or -1 (roiaware_pool3d_kernel.cu:313-336,
+    MARGIN 1e-5, with the CPU arithmetic)."""
+    out = []
+    for p, b in zip(points, boxes):
+        m = pcdet_points_in_boxes_cpu(p, b, margin=1e-5)  # (T,N)
+        hit = m.argmax(axis=0).astype(np.int32) if m.shape[0] else np.zeros(m.shape[1], np.int32)
+        any_ = m.any(axis=0) if m.shape[0] else np.zeros(m.shape[1], bool)
+        out.append(np.where(any_, hit, -1).astype(np.int32))
+    return np.stack(out)
 
 
 def points_in_boxes_batch(points, boxes):

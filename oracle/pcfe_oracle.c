@@ -388,6 +388,33 @@ int pcfe_oracle_points_in_boxes_cpu(const float* boxes, int t,
   return pib_impl(boxes, t, points, n, out, 0);
 }
 
+/* OpenPCDet variant: thirdparty/Spconv-OpenPCDet/pcdet/ops/roiaware_pool3d/src/
+ * roiaware_pool3d.cpp:121-140 (check_pt_in_box3d_cpu, MARGIN = 1e-2) and its CUDA twin
+ * roiaware_pool3d_kernel.cu:16-37 (MARGIN = 1e-5): boxes (x, y, z_CENTRE, dx, dy, dz, heading). */
+static inline int pcdet_check_pt_in_box3d(const float* pt, const float* box3d, const float MARGIN) {
+  float x = pt[0], y = pt[1], z = pt[2];
+  float cx = box3d[0], cy = box3d[1], cz = box3d[2];
+  float dx = box3d[3], dy = box3d[4], dz = box3d[5], rz = box3d[6];
+  if (fabsf(z - cz) > dz / 2.0) return 0;          /* :136 float |dz| vs double dz/2 */
+  float shift_x = x - cx, shift_y = y - cy;        /* :137 */
+  float rot_angle = rz;
+  float cosa = cosf(-rot_angle), sina = sinf(-rot_angle); /* :122 (cos/sin on a float resolve to cosf/sinf) */
+  float local_x = shift_x * cosa + shift_y * (-sina);     /* :123 (no FMA) */
+  float local_y = shift_x * sina + shift_y * cosa;        /* :124 */
+  float in_flag = (fabsf(local_x) < dx / 2.0 + MARGIN) & (fabsf(local_y) < dy / 2.0 + MARGIN); /* :138, double rhs */
+  return (int)in_flag;
+}
+
+/* roiaware_pool3d.cpp:143-168: out (t, n) box-major 0/1 */
+int pcfe_oracle_pcdet_points_in_boxes(const float* boxes, int t, const float* points, int64_t n,
+                                      float margin, int32_t* out) {
+  if (t < 0 || n < 0) return -1;
+  for (int i = 0; i < t; ++i)
+    for (int64_t j = 0; j < n; ++j)
+      out[(int64_t)i * n + j] = pcdet_check_pt_in_box3d(points + j * 3, boxes + i * 7, margin);
+  return 1;
+}
+
 int pcfe_oracle_points_in_boxes_restated(const float* boxes, int t,
                                          const float* points, int64_t n, int32_t* out) {
   return pib_impl(boxes, t, points, n, out, 1);

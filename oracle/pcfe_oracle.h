@@ -70,6 +70,12 @@ int pcfe_oracle_points_in_boxes_cpu(const float* boxes, int t,
 /* Same test but with pcfe_oracle_sincosf() instead of the host libm: what the
  * device computes.  Equal to the function above wherever the restated trig
  * equals the host's (checked exhaustively in tests). */
+/* OpenPCDet variant (thirdparty/Spconv-OpenPCDet/pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:
+ * 121-168; margin 1e-2 = the CPU op, 1e-5 = the CUDA kernel roiaware_pool3d_kernel.cu:16-37).
+ * boxes (t,7) = (x, y, z_centre, dx, dy, dz, heading), out (t,n) 0/1. */
+int pcfe_oracle_pcdet_points_in_boxes(const float* boxes, int t, const float* points, int64_t n,
+                                      float margin, int32_t* out);
+
 int pcfe_oracle_points_in_boxes_restated(const float* boxes, int t,
                                          const float* points, int64_t n,
                                          int32_t* out);

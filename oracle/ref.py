@@ -50,3 +50,26 @@ def points_in_boxes_cpu(points, boxes):
     out = points.new_zeros((boxes.shape[0], points.shape[0]), dtype=torch.int)
     ext.points_in_boxes_cpu(boxes.float().contiguous(), points.float().contiguous(), out)
     return out
+
+
+_PCDET_SO = os.path.join(_HERE, "_ref", "pcdet_ref_cpu.so")
+_pcdet = None
+
+
+def pcdet_available():
+    return os.path.exists(_PCDET_SO)
+
+
+def pcdet_points_in_boxes_cpu(points, boxes):
+    """thirdparty/Spconv-OpenPCDet/pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py:9-25 on the
+    reference's unmodified roiaware_pool3d.cpp (compiled in place): (N,3),(T,7) -> (T,N) int32."""
+    global _pcdet
+    import torch
+    if _pcdet is None:
+        spec = importlib.util.spec_from_file_location("pcdet_ref_cpu", _PCDET_SO)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        _pcdet = m
+    out = points.new_zeros((boxes.shape[0], points.shape[0]), dtype=torch.int)
+    _pcdet.points_in_boxes_cpu(boxes.float().contiguous(), points.float().contiguous(), out)
+    return out

@@ -207,11 +207,52 @@ def vfe_cases():
     _save("vfe_mean", **out)
 
 
+def pcdet_cases():
+    """OpenPCDet points_in_boxes_cpu (roiaware_pool3d.cpp:121-168) from the reference's own file."""
+    assert ref.pcdet_available(), "run oracle/build_ref.py first"
+    c3 = synth.CONFIGS["C3"]
+    pts = synth.lidar_frame(4000, 3, synth.seed_for(3, 1), c3["r_max"]).numpy()
+    bxs = synth.random_boxes(64, synth.seed_for(3, 1) + 500, c3["point_cloud_range"]).numpy()
+    bxs[:16, 0:3] = pts[:16]  # centred on existing points (z is the centre here)
+    out = ref.pcdet_points_in_boxes_cpu(torch.from_numpy(pts), torch.from_numpy(bxs)).numpy()
+    assert out.sum() > 100
+    # points within a few ulps of the MARGIN-expanded faces (both margins), axis-aligned and odd headings
+    rng = np.random.default_rng(91)
+    yaws = [0.0, math.pi / 2, -math.pi / 2, math.pi, -math.pi, math.pi / 4, 0.3, 2.5, -1.1, 100.0, -12345.678, 1e-5]
+    fb = synth.random_boxes(len(yaws) * 2, 92, [-20, -20, -3, 20, 20, 1]).numpy()
+    fb[:, 6] = np.float32(yaws * 2)
+    fb[-1, 3:6] = 0.0
+    fp = []
+    for b in fb.astype(np.float64):
+        for margin in (1e-2, 1e-5):
+            for _ in range(24):
+                lx = (b[3] / 2 + margin) * rng.choice([-1, 1]) * (1 + rng.integers(-3, 4) * 2.0 ** -23)
+                ly = (b[4] / 2 + margin) * rng.choice([-1, 1]) * (1 + rng.integers(-3, 4) * 2.0 ** -23)
+                if rng.random() < 0.5:
+                    lx *= rng.random()
+                else:
+                    ly *= rng.random()
+                dz = (b[5] / 2) * rng.choice([-1, 1]) * (1 + rng.integers(-2, 3) * 2.0 ** -23) * (1 if rng.random() < 0.3 else rng.random())
+                c, s_ = math.cos(b[6]), math.sin(b[6])
+                fp.append([b[0] + lx * c - ly * s_, b[1] + lx * s_ + ly * c, b[2] + dz])
+    nan = float("nan")
+    fp = np.float32(fp + [[0, 0, nan], [nan, 0, 0], [np.inf, 0, 0], [0, 0, np.inf], [1e30, 1e30, 0]])
+    fb2 = np.concatenate([fb, np.float32([[0, 0, 0, 2, 4, 1, nan], [0, 0, 0, nan, 4, 1, 0.1], [0, 0, 0, 2, 4, nan, 0.1],
+                                          [0, 0, 0, -1, 4, 2, 0.2], [0, 0, 0, np.inf, np.inf, np.inf, 0.0]])])
+    fout = ref.pcdet_points_in_boxes_cpu(torch.from_numpy(fp), torch.from_numpy(fb2)).numpy()
+    print("pcdet faces inside pairs:", int(fout.sum()), "of", fout.size)
+    _save("pcdet_pib", boxes=bxs, points=pts, expected_cpu=out, face_boxes=fb2, face_points=fp, face_expected_cpu=fout)
+
+
 if __name__ == "__main__":
     assert ref.available(), "run oracle/build_ref.py first"
     if len(sys.argv) > 1 and sys.argv[1] == "vfe":
         vfe_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "pcdet":
+        pcdet_cases()
+        sys.exit(0)
     voxel_cases()
     pib_cases()
     vfe_cases()
+    pcdet_cases()

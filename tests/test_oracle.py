@@ -154,3 +154,28 @@ def test_vfe_mean_restatement_vs_reference_golden(tag, nf, exact):
     err = np.abs(got.astype(np.float64) - exp.astype(np.float64))
     assert np.all(err <= bound)
     assert np.mean(got.view(np.uint32) == exp.view(np.uint32)) > 0.85
+
+
+def test_oracle_pcdet_pib_golden():
+    """The OpenPCDet restatement against outputs of the reference's own roiaware_pool3d.cpp
+    (compiled in place, tests/golden/make_golden.py: pcdet_cases): LiDAR-like points, and points
+    within a few ulps of the MARGIN-expanded faces, NaN / Inf points and boxes."""
+    g = golden("pcdet_pib")
+    assert_same_bits(oracle.pcdet_points_in_boxes_cpu(g["points"], g["boxes"]), g["expected_cpu"], "pcdet random")
+    assert_same_bits(oracle.pcdet_points_in_boxes_cpu(g["face_points"], g["face_boxes"]), g["face_expected_cpu"],
+                     "pcdet faces")
+    # the two margins really separate on the face set (the GPU flavour's 1e-5 is not the CPU's 1e-2)
+    tight = oracle.pcdet_points_in_boxes_cpu(g["face_points"], g["face_boxes"], margin=1e-5)
+    assert (tight != g["face_expected_cpu"]).sum() > 100 and np.all(tight <= g["face_expected_cpu"])
+
+
+@pytest.mark.skipif(not ref.pcdet_available(), reason="oracle/_ref/pcdet_ref_cpu.so not built")
+def test_oracle_pcdet_vs_reference():
+    import torch
+    c3 = synth.CONFIGS["C3"]
+    pts = synth.lidar_frame(30000, 3, 4242, c3["r_max"])
+    bxs = synth.random_boxes(200, 4243, c3["point_cloud_range"])
+    bxs[:60, 0:3] = pts[:60]
+    exp = ref.pcdet_points_in_boxes_cpu(pts, bxs).numpy()
+    assert exp.sum() > 1000
+    assert_same_bits(oracle.pcdet_points_in_boxes_cpu(pts.numpy(), bxs.numpy()), exp, "pcdet vs _ref")
