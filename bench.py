@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--e2e-chunk", type=int, default=8, help="frames per pipelined chunk of the e2e measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the packed / fused-encoder timings (\"fused\" key)")
     ap.add_argument("--frames-in-flight", type=int, default=0)
     ap.add_argument("--hv-wave", type=int, default=0, help="tuning: frames per wave (0 = library default)")
     ap.add_argument("--hv-bucket-avg", type=int, default=0, help="tuning: target points per bucket")
@@ -369,6 +370,10 @@ def run_ours(args):
                                        "frac": round(k_bytes / (k_ms * 1e-3) / 1e9 / peak, 4),
                                        "traffic": NCU_EXPAND_TRAFFIC.get(args.workload)}
 
+    fused = None
+    if not args.no_extras and P == 5 and C in (4, 5):
+        fused = run_fused_extras(cfg, pts, plan, dev)
+
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         cpu_baseline = cpu_baseline_subprocess(args)
@@ -379,11 +384,56 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
         "config": _config_dict(cfg, args, frames_per_step=F),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "kernels": kernels,
+        "clocks": clocks, "kernels": kernels, "fused": fused,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_fused_extras(cfg, pts, plan, dev, reps=50):
+    """Not the headline metric: the same batch through the two SURVEY 8(f)-1 output modes, device
+    time per step (CUDA events, rank 0).  packed = concatenated voxels / num_points / (b, z, y, x)
+    coordinates written directly (what the detectors' voxelize() returns after torch.cat);
+    packed_mean = the same with HardSimpleVFE folded into the expansion ((sum M, C) means instead of
+    the (sum M, P, C) tensor)."""
+    import ctypes
+
+    import torch
+    from detmatch_b200 import _cabi
+    from detmatch_b200._torch_glue import ptr, stream_ptr
+    F, N, C = cfg["frames"], cfg["n"], cfg["c"]
+    P, V = cfg["max_num_points"], cfg["max_voxels"]
+    L = _cabi.lib()
+    cap = F * min(N, V)
+    coors = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((cap,), dtype=torch.int32, device=dev)
+    vnum = torch.empty((F,), dtype=torch.int32, device=dev)
+    pp = (ctypes.c_void_p * F)(*[t.data_ptr() for t in pts])
+    nn = (ctypes.c_int64 * F)(*[N] * F)
+    out = {}
+    for name, mean in (("packed", 0), ("packed_mean", 1)):
+        vox = torch.empty((cap, C) if mean else (cap, P, C), dtype=torch.float32, device=dev)
+
+        def run():
+            _cabi.check(L.pcfe_hard_voxelize_packed_batch_f32(pp, nn, F, C, plan.vs, plan.rg, None, P, V, mean, ptr(vox),
+                                                              ptr(coors), ptr(num), cap, ptr(vnum), ptr(plan.ws),
+                                                              plan.ws.numel(), dev.index, stream_ptr(dev)), name)
+        for _ in range(5):
+            run()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            run()
+        b.record()
+        torch.cuda.synchronize(dev)
+        out[name + "_ms_per_step"] = round(a.elapsed_time(b) / reps, 4)
+        del vox
+    out["rows"] = int(vnum.sum().item())
+    out["note"] = ("device time of pcfe_hard_voxelize_packed_batch_f32 on the same batch (mean = 0 / 1); "
+                   "parity: tests/test_gpu_packed.py, tests/test_gpu_vfe.py")
+    return out
 
 
 def run_e2e(args, cfg, plan, host, pts, dev, world, barrier):
