@@ -211,6 +211,47 @@ int pcfe_hard_voxelize_packed_batch_f32(const float* const* points, const int64_
                                         size_t workspace_bytes, int device, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * DynamicScatter: per-voxel max / sum / mean of point features (consumer of dynamic voxelization)
+ * Replaces: voxel_layer.dynamic_point_to_voxel_forward / _backward
+ *           mmdet3d/ops/voxel/src/scatter_points_cuda.cu:183-303 (kernels :85-181),
+ *           voxelization.h:96-123; call sites mmdet3d/ops/voxel/scatter_points.py:28,43.
+ * coors (n, ndim) int32, ndim 1..4; a row with any coordinate outside [0, dims[j]) is dropped
+ * (the reference drops rows with a negative coordinate, :202; callers pass dims = column maxima
+ * + 1).  Voxels are the distinct kept rows in lexicographic order -- what at::unique_dim(sorted)
+ * returns after the reference strips its (-1, ...) row -- found with an occupancy bitmap over the
+ * dims[0] x ... box instead of a sort (product of dims <= 2^34).
+ *
+ * Two calls, because the number of voxels sizes the outputs (the reference synchronises inside
+ * unique_dim for the same reason):
+ *   _map_i32:    coors_map (n,) = voxel id of every point or -1; *num_voxels (device int32) = M.
+ *   _reduce_f32: voxel_feats (m, c), voxel_coors (m, ndim), point_count (m,) for m = M read back
+ *                by the caller.  reduce: PCFE_REDUCE_MAX is order independent (bit-exact,
+ *                NaN inputs ignored like fmaxf, a voxel of only NaNs stays -inf);
+ *                PCFE_REDUCE_SUM / _MEAN accumulate with float atomicAdd like the reference
+ *                (:99) -- association unspecified there and here; _MEAN divides (IEEE) by the
+ *                count (:243).
+ *   _backward_f32: grad_feats (n, c), every element written (:108-181): SUM copies the voxel's
+ *                gradient, MEAN divides it by the count, MAX routes it to the lowest-index point
+ *                whose feature equals the maximum (workspace >= m * c * 4 bytes for MAX, else
+ *                unused).
+ * ------------------------------------------------------------------------------------------- */
+enum { PCFE_REDUCE_SUM = 0, PCFE_REDUCE_MEAN = 1, PCFE_REDUCE_MAX = 2 }; /* scatter_points_cuda.cu:7 */
+
+size_t pcfe_dynamic_scatter_workspace_bytes(const int32_t* dims, int ndim);
+int pcfe_dynamic_scatter_map_i32(const int32_t* coors, int64_t n, int ndim, const int32_t* dims,
+                                 int32_t* coors_map, int32_t* num_voxels, void* workspace,
+                                 size_t workspace_bytes, int device, void* stream);
+int pcfe_dynamic_scatter_reduce_f32(const float* feats, const int32_t* coors, const int32_t* coors_map,
+                                    int64_t n, int c, int ndim, int reduce, int64_t m,
+                                    float* voxel_feats, int32_t* voxel_coors, int32_t* point_count,
+                                    int device, void* stream);
+int pcfe_dynamic_scatter_backward_f32(const float* grad_voxel_feats, const float* feats,
+                                      const float* voxel_feats, const int32_t* coors_map,
+                                      const int32_t* point_count, int64_t n, int64_t m, int c,
+                                      int reduce, float* grad_feats, void* workspace,
+                                      size_t workspace_bytes, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * points in boxes
  * Replaces: roiaware_pool3d_ext.points_in_boxes_{gpu,batch,cpu}(boxes, points, out)
  *           mmdet3d/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:40-47,126-136,

@@ -244,10 +244,31 @@ def pcdet_cases():
     _save("pcdet_pib", boxes=bxs, points=pts, expected_cpu=out, face_boxes=fb2, face_points=fp, face_expected_cpu=fout)
 
 
+def scatter_cases():
+    """DynamicScatter: the reference TEST's own expected values
+    (tests/test_models/test_voxel_encoder/test_dynamic_scatter.py:13-16,55-66, N reduced 200000 -> 6000),
+    evaluated by torch on the CPU."""
+    gen = torch.Generator().manual_seed(17)
+    feats = torch.rand(size=(6000, 3), dtype=torch.float32, generator=gen) * 100 - 50
+    coors = torch.randint(low=-1, high=20, size=(6000, 3), dtype=torch.int32, generator=gen)
+    ref_voxel_coors = coors.unique(dim=0, sorted=True)
+    ref_voxel_coors = ref_voxel_coors[ref_voxel_coors.min(dim=-1).values >= 0]
+    mean, mx = [], []
+    for ref_voxel_coor in ref_voxel_coors:
+        voxel_mask = (coors == ref_voxel_coor).all(dim=-1)
+        mean.append(feats[voxel_mask].mean(dim=0))
+        mx.append(feats[voxel_mask].max(dim=0).values)
+    _save("dynamic_scatter", feats=feats.numpy(), coors=coors.numpy(), voxel_coors=ref_voxel_coors.numpy(),
+          mean=torch.stack(mean).numpy(), max=torch.stack(mx).numpy())
+
+
 if __name__ == "__main__":
     assert ref.available(), "run oracle/build_ref.py first"
     if len(sys.argv) > 1 and sys.argv[1] == "vfe":
         vfe_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "scatter":
+        scatter_cases()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pcdet":
         pcdet_cases()
@@ -256,3 +277,4 @@ if __name__ == "__main__":
     pib_cases()
     vfe_cases()
     pcdet_cases()
+    scatter_cases()

@@ -130,11 +130,47 @@ def hard_mean(name):
     _cabi.profile(False)
 
 
+def dyn_scatter():
+    """C2 frames: dynamic voxelization coordinates -> DynamicScatter over the whole batch (b, z, y, x)."""
+    from detmatch_b200.ops import dynamic_scatter, voxelization
+    cfg = synth.CONFIGS["C2"]
+    F = cfg["frames"]
+    pts = [synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(2, k), cfg["r_max"]).cuda() for k in range(F)]
+    coors = [voxelization(p, cfg["voxel_size"], cfg["point_cloud_range"], -1, -1) for p in pts]
+    feats = torch.cat(pts)
+    cb = torch.cat([torch.nn.functional.pad(c, (1, 0), value=i) for i, c in enumerate(coors)]).contiguous()
+    n, c = feats.shape
+    for r in ("max", "mean"):
+        ms = timeit(lambda: dynamic_scatter(feats, cb, r), reps=20)
+        out, oc = dynamic_scatter(feats, cb, r)
+        m = out.size(0)
+        nbytes = n * (c * 4 + 16) + m * (c * 4 + 16)
+        report(f"C2-shape DynamicScatter {r} x{F} (M={m}, incl. 2 host syncs)", ms, nbytes, n, "pts")
+    _cabi.profile(True)
+    dynamic_scatter(feats, cb, "mean")
+    torch.cuda.synchronize()
+    print("      ", {k: round(v[0], 4) for k, v in _cabi.profile_report().items()})
+    _cabi.profile(False)
+
+
+def pcdet_pib():
+    from detmatch_b200.ops.pcdet_roiaware_pool3d import roiaware_pool3d_cuda
+    c3 = synth.CONFIGS["C3"]
+    B, M, T = c3["frames"], c3["n"], c3["boxes"]
+    pts = torch.stack([synth.lidar_frame(M, 3, synth.seed_for(3, k), c3["r_max"]) for k in range(B)]).cuda()
+    bxs = torch.stack([synth.random_boxes(T, synth.seed_for(3, k) + 500, c3["point_cloud_range"]) for k in range(B)]).cuda()
+    out = torch.empty((B, M), dtype=torch.int32, device="cuda")
+    ms = timeit(lambda: roiaware_pool3d_cuda.points_in_boxes_gpu(bxs, pts, out))
+    report(f"C3-shape OpenPCDet points_in_boxes_gpu {B}x{M}x{T}", ms, B * M * 16 + B * T * 28, B * M * T, "pairs")
+
+
 if __name__ == "__main__":
     torch.cuda.set_device(0)
     hard("C1", 16)
     dynamic()
     pib()
+    pcdet_pib()
+    dyn_scatter()
     hard("C4")
     hard_mean("C4")
     hard("C5", 16)

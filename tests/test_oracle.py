@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from detmatch_b200 import synth
-from oracle import oracle, ref, vfe_mean
+from oracle import oracle, ref, scatter, vfe_mean
 from tests.helpers import assert_same_bits, golden, golden_names
 
 
@@ -179,3 +179,20 @@ def test_oracle_pcdet_vs_reference():
     exp = ref.pcdet_points_in_boxes_cpu(pts, bxs).numpy()
     assert exp.sum() > 1000
     assert_same_bits(oracle.pcdet_points_in_boxes_cpu(pts.numpy(), bxs.numpy()), exp, "pcdet vs _ref")
+
+
+def test_oracle_dynamic_scatter_vs_reference_test_construction():
+    """oracle/scatter.py against the expected values the reference's own test builds
+    (test_dynamic_scatter.py:55-84, evaluated by torch; tests/golden/make_golden.py: scatter_cases):
+    voxel order and max bit for bit, mean within the test's tolerance (atol 1e-2, rtol 1e-5 -- in
+    fact within 4 float32 ulps of the sum)."""
+    g = golden("dynamic_scatter")
+    for r in ("mean", "max"):
+        out, vc, mp, cnt = scatter.forward(g["feats"], g["coors"], r)
+        assert_same_bits(vc, g["voxel_coors"], "voxel_coors")
+        if r == "max":
+            assert_same_bits(out, g["max"], "max")
+        else:
+            assert np.allclose(out, g["mean"], atol=1e-2, rtol=1e-5)
+            assert np.abs(out - g["mean"]).max() < 1e-5
+        assert cnt.sum() == (mp >= 0).sum() and (mp >= 0).sum() == (g["coors"] >= 0).all(axis=1).sum()
