@@ -53,7 +53,7 @@ PROTOTYPES = {
     "pcfe_hard_voxelize_packed_batch_f32": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64), c_int, c_int, _f3, _f6,
                                                     ctypes.POINTER(ctypes.c_float), c_int, c_int, c_int, c_void_p, c_void_p,
                                                     c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
-    "pcfe_dynamic_scatter_workspace_bytes": (c_size_t, [ctypes.POINTER(ctypes.c_int32), c_int]),
+    "pcfe_dynamic_scatter_workspace_bytes": (c_size_t, [ctypes.POINTER(ctypes.c_int32), c_int, c_int64]),
     "pcfe_dynamic_scatter_map_i32": (c_int, [c_void_p, c_int64, c_int, ctypes.POINTER(ctypes.c_int32), c_void_p, c_void_p,
                                              c_void_p, c_size_t, c_int, c_void_p]),
     "pcfe_dynamic_scatter_reduce_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64,

@@ -9,9 +9,9 @@
 // from an occupancy bitmap over the coordinate box instead: one bit per cell in row-major
 // (lexicographic) order, set by the points; the rank of a cell's bit among the set bits IS its
 // position in the sorted unique list, so a popcount prefix over the bitmap replaces the sort
-// (the same device the hard voxelizer uses over point indices).  Traffic: the bitmap (1 bit per
-// cell: 11 MB for a 1408 x 1600 x 40 KITTI grid) is written once and read twice; the points are
-// read twice (mark, map) plus once for the reduction.
+// (the same device the hard voxelizer uses over point indices).  The bitmap has two levels so that
+// every pass scales with the points and the occupied blocks, not with the volume of the box: the
+// coordinates are read three times (mark level 1, mark level 2, map) plus once for the reduction.
 //
 // max is order independent and therefore deterministic and bit-exact; sum / mean use float
 // atomicAdd exactly like the reference (:99), whose result depends on the arrival order.
@@ -49,28 +49,52 @@ __device__ __forceinline__ long long ds_key(const int32_t* __restrict__ row, con
   return ok ? key : -1ll;
 }
 
+// ---- two-level occupancy bitmap -----------------------------------------------------------------
+// Level 1: one bit per coarse block of kFine = 256 consecutive cells (cells / 256 bits: 0.7 MB for a
+// 16-frame batch of 1408 x 1600 x 40 grids).  Level 2: 256 bits (8 words) for every OCCUPIED coarse
+// block only, in coarse order -- the rank of a coarse block among the set level-1 bits is its slot.
+// Row-major order of the cells = (coarse order, order inside the block), so the rank of a cell's bit
+// in the compact level-2 bitmap is its position in the sorted unique list.  Every pass is
+// proportional to the points and the occupied blocks, not to the volume of the coordinate box.
+constexpr int kFineLog2 = 8, kFine = 1 << kFineLog2, kFineWords = kFine / 32;
+
 __global__ void __launch_bounds__(kDsThreads)
-ds_mark_kernel(const int32_t* __restrict__ coors, const long long n, const DsDims dm, uint32_t* __restrict__ bitmap) {
+ds_mark1_kernel(const int32_t* __restrict__ coors, const long long n, const DsDims dm, uint32_t* __restrict__ l1) {
   const long long i = (long long)blockIdx.x * kDsThreads + threadIdx.x;
   if (i >= n) return;
   const long long key = ds_key(coors + i * dm.ndim, dm);
-  if (key >= 0) atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+  if (key < 0) return;
+  const long long ck = key >> kFineLog2;
+  const uint32_t bit = 1u << (ck & 31);
+  if (!(__ldcg(&l1[ck >> 5]) & bit)) atomicOr(&l1[ck >> 5], bit);  // most points find their block marked
+}
+
+// words the scans of a level cover: host constant, or (level 2) the occupied blocks' words rounded
+// up to whole scan blocks, known on the device only
+__device__ __forceinline__ size_t ds_limit_words(const size_t words_host, const int32_t* __restrict__ nocc) {
+  if (!nocc) return words_host;
+  const size_t w = (size_t)(*nocc) * kFineWords;
+  return (w + kDsScanThreads - 1) / kDsScanThreads * kDsScanThreads;
 }
 
 // popcount of every 1024-word block
 __global__ void __launch_bounds__(kDsScanThreads)
-ds_blocksum_kernel(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ blocksum) {
+ds_blocksum_kernel(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ blocksum, const size_t words_host,
+                   const int32_t* __restrict__ nocc) {
   __shared__ uint32_t warp_sums[33];
   const size_t w = (size_t)blockIdx.x * kDsScanThreads + threadIdx.x;
+  if ((size_t)blockIdx.x * kDsScanThreads >= ds_limit_words(words_host, nocc)) return;  // block-uniform
   uint32_t total;
   block_exscan((uint32_t)__popc(bitmap[w]), warp_sums, &total);
   if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
 }
 
-// exclusive scan of the block sums in place (one CTA), total -> *num_voxels
+// exclusive scan of the block sums in place (one CTA), total -> *total_out
 __global__ void __launch_bounds__(kDsScanThreads)
-ds_scan_blocks_kernel(uint32_t* __restrict__ blocksum, const int nblk, int32_t* __restrict__ num_voxels) {
+ds_scan_blocks_kernel(uint32_t* __restrict__ blocksum, const size_t words_host, const int32_t* __restrict__ nocc,
+                      int32_t* __restrict__ total_out) {
   __shared__ uint32_t warp_sums[33];
+  const int nblk = (int)(ds_limit_words(words_host, nocc) / kDsScanThreads);
   uint32_t carry = 0;
   for (int b0 = 0; b0 < nblk; b0 += kDsScanThreads) {
     const int b = b0 + threadIdx.x;
@@ -81,31 +105,59 @@ ds_scan_blocks_kernel(uint32_t* __restrict__ blocksum, const int nblk, int32_t* 
     carry += total;
     __syncthreads();  // warp_sums is reused by the next trip
   }
-  if (threadIdx.x == 0) *num_voxels = (int32_t)carry;
+  if (threadIdx.x == 0) *total_out = (int32_t)carry;
 }
 
 // prefix[w] = number of set bits in the words before w
 __global__ void __launch_bounds__(kDsScanThreads)
 ds_prefix_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ blocksum,
-                 uint32_t* __restrict__ prefix) {
+                 uint32_t* __restrict__ prefix, const size_t words_host, const int32_t* __restrict__ nocc) {
   __shared__ uint32_t warp_sums[33];
   const size_t w = (size_t)blockIdx.x * kDsScanThreads + threadIdx.x;
+  if ((size_t)blockIdx.x * kDsScanThreads >= ds_limit_words(words_host, nocc)) return;
   uint32_t total;
   const uint32_t ex = block_exscan((uint32_t)__popc(bitmap[w]), warp_sums, &total);
   prefix[w] = blocksum[blockIdx.x] + ex;
 }
 
 __global__ void __launch_bounds__(kDsThreads)
-ds_map_kernel(const int32_t* __restrict__ coors, const long long n, const DsDims dm,
-              const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
-              int32_t* __restrict__ coors_map) {
+ds_zero2_kernel(uint32_t* __restrict__ l2, const int32_t* __restrict__ nocc) {
+  const size_t lim = ds_limit_words(0, nocc);
+  for (size_t w = (size_t)blockIdx.x * kDsThreads + threadIdx.x; w < lim; w += (size_t)gridDim.x * kDsThreads) l2[w] = 0u;
+}
+
+// level-2 word and bit of a cell: slot of its coarse block (rank among the level-1 bits) * 8 words
+__device__ __forceinline__ size_t ds_fine_word(const long long key, const uint32_t* __restrict__ l1,
+                                               const uint32_t* __restrict__ prefix1) {
+  const long long ck = key >> kFineLog2;
+  const uint32_t bits = __ldg(&l1[ck >> 5]);
+  const uint32_t slot = __ldg(&prefix1[ck >> 5]) + (uint32_t)__popc(bits & ((1u << (ck & 31)) - 1u));
+  return (size_t)slot * kFineWords + (size_t)((key & (kFine - 1)) >> 5);
+}
+
+__global__ void __launch_bounds__(kDsThreads)
+ds_mark2_kernel(const int32_t* __restrict__ coors, const long long n, const DsDims dm, const uint32_t* __restrict__ l1,
+                const uint32_t* __restrict__ prefix1, uint32_t* __restrict__ l2) {
+  const long long i = (long long)blockIdx.x * kDsThreads + threadIdx.x;
+  if (i >= n) return;
+  const long long key = ds_key(coors + i * dm.ndim, dm);
+  if (key < 0) return;
+  const size_t fw = ds_fine_word(key, l1, prefix1);
+  const uint32_t bit = 1u << (key & 31);
+  if (!(__ldcg(&l2[fw]) & bit)) atomicOr(&l2[fw], bit);
+}
+
+__global__ void __launch_bounds__(kDsThreads)
+ds_map_kernel(const int32_t* __restrict__ coors, const long long n, const DsDims dm, const uint32_t* __restrict__ l1,
+              const uint32_t* __restrict__ prefix1, const uint32_t* __restrict__ l2,
+              const uint32_t* __restrict__ prefix2, int32_t* __restrict__ coors_map) {
   const long long i = (long long)blockIdx.x * kDsThreads + threadIdx.x;
   if (i >= n) return;
   const long long key = ds_key(coors + i * dm.ndim, dm);
   int32_t vid = -1;
   if (key >= 0) {
-    const uint32_t bits = __ldg(&bitmap[key >> 5]);
-    vid = (int32_t)(__ldg(&prefix[key >> 5]) + (uint32_t)__popc(bits & ((1u << (key & 31)) - 1u)));
+    const size_t fw = ds_fine_word(key, l1, prefix1);
+    vid = (int32_t)(__ldg(&prefix2[fw]) + (uint32_t)__popc(__ldg(&l2[fw]) & ((1u << (key & 31)) - 1u)));
   }
   coors_map[i] = vid;
 }
@@ -213,14 +265,18 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct DsPlan {
   DsDims dm;
   long long cells;
-  size_t words;  // multiple of kDsScanThreads
-  int nblk;
-  size_t bitmap_b, prefix_b, blocksum_b;
+  size_t words1;     // level-1 words, multiple of kDsScanThreads
+  long long cap_occ; // occupied coarse blocks at most: min(n, coarse blocks)
+  size_t words2;     // level-2 words at most, multiple of kDsScanThreads
+  size_t l1_b, p1_b, s1_b, l2_b, p2_b, s2_b, ctl_b;
+  size_t total() const { return l1_b + p1_b + s1_b + l2_b + p2_b + s2_b + ctl_b; }
 };
 
-int ds_make_plan(const int32_t* dims, int ndim, DsPlan* p) {
+inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+int ds_make_plan(const int32_t* dims, int ndim, long long n, DsPlan* p) {
   if (!dims) return PCFE_ERR_NULL;
-  if (ndim < 1 || ndim > kMaxDim) return PCFE_ERR_SHAPE;
+  if (ndim < 1 || ndim > kMaxDim || n < 0) return PCFE_ERR_SHAPE;
   long long cells = 1;
   p->dm.ndim = ndim;
   for (int j = 0; j < kMaxDim; ++j) p->dm.d[j] = 1;
@@ -228,15 +284,20 @@ int ds_make_plan(const int32_t* dims, int ndim, DsPlan* p) {
     if (dims[j] < 0) return PCFE_ERR_SHAPE;
     p->dm.d[j] = dims[j];
     cells *= dims[j];
-    if (cells > (1ll << 34)) return PCFE_ERR_TOO_LARGE;  // 2 GiB of bitmap
+    if (cells > (1ll << 38)) return PCFE_ERR_TOO_LARGE;  // 128 MiB of level-1 bitmap
   }
   p->cells = cells;
-  const size_t words = (size_t)((cells + 31) / 32);
-  p->words = std::max<size_t>((words + kDsScanThreads - 1) / kDsScanThreads, 1) * kDsScanThreads;
-  p->nblk = (int)(p->words / kDsScanThreads);
-  p->bitmap_b = align256(p->words * 4);
-  p->prefix_b = align256(p->words * 4);
-  p->blocksum_b = align256((size_t)p->nblk * 4);
+  const long long ncoarse = (cells + kFine - 1) / kFine;
+  p->words1 = round_up(std::max<size_t>((size_t)((ncoarse + 31) / 32), 1), kDsScanThreads);
+  p->cap_occ = std::max<long long>(std::min<long long>(n, ncoarse), 1);
+  p->words2 = round_up((size_t)p->cap_occ * kFineWords, kDsScanThreads);
+  p->l1_b = align256(p->words1 * 4);
+  p->p1_b = align256(p->words1 * 4);
+  p->s1_b = align256(p->words1 / kDsScanThreads * 4);
+  p->l2_b = align256(p->words2 * 4);
+  p->p2_b = align256(p->words2 * 4);
+  p->s2_b = align256(p->words2 / kDsScanThreads * 4);
+  p->ctl_b = 256;
   return PCFE_OK;
 }
 
@@ -247,19 +308,18 @@ inline unsigned blocks_for(long long cnt) { return (unsigned)((cnt + kDsThreads 
 
 using namespace pcfe;
 
-extern "C" size_t pcfe_dynamic_scatter_workspace_bytes(const int32_t* dims, int ndim) {
+extern "C" size_t pcfe_dynamic_scatter_workspace_bytes(const int32_t* dims, int ndim, int64_t n) {
   DsPlan p;
-  if (ds_make_plan(dims, ndim, &p) != PCFE_OK) return 0;
-  return p.bitmap_b + p.prefix_b + p.blocksum_b;
+  if (ds_make_plan(dims, ndim, n, &p) != PCFE_OK) return 0;
+  return p.total();
 }
 
 extern "C" int pcfe_dynamic_scatter_map_i32(const int32_t* coors, int64_t n, int ndim, const int32_t* dims,
                                             int32_t* coors_map, int32_t* num_voxels, void* workspace,
                                             size_t workspace_bytes, int device, void* stream) {
   DsPlan p;
-  int rc = ds_make_plan(dims, ndim, &p);
+  int rc = ds_make_plan(dims, ndim, n, &p);
   if (rc != PCFE_OK) return rc;
-  if (n < 0) return PCFE_ERR_SHAPE;
   if (n >= (1ll << 31)) return PCFE_ERR_TOO_LARGE;
   if (!num_voxels) return PCFE_ERR_NULL;
   if (n > 0 && (!coors || !coors_map)) return PCFE_ERR_NULL;
@@ -277,21 +337,40 @@ extern "C" int pcfe_dynamic_scatter_map_i32(const int32_t* coors, int64_t n, int
   }
   if (!workspace) return PCFE_ERR_NULL;
   if ((uintptr_t)workspace & 255) return PCFE_ERR_ALIGN;
-  if (workspace_bytes < p.bitmap_b + p.prefix_b + p.blocksum_b) return PCFE_ERR_WORKSPACE;
-  uint32_t* bitmap = (uint32_t*)workspace;
-  uint32_t* prefix = (uint32_t*)((char*)workspace + p.bitmap_b);
-  uint32_t* blocksum = (uint32_t*)((char*)workspace + p.bitmap_b + p.prefix_b);
+  if (workspace_bytes < p.total()) return PCFE_ERR_WORKSPACE;
+  char* base = (char*)workspace;
+  uint32_t* l1 = (uint32_t*)base;
+  uint32_t* prefix1 = (uint32_t*)(base + p.l1_b);
+  uint32_t* sum1 = (uint32_t*)(base + p.l1_b + p.p1_b);
+  uint32_t* l2 = (uint32_t*)(base + p.l1_b + p.p1_b + p.s1_b);
+  uint32_t* prefix2 = (uint32_t*)(base + p.l1_b + p.p1_b + p.s1_b + p.l2_b);
+  uint32_t* sum2 = (uint32_t*)(base + p.l1_b + p.p1_b + p.s1_b + p.l2_b + p.p2_b);
+  int32_t* nocc = (int32_t*)(base + p.l1_b + p.p1_b + p.s1_b + p.l2_b + p.p2_b + p.s2_b);
+  const unsigned nblk1 = (unsigned)(p.words1 / kDsScanThreads), nblk2 = (unsigned)(p.words2 / kDsScanThreads);
   ProfScope ps("dynamic_scatter_map", st);
-  PCFE_CUDA_TRY(cudaMemsetAsync(bitmap, 0, p.words * 4, st));
-  ds_mark_kernel<<<blocks_for(n), kDsThreads, 0, st>>>(coors, n, p.dm, bitmap);
+  // level 1: occupied coarse blocks and their slots
+  PCFE_CUDA_TRY(cudaMemsetAsync(l1, 0, p.words1 * 4, st));
+  ds_mark1_kernel<<<blocks_for(n), kDsThreads, 0, st>>>(coors, n, p.dm, l1);
   PCFE_LAUNCH_CHECK();
-  ds_blocksum_kernel<<<p.nblk, kDsScanThreads, 0, st>>>(bitmap, blocksum);
+  ds_blocksum_kernel<<<nblk1, kDsScanThreads, 0, st>>>(l1, sum1, p.words1, nullptr);
   PCFE_LAUNCH_CHECK();
-  ds_scan_blocks_kernel<<<1, kDsScanThreads, 0, st>>>(blocksum, p.nblk, num_voxels);
+  ds_scan_blocks_kernel<<<1, kDsScanThreads, 0, st>>>(sum1, p.words1, nullptr, nocc);
   PCFE_LAUNCH_CHECK();
-  ds_prefix_kernel<<<p.nblk, kDsScanThreads, 0, st>>>(bitmap, blocksum, prefix);
+  ds_prefix_kernel<<<nblk1, kDsScanThreads, 0, st>>>(l1, sum1, prefix1, p.words1, nullptr);
   PCFE_LAUNCH_CHECK();
-  ds_map_kernel<<<blocks_for(n), kDsThreads, 0, st>>>(coors, n, p.dm, bitmap, prefix, coors_map);
+  // level 2: the cells of the occupied blocks (sizes known on the device only: the grids cover the
+  // worst case and the blocks beyond *nocc return at once)
+  ds_zero2_kernel<<<std::min<unsigned>((unsigned)((p.words2 + kDsThreads - 1) / kDsThreads), 148u * 16u), kDsThreads, 0, st>>>(l2, nocc);
+  PCFE_LAUNCH_CHECK();
+  ds_mark2_kernel<<<blocks_for(n), kDsThreads, 0, st>>>(coors, n, p.dm, l1, prefix1, l2);
+  PCFE_LAUNCH_CHECK();
+  ds_blocksum_kernel<<<nblk2, kDsScanThreads, 0, st>>>(l2, sum2, 0, nocc);
+  PCFE_LAUNCH_CHECK();
+  ds_scan_blocks_kernel<<<1, kDsScanThreads, 0, st>>>(sum2, 0, nocc, num_voxels);
+  PCFE_LAUNCH_CHECK();
+  ds_prefix_kernel<<<nblk2, kDsScanThreads, 0, st>>>(l2, sum2, prefix2, 0, nocc);
+  PCFE_LAUNCH_CHECK();
+  ds_map_kernel<<<blocks_for(n), kDsThreads, 0, st>>>(coors, n, p.dm, l1, prefix1, l2, prefix2, coors_map);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }

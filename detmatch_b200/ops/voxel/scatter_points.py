@@ -42,7 +42,7 @@ def dynamic_point_to_voxel_forward(feats, coors, reduce_type, dims=None):
         dims = [max(int(v) + 1, 0) for v in coors.amax(dim=0).tolist()]
     cd = (ctypes.c_int32 * ndim)(*[int(d) for d in dims])
     L = _cabi.lib()
-    ws = workspace(dev, L.pcfe_dynamic_scatter_workspace_bytes(cd, ndim))
+    ws = workspace(dev, L.pcfe_dynamic_scatter_workspace_bytes(cd, ndim, n))
     coors_map = torch.empty((n,), dtype=torch.int32, device=dev)
     num = torch.empty((1,), dtype=torch.int32, device=dev)
     _cabi.check(L.pcfe_dynamic_scatter_map_i32(ptr(coors), n, ndim, cd, ptr(coors_map), ptr(num), ptr(ws), ws.numel(),

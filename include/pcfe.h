@@ -218,8 +218,9 @@ int pcfe_hard_voxelize_packed_batch_f32(const float* const* points, const int64_
  * coors (n, ndim) int32, ndim 1..4; a row with any coordinate outside [0, dims[j]) is dropped
  * (the reference drops rows with a negative coordinate, :202; callers pass dims = column maxima
  * + 1).  Voxels are the distinct kept rows in lexicographic order -- what at::unique_dim(sorted)
- * returns after the reference strips its (-1, ...) row -- found with an occupancy bitmap over the
- * dims[0] x ... box instead of a sort (product of dims <= 2^34).
+ * returns after the reference strips its (-1, ...) row -- found with a two-level occupancy bitmap
+ * over the dims[0] x ... box instead of a sort (product of dims <= 2^38; the workspace grows with
+ * min(n, cells / 256), 64 bytes each, plus cells / 1024 bytes).
  *
  * Two calls, because the number of voxels sizes the outputs (the reference synchronises inside
  * unique_dim for the same reason):
@@ -237,7 +238,7 @@ int pcfe_hard_voxelize_packed_batch_f32(const float* const* points, const int64_
  * ------------------------------------------------------------------------------------------- */
 enum { PCFE_REDUCE_SUM = 0, PCFE_REDUCE_MEAN = 1, PCFE_REDUCE_MAX = 2 }; /* scatter_points_cuda.cu:7 */
 
-size_t pcfe_dynamic_scatter_workspace_bytes(const int32_t* dims, int ndim);
+size_t pcfe_dynamic_scatter_workspace_bytes(const int32_t* dims, int ndim, int64_t n);
 int pcfe_dynamic_scatter_map_i32(const int32_t* coors, int64_t n, int ndim, const int32_t* dims,
                                  int32_t* coors_map, int32_t* num_voxels, void* workspace,
                                  size_t workspace_bytes, int device, void* stream);
