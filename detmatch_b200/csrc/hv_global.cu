@@ -366,8 +366,8 @@ hvg_slow_frame_kernel(const __grid_constant__ HvBatch batch, uint32_t* __restric
   if (mean) {
     float* out = fr.voxels + off * c;
     for (long long e = tid; e < (long long)m * c; e += kSlowThreads) {
-      const long long v = e / c;
-      const int j = (int)(e - v * c);
+      int j;
+      const long long v = elem_row(e, c, j);
       const uint32_t* lst = idxlist + (size_t)v * max_points;
       float a = 0.0f;
       int cnt = 0;

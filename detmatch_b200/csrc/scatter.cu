@@ -187,8 +187,8 @@ ds_reduce_kernel(const float* __restrict__ feats, const int32_t* __restrict__ co
                  float* __restrict__ voxel_feats, int32_t* __restrict__ voxel_coors, int32_t* __restrict__ count) {
   const long long e = (long long)blockIdx.x * kDsThreads + threadIdx.x;
   if (e >= n * c) return;
-  const long long i = e / c;
-  const int j = (int)(e - i * c);
+  int j;
+  const long long i = elem_row(e, c, j);
   const int32_t vid = __ldg(coors_map + i);
   if (vid < 0) return;
   const float x = __ldg(feats + e);
@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(kDsThreads)
 ds_divide_kernel(float* __restrict__ voxel_feats, const int32_t* __restrict__ count, const long long m, const int c) {
   const long long e = (long long)blockIdx.x * kDsThreads + threadIdx.x;
   if (e >= m * c) return;
-  voxel_feats[e] = __fdiv_rn(voxel_feats[e], (float)count[e / c]);  // :243 reduced_feats /= reduce_count
+  int j;
+  voxel_feats[e] = __fdiv_rn(voxel_feats[e], (float)count[elem_row(e, c, j)]);  // :243 reduced_feats /= reduce_count
 }
 
 // scatter_points_cuda.cu:108-135: every element of grad_feats is written (dropped points get 0)
@@ -216,8 +217,8 @@ ds_backward_add_kernel(const float* __restrict__ grad_voxel, const int32_t* __re
                        float* __restrict__ grad_feats) {
   const long long e = (long long)blockIdx.x * kDsThreads + threadIdx.x;
   if (e >= n * c) return;
-  const long long i = e / c;
-  const int j = (int)(e - i * c);
+  int j;
+  const long long i = elem_row(e, c, j);
   const int32_t vid = __ldg(coors_map + i);
   float g = 0.0f;
   if (vid >= 0) {
@@ -241,8 +242,8 @@ ds_backward_max_from_kernel(const float* __restrict__ feats, const float* __rest
   const long long e = (long long)blockIdx.x * kDsThreads + threadIdx.x;
   if (e >= n * c) return;
   grad_feats[e] = 0.0f;  // :270 grad_feats.fill_(0)
-  const long long i = e / c;
-  const int j = (int)(e - i * c);
+  int j;
+  const long long i = elem_row(e, c, j);
   const int32_t vid = __ldg(coors_map + i);
   if (vid < 0) return;
   if (__ldg(feats + e) == __ldg(voxel_feats + (size_t)vid * c + j)) atomicMin(reduce_from + (size_t)vid * c + j, (int32_t)i);
@@ -255,7 +256,8 @@ ds_backward_max_scatter_kernel(const float* __restrict__ grad_voxel, const int32
                                const long long m, const int c, const long long n, float* __restrict__ grad_feats) {
   const long long e = (long long)blockIdx.x * kDsThreads + threadIdx.x;
   if (e >= m * c) return;
-  const int j = (int)(e % c);
+  int j;
+  elem_row(e, c, j);
   const long long src = reduce_from[e];
   if (src < n) grad_feats[src * c + j] = __ldg(grad_voxel + e);
 }

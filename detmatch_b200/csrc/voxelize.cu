@@ -358,10 +358,11 @@ voxel_mean_kernel(const float* __restrict__ voxels, const int32_t* __restrict__ 
   const long long total = m * c;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
-    const long long v = e / c;
-    const int q = (int)(e - v * c);
+    int q;
+    const long long v = elem_row(e, c, q);
     const float* src = voxels + (size_t)v * max_points * c + q;
     float a = __ldg(src);
+#pragma unroll 5
     for (int sl = 1; sl < max_points; ++sl) a = __fadd_rn(a, __ldg(src + (size_t)sl * c));
     out[e] = __fdiv_rn(a, (float)__ldg(num_points + v));
   }
