@@ -1374,6 +1374,9 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
 #ifndef PCFE_EXP_REC_MINB
 #define PCFE_EXP_REC_MINB 8
 #endif
+#ifndef PCFE_EXP_MEAN_MINB  // the mean epilogue keeps C words per lane instead of P * C
+#define PCFE_EXP_MEAN_MINB 8
+#endif
 // MEAN: instead of the (P, C) rows of a voxel, the mean of its points is written (fr.voxels is a
 // (max_voxels, C) buffer): sum over the P slots in slot order (absent slots are +0, as in the
 // zero-padded tensor HardSimpleVFE sums, voxel_encoder.py:27-44), IEEE divide by the count.
@@ -1382,7 +1385,7 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
 // its rows at offset sum(voxel_num of the batch's earlier frames) and its coordinates as
 // (batch index, z, y, x) rows of 16 bytes.
 template <int C, bool MEAN, bool PACK>
-__global__ void __launch_bounds__(kExpThreads, PCFE_EXP_REC_MINB)
+__global__ void __launch_bounds__(kExpThreads, MEAN ? PCFE_EXP_MEAN_MINB : PCFE_EXP_REC_MINB)
 hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
                       const int use_fast_div,
                       const int32_t* __restrict__ voxel_num, const int frames, const int pf_dist,
@@ -1393,11 +1396,10 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   constexpr int PT = 5;
   constexpr int W = PT * C;  // output words per voxel
   // source word (point index * C + feature) of every output word of a warp's tile, kEmpty = zero
-  __shared__ uint32_t eff_all[kExpWarps * 32 * W];
+  __shared__ uint32_t eff_all[MEAN ? 1 : kExpWarps * 32 * W];
   __shared__ __align__(16) int32_t coor_all[kExpWarps * 96];  // (z, y, x) of a tile: one coalesced store
-  __shared__ float mean_all[MEAN ? kExpWarps * 32 * C : 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t* eff = eff_all + wid * (32 * W);
+  uint32_t* eff = eff_all + (MEAN ? 0 : wid * (32 * W));
   int32_t* cstage = coor_all + wid * 96;
 #pragma unroll 1
   for (int wi = blockIdx.x; wi < tiles_x * frames; wi += gridDim.x) {
@@ -1449,7 +1451,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     const bool have = fi_cur != kEmpty;  // false for lanes past the end
     const uint32_t first = fi_cur & 0x7FFFFFFFu;
     const uint32_t len = (have ? 1u : 0u) + (ra_cur.x != kEmpty) + (ra_cur.y != kEmpty) + (ra_cur.z != kEmpty) + (ra_cur.w != kEmpty);
-    {  // lane = voxel: the 25 (20) source words of its output, slot by slot
+    if (!MEAN) {  // lane = voxel: the 25 (20) source words of its output, slot by slot
       const uint32_t idx5[PT] = {have ? first : kEmpty, ra_cur.x, ra_cur.y, ra_cur.z, ra_cur.w};
 #pragma unroll
       for (int j = 0; j < PT; ++j) {
@@ -1467,12 +1469,37 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     }
     __syncwarp();
     // rows of this tile, lane = output word
-    float val[W];
+    float val[MEAN ? C : W];
+    if (MEAN) {
+      // lane = output word of the (32, C) mean tile: word o = lane + 32 r is feature o % C of voxel
+      // o / C, whose point indices sit in that lane's registers (shuffles, no shared memory); the
+      // C lanes of a voxel read the C consecutive words of each of its rows
+      const uint32_t f0 = have ? first : kEmpty;
+#pragma unroll
+      for (int r = 0; r < C; ++r) {
+        const int o = lane + 32 * r;
+        const int vl = o / C, q = o - vl * C;
+        const uint32_t i0 = __shfl_sync(0xFFFFFFFFu, f0, vl), i1 = __shfl_sync(0xFFFFFFFFu, ra_cur.x, vl),
+                       i2 = __shfl_sync(0xFFFFFFFFu, ra_cur.y, vl), i3 = __shfl_sync(0xFFFFFFFFu, ra_cur.z, vl),
+                       i4 = __shfl_sync(0xFFFFFFFFu, ra_cur.w, vl);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+        if (i0 != kEmpty) s0 = __ldg(pts + (size_t)i0 * C + q);
+        if (i1 != kEmpty) s1 = __ldg(pts + (size_t)i1 * C + q);
+        if (i2 != kEmpty) s2 = __ldg(pts + (size_t)i2 * C + q);
+        if (i3 != kEmpty) s3 = __ldg(pts + (size_t)i3 * C + q);
+        if (i4 != kEmpty) s4 = __ldg(pts + (size_t)i4 * C + q);
+        const int cnt = (i0 != kEmpty) + (i1 != kEmpty) + (i2 != kEmpty) + (i3 != kEmpty) + (i4 != kEmpty);
+        // slot-order sum over all five slots (absent = +0), IEEE divide by the count
+        const float a = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3), s4);
+        val[r] = cnt ? __fdiv_rn(a, (float)cnt) : 0.0f;
+      }
+    } else {
 #pragma unroll
     for (int k = 0; k < W; ++k) {
       const uint32_t src = eff[lane + 32 * k];  // word lane + 32 k of the tile
       val[k] = 0.0f;
       if (src != kEmpty) val[k] = __ldg(pts + src);
+    }
     }
     // records of the next tile, first-point indices of the one after
     const uint4 ra_nxt = load_rec(fi_nxt);
@@ -1496,23 +1523,10 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     }
     __syncwarp();
     if (MEAN) {
-      // rows back to (voxel, slot, feature) order through the tile buffer (every lane has read its
-      // source words: the __syncwarp() above), then lane = voxel sums its slots
-      float* tile = reinterpret_cast<float*>(eff);
-#pragma unroll
-      for (int k = 0; k < W; ++k) tile[lane + 32 * k] = val[k];
-      __syncwarp();
-      float* mstage = mean_all + wid * (32 * C);
-#pragma unroll
-      for (int q = 0; q < C; ++q) {
-        float a = tile[lane * W + q];
-#pragma unroll
-        for (int j = 1; j < PT; ++j) a = __fadd_rn(a, tile[lane * W + j * C + q]);
-        mstage[lane * C + q] = have ? __fdiv_rn(a, (float)len) : 0.0f;
-      }
-      __syncwarp();
       float* __restrict__ mdst = fr.voxels + (off + v0) * C;
-      for (int i = lane; i < nvox * C; i += 32) mdst[i] = mstage[i];
+#pragma unroll
+      for (int r = 0; r < C; ++r)
+        if (lane + 32 * r < nvox * C) mdst[lane + 32 * r] = val[r];
     } else {
     float* __restrict__ dst = fr.voxels + (off + v0) * W;
     if (nvox == 32) {
