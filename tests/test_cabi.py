@@ -101,3 +101,51 @@ def test_no_cpu_fallback():
         ops.voxelization(torch.zeros(4, 4), [0.5] * 3, [0, -40, -3, 70.4, 40, 1], 5, 10)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.points_in_boxes_cpu(torch.zeros(4, 3), torch.zeros(1, 7))
+
+
+def test_next_row_entries_argument_errors_without_gpu(lib):
+    """Packed / mean voxelization, the encoder, DynamicScatter and the OpenPCDet point-in-box entries
+    validate their arguments before any CUDA call."""
+    vs, rg = _cabi.f3([0.5] * 3), _cabi.f6([0, -40, -3, 70.4, 40, 1])
+    null, fake = ctypes.c_void_p(0), ctypes.c_void_p(0x1000)
+    fr = (_cabi.Frame * 1)()
+    assert lib.pcfe_hard_voxelize_mean_batch_f32(fr, 1, 5, vs, rg, None, 64, 10, null, null, 0, 0, null) == -2  # P != 5
+    assert lib.pcfe_hard_voxelize_mean_batch_f32(fr, 1, 3, vs, rg, None, 5, 10, null, null, 0, 0, null) == -2   # C not 4 / 5
+    pp, nn = (ctypes.c_void_p * 1)(0x1000), (ctypes.c_int64 * 1)(100)
+    args = (vs, rg, None, 5, 50, 0)
+    assert lib.pcfe_hard_voxelize_packed_batch_f32(pp, nn, 1, 5, *args, fake, fake, fake, 49, fake, fake, 1 << 20, 0, null) == -4
+    assert lib.pcfe_hard_voxelize_packed_batch_f32(pp, nn, 1, 5, *args, fake, ctypes.c_void_p(0x1008), fake, 50, fake, fake,
+                                                   1 << 20, 0, null) == -5
+    assert lib.pcfe_voxel_mean_f32(null, null, null, -1, 5, 4, null, 0, null) == -2
+    assert lib.pcfe_voxel_mean_f32(null, null, null, 0, 5, 4, null, 0, null) == 0      # nothing to do
+    assert lib.pcfe_voxel_mean_f32(null, fake, null, 3, 5, 4, fake, 0, null) == -1
+    dims = (ctypes.c_int32 * 3)(40, 1600, 1408)
+    need = lib.pcfe_dynamic_scatter_workspace_bytes(dims, 3, 120000)
+    # level 1: one bit per 256 cells; level 2: 32 bytes (+ 32 of prefix) per point at most
+    assert 2 * 120000 * 32 <= need <= 2 * 120000 * 32 + 4 * (40 * 1600 * 1408 // 256 // 8) + (1 << 16)
+    assert lib.pcfe_dynamic_scatter_workspace_bytes((ctypes.c_int32 * 3)(1 << 20, 1 << 20, 1 << 20), 3, 10) == 0  # too large
+    assert lib.pcfe_dynamic_scatter_map_i32(fake, 10, 5, dims, fake, fake, fake, 1 << 30, 0, null) == -2  # ndim > 4
+    assert lib.pcfe_dynamic_scatter_map_i32(fake, 10, 3, dims, fake, null, fake, 1 << 30, 0, null) == -1
+    assert lib.pcfe_dynamic_scatter_reduce_f32(fake, fake, fake, 10, 4, 3, 7, 5, fake, fake, fake, 0, null) == -2  # reduce
+    assert lib.pcfe_dynamic_scatter_backward_f32(fake, fake, fake, fake, fake, 10, 5, 0, 2, fake, fake, 0, 0, null) == -2
+    assert lib.pcfe_pcdet_points_in_boxes_gpu_f32(fake, fake, -1, 1, 1, fake, fake, 1 << 20, 0, null) == -2
+    assert lib.pcfe_pcdet_points_in_boxes_cpu_f32(fake, fake, 4, 8, fake, fake, 16, 0, null) == -4
+
+
+def test_next_row_python_mirrors():
+    import torch
+    import detmatch_b200.ops as ops
+    from detmatch_b200.ops.pcdet_roiaware_pool3d import roiaware_pool3d_cuda, roiaware_pool3d_utils
+    for name in ("DynamicScatter", "dynamic_scatter", "HardSimpleVFE", "voxelize_batch_packed", "voxelize_mean_batch"):
+        assert hasattr(ops, name)
+    for mod in (roiaware_pool3d_cuda, roiaware_pool3d_utils):
+        assert hasattr(mod, "points_in_boxes_gpu") and hasattr(mod, "points_in_boxes_cpu")
+    assert repr(ops.DynamicScatter([0.32, 0.32, 6], [-74.88, -74.88, -2, 74.88, 74.88, 4], True)) == (
+        "DynamicScatter(voxel_size=[0.32, 0.32, 6], point_cloud_range=[-74.88, -74.88, -2, 74.88, 74.88, 4], "
+        "average_points=True)")
+    assert ops.HardSimpleVFE(num_features=5).num_features == 5
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU"):
+            ops.hard_simple_vfe(torch.zeros(2, 5, 4), torch.ones(2, dtype=torch.int32))
+        with pytest.raises(RuntimeError, match="no CPU"):
+            ops.dynamic_scatter(torch.zeros(2, 4), torch.zeros(2, 3, dtype=torch.int32), "max")
