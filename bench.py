@@ -26,11 +26,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = "C4"
-# DRAM traffic per 64-frame step from the committed ncu capture (profiles/r01_v13_ncu_summary.txt):
+# DRAM traffic per 64-frame step from the committed ncu capture (profiles/r01_v14_ncu_summary.txt):
 # hvb_bin 288.7 MB + hvb_bucket_rec 174.3 MB + hvb_scan_firsts 3.1 MB + hvb_expand_rec 1042.4 MB
-NCU_TRAFFIC_BYTES_PER_STEP = {"C4": 1_508_500_000}
-NCU_EXPAND_TRAFFIC = {"C4": 1_042_400_000}
-NCU_PROFILE = "profiles/r01_v13_ncu_summary.txt"
+NCU_TRAFFIC_BYTES_PER_STEP = {"C4": 1_510_900_000}
+NCU_EXPAND_TRAFFIC = {"C4": 1_045_500_000}
+NCU_PROFILE = "profiles/r01_v14_ncu_summary.txt"
 KEPT_POINTS_PER_FRAME = {"C4": 156_000}  # points surviving the max_points cap (oracle, seed 4000)
 METRIC = "hard_voxelize_throughput"
 UNIT = "Mpoints/s"
