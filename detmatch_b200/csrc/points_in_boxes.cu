@@ -13,9 +13,11 @@
 // float32 operations.
 #include <algorithm>
 
+#include "hv_common.cuh"
 #include "pcfe_common.cuh"
 
 namespace pcfe {
+int g_opt_pib_grid = 1;  // 0: brute-force first-hit assignment for every frame (test knob)
 namespace {
 
 // ------------------------------------------------------------------------------------------
@@ -124,6 +126,17 @@ struct __align__(16) RBox {
   float cx, cy, r, pad;
 };
 static_assert(sizeof(RBox) == 16, "RBox must be 16 bytes");
+
+// uniform xy grid over a frame's boxes (first-hit assignment, see pib_grid_build_kernel)
+constexpr int kGridN = 64, kGridCells = kGridN * kGridN, kGridMaxSpan = 8, kGridMaxBoxes = 4096;
+constexpr int kGridThreads = 256;
+
+struct __align__(16) GridHdr {
+  float x0, y0, sx, sy;  // origin, cells per unit length
+  int32_t ok, pad0, pad1, pad2;
+};
+static_assert(sizeof(GridHdr) == 32, "GridHdr must be 32 bytes");
+
 
 // pcdet == 0: mmdet3d boxes (cx, cy, cz_bottom, w, l, h, rz), points_in_boxes_cpu.cpp:16-40.
 // pcdet != 0: OpenPCDet boxes (cx, cy, cz_CENTRE, dx, dy, dz, heading) and test,
@@ -325,11 +338,13 @@ pib_all_generic_kernel(const PBox* __restrict__ pboxes, const float* __restrict_
 template <bool BOXMAJOR>
 __global__ void __launch_bounds__(256)
 pib_point_kernel(const PBox* __restrict__ pboxes, const RBox* __restrict__ rboxes,
-                 const float* __restrict__ points, int t, long long m, int32_t* __restrict__ out) {
+                 const float* __restrict__ points, int t, long long m, int32_t* __restrict__ out,
+                 const GridHdr* __restrict__ skip_if_grid = nullptr) {
   __shared__ __align__(16) PBox sboxes[kPointChunk];
   __shared__ __align__(16) RBox srej[kPointChunk];
   __shared__ __align__(8) uint64_t bar;
   const int b = blockIdx.y;
+  if (skip_if_grid && skip_if_grid[b].ok) return;  // the frame was assigned through its grid
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float x = 0.f, y = 0.f, z = 0.f;
   if (p < m) {
@@ -367,6 +382,162 @@ pib_point_kernel(const PBox* __restrict__ pboxes, const RBox* __restrict__ rboxe
   if (!BOXMAJOR && p < m) out[(size_t)b * m + p] = first;
 }
 
+// ------------------------------------------------------------------------------------------
+// First-hit assignment through a uniform xy grid over the frame's boxes.
+// The brute-force kernel above spends 6 instructions on each of the m * t pairs just to reject
+// them.  Here every frame gets a 64 x 64 grid over the bounding square of its boxes' reject
+// circles; a cell lists, in ascending box index, the boxes whose circle (plus a slack that
+// dwarfs float rounding) touches it, and a point runs the exact test only on the list of its own
+// cell.  cell(x) = clamp(floor((x - x0) * sx)) is monotone, a box is listed in every cell of
+// [cell(cx - r - slack), cell(cx + r + slack)]^2, and a point inside a box has |x - cx| <= r and
+// |y - cy| <= r (RBox), so the list of its cell contains every box it can be inside of: the result
+// -- lowest containing box index -- is the brute-force one.  Frames the grid cannot represent
+// (non-finite boxes, a box spanning more than kGridMaxSpan cells per axis, degenerate extent,
+// t > kGridMaxBoxes) are flagged and taken by the brute-force kernel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int grid_cell(float v, float v0, float s) {
+  const float q = floorf(__fmul_rn(__fsub_rn(v, v0), s));
+  // NaN compares false twice and lands in cell 0 (the exact test rejects a NaN point anyway)
+  return q >= (float)(kGridN - 1) ? kGridN - 1 : (q > 0.0f ? (int)q : 0);
+}
+
+__device__ __forceinline__ float grid_slack(float c, float r) {
+  return __fadd_rn(1e-2f, __fmul_rn(1e-6f, __fadd_rn(fabsf(c), r)));
+}
+
+// one CTA per frame
+__global__ void __launch_bounds__(kGridThreads)
+pib_grid_build_kernel(const RBox* __restrict__ rboxes, const int t, GridHdr* __restrict__ hdrs,
+                      uint32_t* __restrict__ starts_base, uint16_t* __restrict__ entries_base) {
+  __shared__ uint32_t cnt[kGridCells];
+  __shared__ uint32_t warp_sums[33];
+  __shared__ float red[4][kGridThreads / 32];
+  __shared__ int s_bad;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const RBox* rb = rboxes + (size_t)b * t;
+  uint32_t* starts = starts_base + (size_t)b * (kGridCells + 1);
+  uint16_t* entries = entries_base + (size_t)b * t * (kGridMaxSpan * kGridMaxSpan);
+  GridHdr* hdr = hdrs + b;
+  if (tid == 0) s_bad = t > kGridMaxBoxes ? 1 : 0;
+  for (int i = tid; i < kGridCells; i += kGridThreads) cnt[i] = 0u;
+  // bounds of the reject circles
+  float xlo = INFINITY, ylo = INFINITY, xhi = -INFINITY, yhi = -INFINITY;
+  bool bad = false;
+  for (int k = tid; k < t; k += kGridThreads) {
+    const RBox r = rb[k];
+    const float sl = grid_slack(fmaxf(fabsf(r.cx), fabsf(r.cy)), r.r);
+    const float e = __fadd_rn(r.r, sl);
+    bad |= !(isfinite(r.cx) && isfinite(r.cy) && isfinite(e));
+    xlo = fminf(xlo, __fsub_rn(r.cx, e)); xhi = fmaxf(xhi, __fadd_rn(r.cx, e));
+    ylo = fminf(ylo, __fsub_rn(r.cy, e)); yhi = fmaxf(yhi, __fadd_rn(r.cy, e));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    xlo = fminf(xlo, __shfl_xor_sync(0xFFFFFFFFu, xlo, d)); xhi = fmaxf(xhi, __shfl_xor_sync(0xFFFFFFFFu, xhi, d));
+    ylo = fminf(ylo, __shfl_xor_sync(0xFFFFFFFFu, ylo, d)); yhi = fmaxf(yhi, __shfl_xor_sync(0xFFFFFFFFu, yhi, d));
+  }
+  if (lane == 0) { red[0][wid] = xlo; red[1][wid] = xhi; red[2][wid] = ylo; red[3][wid] = yhi; }
+  __syncthreads();
+  if (bad) s_bad = 1;
+  xlo = red[0][0]; xhi = red[1][0]; ylo = red[2][0]; yhi = red[3][0];
+  for (int k = 1; k < kGridThreads / 32; ++k) {
+    xlo = fminf(xlo, red[0][k]); xhi = fmaxf(xhi, red[1][k]); ylo = fminf(ylo, red[2][k]); yhi = fmaxf(yhi, red[3][k]);
+  }
+  const float sx = __fdiv_rn((float)kGridN, __fsub_rn(xhi, xlo)), sy = __fdiv_rn((float)kGridN, __fsub_rn(yhi, ylo));
+  __syncthreads();
+  if (tid == 0 && !(isfinite(sx) && isfinite(sy) && sx > 0.0f && sy > 0.0f)) s_bad = 1;
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) *hdr = GridHdr{0.f, 0.f, 0.f, 0.f, 0, 0, 0, 0};
+    return;
+  }
+  // pass 1: cells per box, counts per cell
+  for (int k = tid; k < t; k += kGridThreads) {
+    const RBox r = rb[k];
+    const float e = __fadd_rn(r.r, grid_slack(fmaxf(fabsf(r.cx), fabsf(r.cy)), r.r));
+    const int cx0 = grid_cell(__fsub_rn(r.cx, e), xlo, sx), cx1 = grid_cell(__fadd_rn(r.cx, e), xlo, sx);
+    const int cy0 = grid_cell(__fsub_rn(r.cy, e), ylo, sy), cy1 = grid_cell(__fadd_rn(r.cy, e), ylo, sy);
+    if (cx1 - cx0 >= kGridMaxSpan || cy1 - cy0 >= kGridMaxSpan) { s_bad = 1; continue; }
+    for (int cy = cy0; cy <= cy1; ++cy)
+      for (int cx = cx0; cx <= cx1; ++cx) atomicAdd(&cnt[cy * kGridN + cx], 1u);
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) *hdr = GridHdr{0.f, 0.f, 0.f, 0.f, 0, 0, 0, 0};
+    return;
+  }
+  // exclusive scan of the counts: thread i owns cells [16 i, 16 i + 16)
+  constexpr int kPerThread = kGridCells / kGridThreads;
+  uint32_t local[kPerThread], sum = 0;
+#pragma unroll
+  for (int j = 0; j < kPerThread; ++j) { local[j] = cnt[tid * kPerThread + j]; sum += local[j]; }
+  uint32_t total;
+  uint32_t run = block_exscan(sum, warp_sums, &total);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kPerThread; ++j) {
+    starts[tid * kPerThread + j] = run;
+    cnt[tid * kPerThread + j] = run;  // becomes the fill cursor
+    run += local[j];
+  }
+  if (tid == kGridThreads - 1) starts[kGridCells] = total;
+  __syncthreads();
+  // pass 2: fill (unordered inside a cell)
+  for (int k = tid; k < t; k += kGridThreads) {
+    const RBox r = rb[k];
+    const float e = __fadd_rn(r.r, grid_slack(fmaxf(fabsf(r.cx), fabsf(r.cy)), r.r));
+    const int cx0 = grid_cell(__fsub_rn(r.cx, e), xlo, sx), cx1 = grid_cell(__fadd_rn(r.cx, e), xlo, sx);
+    const int cy0 = grid_cell(__fsub_rn(r.cy, e), ylo, sy), cy1 = grid_cell(__fadd_rn(r.cy, e), ylo, sy);
+    for (int cy = cy0; cy <= cy1; ++cy)
+      for (int cx = cx0; cx <= cx1; ++cx) entries[atomicAdd(&cnt[cy * kGridN + cx], 1u)] = (uint16_t)k;
+  }
+  __syncthreads();
+  // pass 3: ascending box index inside every cell (first hit = lowest index); the owner of a cell
+  // sorts the list it finds in global memory (written by this CTA: visible after the barrier)
+#pragma unroll 1
+  for (int j = 0; j < kPerThread; ++j) {
+    const int cell = tid * kPerThread + j;
+    const uint32_t lo = starts[cell], hi = cnt[cell];
+    for (uint32_t i = lo + 1; i < hi; ++i) {
+      const uint16_t v = entries[i];
+      uint32_t q = i;
+      while (q > lo && entries[q - 1] > v) { entries[q] = entries[q - 1]; --q; }
+      entries[q] = v;
+    }
+  }
+  if (tid == 0) *hdr = GridHdr{xlo, ylo, sx, sy, 1, 0, 0, 0};
+}
+
+// thread = one point of a frame with a grid
+__global__ void __launch_bounds__(256)
+pib_point_grid_kernel(const PBox* __restrict__ pboxes, const GridHdr* __restrict__ hdrs,
+                      const uint32_t* __restrict__ starts_base, const uint16_t* __restrict__ entries_base,
+                      const float* __restrict__ points, const int t, const long long m, int32_t* __restrict__ out) {
+  const int b = blockIdx.y;
+  const GridHdr h = hdrs[b];
+  if (!h.ok) return;  // pib_point_kernel takes the frame
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= m) return;
+  const float* gp = points + ((size_t)b * m + p) * 3;
+  const float x = __ldg(gp), y = __ldg(gp + 1), z = __ldg(gp + 2);
+  const int cell = grid_cell(y, h.y0, h.sy) * kGridN + grid_cell(x, h.x0, h.sx);
+  const uint32_t* starts = starts_base + (size_t)b * (kGridCells + 1);
+  const uint16_t* entries = entries_base + (size_t)b * t * (kGridMaxSpan * kGridMaxSpan);
+  const uint32_t lo = __ldg(starts + cell), hi = __ldg(starts + cell + 1);
+  const float4* pb4 = reinterpret_cast<const float4*>(pboxes + (size_t)b * t);
+  int first = -1;
+  for (uint32_t i = lo; i < hi; ++i) {
+    const int k = (int)__ldg(entries + i);
+    const float4 a = __ldg(pb4 + 2 * k), c = __ldg(pb4 + 2 * k + 1);
+    const PBox bx{a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    if (in_box(x, y, z, bx)) {
+      first = k;
+      break;
+    }
+  }
+  out[(size_t)b * m + p] = first;
+}
+
 __global__ void fill_kernel(int32_t* out, long long n, int32_t v) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = v;
@@ -391,9 +562,18 @@ int check_common(const float* boxes, const float* points, const int32_t* out, in
   return PCFE_OK;
 }
 
-// workspace layout: PBox[nboxes] | (256-byte aligned) RBox[nboxes]
+// workspace layout: PBox[nboxes] | (256-byte aligned) RBox[nboxes] | GridHdr[b] | starts[b][4097] |
+// entries[b][t * 64]   (the grid part is used by the first-hit entries only)
 inline RBox* rbox_base(void* ws, int64_t nboxes) {
   return reinterpret_cast<RBox*>((char*)ws + align256((size_t)nboxes * sizeof(PBox)));
+}
+inline size_t grid_off(int b, int t) {
+  return align256((size_t)b * t * sizeof(PBox)) + align256((size_t)b * t * sizeof(RBox));
+}
+inline size_t grid_hdr_bytes(int b) { return align256((size_t)b * sizeof(GridHdr)); }
+inline size_t grid_starts_bytes(int b) { return align256((size_t)b * (kGridCells + 1) * sizeof(uint32_t)); }
+inline size_t grid_entries_bytes(int b, int t) {
+  return align256((size_t)b * t * (kGridMaxSpan * kGridMaxSpan) * sizeof(uint16_t));
 }
 
 int prepare(const float* boxes, int64_t nboxes, void* ws, cudaStream_t st, int pcdet = 0, float margin = 0.0f) {
@@ -410,7 +590,7 @@ using namespace pcfe;
 
 extern "C" size_t pcfe_points_in_boxes_workspace_bytes(int b, int t) {
   if (b <= 0 || t <= 0) return 256;
-  return align256((size_t)b * (size_t)t * sizeof(PBox)) + align256((size_t)b * (size_t)t * sizeof(RBox));
+  return grid_off(b, t) + grid_hdr_bytes(b) + grid_starts_bytes(b) + grid_entries_bytes(b, t);
 }
 
 static int part_impl(const float* boxes, const float* points, int b, int t, int64_t m, int32_t* out, void* ws,
@@ -428,8 +608,23 @@ static int part_impl(const float* boxes, const float* points, int b, int t, int6
   }
   PBox* pb = (PBox*)ws;
   if ((rc = prepare(boxes, (int64_t)b * t, ws, st, pcdet, margin)) != PCFE_OK) return rc;
+  const RBox* rb = rbox_base(ws, (int64_t)b * t);
   dim3 grid((unsigned)((m + 255) / 256), (unsigned)b);
-  pib_point_kernel<false><<<grid, 256, 0, st>>>(pb, rbox_base(ws, (int64_t)b * t), points, t, (long long)m, out);
+  if (g_opt_pib_grid) {
+    // frames whose boxes fit a 64 x 64 grid are assigned through it, the others by brute force
+    char* gbase = (char*)ws + grid_off(b, t);
+    GridHdr* hdrs = (GridHdr*)gbase;
+    uint32_t* starts = (uint32_t*)(gbase + grid_hdr_bytes(b));
+    uint16_t* entries = (uint16_t*)(gbase + grid_hdr_bytes(b) + grid_starts_bytes(b));
+    pib_grid_build_kernel<<<b, kGridThreads, 0, st>>>(rb, t, hdrs, starts, entries);
+    PCFE_LAUNCH_CHECK();
+    pib_point_grid_kernel<<<grid, 256, 0, st>>>(pb, hdrs, starts, entries, points, t, (long long)m, out);
+    PCFE_LAUNCH_CHECK();
+    pib_point_kernel<false><<<grid, 256, 0, st>>>(pb, rb, points, t, (long long)m, out, hdrs);
+    PCFE_LAUNCH_CHECK();
+    return PCFE_OK;
+  }
+  pib_point_kernel<false><<<grid, 256, 0, st>>>(pb, rb, points, t, (long long)m, out);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
 }

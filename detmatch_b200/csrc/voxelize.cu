@@ -50,6 +50,7 @@ extern int g_opt_bucket_variant;
 extern int g_opt_expand_variant;
 extern int g_opt_expand_ctas;
 extern int g_opt_pdl;
+extern int g_opt_pib_grid;
 extern int g_opt_expand_vpw;
 extern int g_opt_no_fast_div;
 extern int g_opt_expand_prefetch;
@@ -434,6 +435,7 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_no_fast_div")) g_opt_no_fast_div = value;
   else if (!strcmp(name, "hv_expand_vpw")) g_opt_expand_vpw = value > 0 ? value : 4;
   else if (!strcmp(name, "hv_pdl")) g_opt_pdl = value;
+  else if (!strcmp(name, "pib_grid")) g_opt_pib_grid = value;
   else if (!strcmp(name, "hv_expand_ctas")) g_opt_expand_ctas = value;
   else if (!strcmp(name, "mega_d1")) g_opt_mega_d1 = value;
   else if (!strcmp(name, "mega_d2")) g_opt_mega_d2 = value;

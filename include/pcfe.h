@@ -265,7 +265,9 @@ int pcfe_dynamic_scatter_backward_f32(const float* grad_voxel_feats, const float
  *   _all    -> out (b, m, t) int32 0/1, point-major                                  ("batch")
  *   _boxmajor: boxes (t,7), points (n,3) -> out (t, n) int32 0/1                     ("cpu" layout)
  * Every element of `out` is written (no pre-fill needed).  b, m or t == 0 is a no-op.
- * workspace: >= pcfe_points_in_boxes_workspace_bytes(b, t) bytes, 256-byte aligned.
+ * workspace: >= pcfe_points_in_boxes_workspace_bytes(b, t) bytes, 256-byte aligned (prepared boxes,
+ * reject records and, for _part_, a per-frame 64 x 64 grid of box lists: 48 + 128 bytes per box,
+ * 16 KB per frame).
  * ------------------------------------------------------------------------------------------- */
 size_t pcfe_points_in_boxes_workspace_bytes(int b, int t);
 

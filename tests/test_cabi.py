@@ -57,7 +57,10 @@ def test_workspace_sizing(lib):
     # empty grid -> 0 (error)
     assert lib.pcfe_hard_voxelize_workspace_bytes(10, 1, 1, vs, _cabi.f6([0, 0, 0, 0, 0, 0]), 5, 10) == 0
     # prepared boxes (32 B) + conservative-reject records (16 B) per box
-    assert lib.pcfe_points_in_boxes_workspace_bytes(16, 200) == 16 * 200 * (32 + 16)
+    # prepared boxes + reject records + (first-hit grid) headers, cell starts, cell lists of 64 entries per box
+    al = lambda x: (x + 255) // 256 * 256  # noqa: E731
+    assert lib.pcfe_points_in_boxes_workspace_bytes(16, 200) == (
+        16 * 200 * (32 + 16) + al(16 * 32) + al(16 * 4097 * 4) + al(16 * 200 * 64 * 2))
 
 
 def test_argument_errors_without_gpu(lib):

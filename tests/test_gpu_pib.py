@@ -15,6 +15,15 @@ from tests.helpers import assert_same_bits, golden, golden_names
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["grid", "brute"])
+def pib_mode(request):
+    """First-hit assignment (points_in_boxes_gpu) through the per-frame box grid (default) and by
+    brute force over all boxes; the other two ops ignore the knob."""
+    _cabi.debug_set("pib_grid", 1 if request.param == "grid" else 0)
+    yield request.param
+    _cabi.debug_set("pib_grid", 1)
+
+
 def _all_three(pts, bxs, what):
     """pts (B,M,3), bxs (B,T,7) numpy -> checks the three ops against the oracle."""
     tp, tb = torch.from_numpy(pts).cuda(), torch.from_numpy(bxs).cuda()
@@ -186,3 +195,76 @@ def test_device_trig_equals_host_libm():
     nan = np.isnan(hs) & np.isnan(gs) & np.isnan(hc) & np.isnan(gc)
     bad = ((hs.view(np.uint32) != gs.view(np.uint32)) | (hc.view(np.uint32) != gc.view(np.uint32))) & ~nan
     assert bad.sum() == 0, f"{int(bad.sum())} device sin/cos values differ from the host libm, first x bits {u[np.argmax(bad)]:#x}"
+
+
+def _first_hit(pts, bxs, what):
+    got = points_in_boxes_gpu(torch.from_numpy(pts).cuda(), torch.from_numpy(bxs).cuda()).cpu().numpy()
+    assert_same_bits(got, oracle.points_in_boxes_gpu(pts, bxs), what)
+    return got
+
+
+def test_first_hit_grid_adversarial():
+    """Frames the box grid must get right or hand to the brute-force kernel: heavily overlapping
+    boxes (lowest index wins), one huge box (spans more than 8 cells), non-finite boxes, all boxes
+    identical, a single box, tiny boxes far from the origin, points far outside the boxes' extent,
+    and more boxes than the grid lists (t > 4096)."""
+    rng = np.random.default_rng(7)
+    c3 = synth.CONFIGS["C3"]
+    m = 6000
+    pts = np.stack([synth.lidar_frame(m, 3, 4300 + k, c3["r_max"]).numpy() for k in range(2)])
+    base = np.stack([synth.random_boxes(60, 4310 + k, c3["point_cloud_range"]).numpy() for k in range(2)])
+    base[:, :40, 0:3] = pts[:, :40]
+    base[:, :40, 2] -= 0.5
+
+    # overlapping stacks: boxes 0..39 centred on points, boxes 40..59 copies of earlier ones (never win)
+    ov = base.copy()
+    ov[:, 40:60] = ov[:, 0:20]
+    got = _first_hit(pts, ov, "overlap")
+    assert (got >= 40).sum() == 0 and (got >= 0).sum() > 40
+
+    huge = base.copy()
+    huge[0, 5, 3:6] = [150.0, 160.0, 10.0]      # frame 0 falls back, frame 1 keeps its grid
+    huge[0, 5, 0:3] = [0.0, 0.0, -5.0]
+    got = _first_hit(pts, huge, "huge box")
+    assert (got[0] == 5).sum() > 1000
+
+    bad = base.copy()
+    bad[1, 7, 0] = np.nan
+    bad[1, 8, 3] = np.inf
+    bad[0, 9, 6] = np.nan                        # NaN yaw: finite centre and radius, nothing inside
+    _first_hit(pts, bad, "non-finite boxes")
+
+    same = np.repeat(base[:, :1], 30, axis=1)
+    got = _first_hit(pts, same, "identical boxes")
+    assert set(np.unique(got)) <= {-1, 0}
+
+    _first_hit(pts, base[:, :1], "one box")
+
+    tiny = base.copy()
+    tiny[:, :, 3:6] = 0.02
+    tiny[:, :, 0:2] += 1.0e5                      # ulp(1e5) = 0.0078 > box size
+    far_pts = pts.copy()
+    far_pts[:, :2000, 0:2] += np.float32(1.0e5)
+    far_pts[:, :40, 0:3] = tiny[:, :40, 0:3] + np.float32([0, 0, 0.01])
+    _first_hit(far_pts, tiny, "tiny boxes far from the origin")
+
+    outside = pts.copy()
+    outside[:, ::3, 0] *= 50.0
+    outside[:, 1::7, 1] = -np.inf
+    outside[:, 2::11, 2] = np.nan
+    _first_hit(outside, base, "points outside the grid")
+
+    many = np.stack([synth.random_boxes(4500, 4320 + k, c3["point_cloud_range"]).numpy() for k in range(2)])
+    _first_hit(pts[:, :1500], many, "t > 4096")
+
+
+@pytest.mark.parametrize("t", [1, 33, 200, 513, 1100])
+def test_first_hit_random_vs_oracle(t):
+    c3 = synth.CONFIGS["C3"]
+    pts = np.stack([synth.lidar_frame(20000, 3, 4400 + k, c3["r_max"]).numpy() for k in range(3)])
+    bxs = np.stack([synth.random_boxes(t, 4410 + k, c3["point_cloud_range"]).numpy() for k in range(3)])
+    k = min(t, 64)
+    bxs[:, :k, 0:3] = pts[:, :k]
+    bxs[:, :k, 2] -= 0.4
+    got = _first_hit(pts, bxs, f"t={t}")
+    assert (got >= 0).sum() >= k
