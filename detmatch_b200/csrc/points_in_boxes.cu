@@ -438,7 +438,7 @@ pib_grid_build_kernel(const RBox* __restrict__ rboxes, const int t, GridHdr* __r
   }
   if (lane == 0) { red[0][wid] = xlo; red[1][wid] = xhi; red[2][wid] = ylo; red[3][wid] = yhi; }
   __syncthreads();
-  if (bad) s_bad = 1;
+  if (bad) atomicOr(&s_bad, 1);
   xlo = red[0][0]; xhi = red[1][0]; ylo = red[2][0]; yhi = red[3][0];
   for (int k = 1; k < kGridThreads / 32; ++k) {
     xlo = fminf(xlo, red[0][k]); xhi = fmaxf(xhi, red[1][k]); ylo = fminf(ylo, red[2][k]); yhi = fmaxf(yhi, red[3][k]);
@@ -457,7 +457,7 @@ pib_grid_build_kernel(const RBox* __restrict__ rboxes, const int t, GridHdr* __r
     const float e = __fadd_rn(r.r, grid_slack(fmaxf(fabsf(r.cx), fabsf(r.cy)), r.r));
     const int cx0 = grid_cell(__fsub_rn(r.cx, e), xlo, sx), cx1 = grid_cell(__fadd_rn(r.cx, e), xlo, sx);
     const int cy0 = grid_cell(__fsub_rn(r.cy, e), ylo, sy), cy1 = grid_cell(__fadd_rn(r.cy, e), ylo, sy);
-    if (cx1 - cx0 >= kGridMaxSpan || cy1 - cy0 >= kGridMaxSpan) { s_bad = 1; continue; }
+    if (cx1 - cx0 >= kGridMaxSpan || cy1 - cy0 >= kGridMaxSpan) { atomicOr(&s_bad, 1); continue; }
     for (int cy = cy0; cy <= cy1; ++cy)
       for (int cx = cx0; cx <= cx1; ++cx) atomicAdd(&cnt[cy * kGridN + cx], 1u);
   }
