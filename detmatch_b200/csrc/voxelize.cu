@@ -369,6 +369,42 @@ voxel_mean_kernel(const float* __restrict__ voxels, const int32_t* __restrict__ 
   }
 }
 
+// Short voxels (max_points * c <= 64 words): a warp stages 32 voxels -- one contiguous run of
+// 32 * W words, read as 128-byte coalesced loads -- in shared memory, then lane = output word adds
+// the slots of its (voxel, feature) in slot order and the (32, nf) tile leaves as coalesced stores.
+constexpr int kVfeWarps = 8, kVfeMaxW = 64;
+
+__global__ void __launch_bounds__(kVfeWarps * 32)
+voxel_mean_tile_kernel(const float* __restrict__ voxels, const int32_t* __restrict__ num_points,
+                       const int32_t* __restrict__ voxel_num, const long long m_cap, const int max_points,
+                       const int c, const int nf /* row stride of voxels is c, the first nf features are reduced */,
+                       float* __restrict__ out) {
+  extern __shared__ float vfe_smem[];
+  const long long m = voxel_num ? min((long long)__ldg(voxel_num), m_cap) : m_cap;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int W = max_points * c;
+  float* buf = vfe_smem + (size_t)wid * 32 * W;
+  const long long tiles = (m + 31) / 32;
+  for (long long tile = (long long)blockIdx.x * kVfeWarps + wid; tile < tiles; tile += (long long)gridDim.x * kVfeWarps) {
+    const long long v0 = tile * 32;
+    const int nvox = (int)min(32ll, m - v0);
+    const float* __restrict__ src = voxels + (size_t)v0 * W;
+    const int words = nvox * W;
+    for (int i = lane; i < words; i += 32) buf[i] = __ldg(src + i);
+    __syncwarp();
+    const int outs = nvox * nf;
+    float* __restrict__ dst = out + (size_t)v0 * nf;
+    for (int o = lane; o < outs; o += 32) {
+      const int v = o / nf, q = o - v * nf;
+      const float* row = buf + v * W + q;
+      float a = row[0];
+      for (int sl = 1; sl < max_points; ++sl) a = __fadd_rn(a, row[sl * c]);
+      dst[o] = __fdiv_rn(a, (float)__ldg(num_points + v0 + v));
+    }
+    __syncwarp();  // the tile buffer is reused
+  }
+}
+
 extern "C" int pcfe_voxel_mean_f32(const float* voxels, const int32_t* num_points, const int32_t* voxel_num,
                                    int64_t m, int max_points, int c, float* out, int device, void* stream) {
   if (m < 0 || max_points < 1 || c < 1) return PCFE_ERR_SHAPE;
@@ -383,6 +419,15 @@ extern "C" int pcfe_voxel_mean_f32(const float* voxels, const int32_t* num_point
   const long long want = (total + 255) / 256;
   const int grid = (int)std::min<long long>(want, 148ll * 8 * 16);
   ProfScope ps("voxel_mean", st);
+  if ((long long)max_points * c <= kVfeMaxW) {
+    const size_t smem = (size_t)kVfeWarps * 32 * max_points * c * sizeof(float);  // <= 64 KB
+    PCFE_CUDA_TRY(cudaFuncSetAttribute(voxel_mean_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long tiles = (m + 31) / 32;
+    const int tgrid = (int)std::min<long long>((tiles + kVfeWarps - 1) / kVfeWarps, 148ll * 8 * 8);
+    voxel_mean_tile_kernel<<<tgrid, kVfeWarps * 32, smem, st>>>(voxels, num_points, voxel_num, m, max_points, c, c, out);
+    PCFE_LAUNCH_CHECK();
+    return PCFE_OK;
+  }
   voxel_mean_kernel<<<grid, 256, 0, st>>>(voxels, num_points, voxel_num, m, max_points, c, out);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
