@@ -129,6 +129,7 @@ static_assert(sizeof(RBox) == 16, "RBox must be 16 bytes");
 
 // uniform xy grid over a frame's boxes (first-hit assignment, see pib_grid_build_kernel)
 constexpr int kGridN = 64, kGridCells = kGridN * kGridN, kGridMaxSpan = 8, kGridMaxBoxes = 4096;
+constexpr int kGridMaxList = 128;  // boxes per cell: longer lists (an outlier box stretching the grid) -> brute force
 constexpr int kGridThreads = 256;
 
 struct __align__(16) GridHdr {
@@ -392,8 +393,8 @@ pib_point_kernel(const PBox* __restrict__ pboxes, const RBox* __restrict__ rboxe
 // [cell(cx - r - slack), cell(cx + r + slack)]^2, and a point inside a box has |x - cx| <= r and
 // |y - cy| <= r (RBox), so the list of its cell contains every box it can be inside of: the result
 // -- lowest containing box index -- is the brute-force one.  Frames the grid cannot represent
-// (non-finite boxes, a box spanning more than kGridMaxSpan cells per axis, degenerate extent,
-// t > kGridMaxBoxes) are flagged and taken by the brute-force kernel.
+// (non-finite boxes, a box spanning more than kGridMaxSpan cells per axis, a cell listing more than
+// kGridMaxList boxes, degenerate extent, t > kGridMaxBoxes) are flagged and taken by the brute-force kernel.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int grid_cell(float v, float v0, float s) {
   const float q = floorf(__fmul_rn(__fsub_rn(v, v0), s));
@@ -469,11 +470,21 @@ pib_grid_build_kernel(const RBox* __restrict__ rboxes, const int t, GridHdr* __r
   // exclusive scan of the counts: thread i owns cells [16 i, 16 i + 16)
   constexpr int kPerThread = kGridCells / kGridThreads;
   uint32_t local[kPerThread], sum = 0;
+  uint32_t longest = 0;
 #pragma unroll
-  for (int j = 0; j < kPerThread; ++j) { local[j] = cnt[tid * kPerThread + j]; sum += local[j]; }
+  for (int j = 0; j < kPerThread; ++j) {
+    local[j] = cnt[tid * kPerThread + j];
+    sum += local[j];
+    longest = max(longest, local[j]);
+  }
+  if (longest > (uint32_t)kGridMaxList) atomicOr(&s_bad, 1);
   uint32_t total;
-  uint32_t run = block_exscan(sum, warp_sums, &total);
+  uint32_t run = block_exscan(sum, warp_sums, &total);  // (contains the barriers that publish s_bad)
   __syncthreads();
+  if (s_bad) {
+    if (tid == 0) *hdr = GridHdr{0.f, 0.f, 0.f, 0.f, 0, 0, 0, 0};
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < kPerThread; ++j) {
     starts[tid * kPerThread + j] = run;
@@ -573,6 +584,7 @@ inline size_t grid_off(int b, int t) {
 inline size_t grid_hdr_bytes(int b) { return align256((size_t)b * sizeof(GridHdr)); }
 inline size_t grid_starts_bytes(int b) { return align256((size_t)b * (kGridCells + 1) * sizeof(uint32_t)); }
 inline size_t grid_entries_bytes(int b, int t) {
+  if (t > kGridMaxBoxes) return 0;  // such frames never get a grid
   return align256((size_t)b * t * (kGridMaxSpan * kGridMaxSpan) * sizeof(uint16_t));
 }
 

@@ -254,6 +254,10 @@ def test_first_hit_grid_adversarial():
     outside[:, 2::11, 2] = np.nan
     _first_hit(outside, base, "points outside the grid")
 
+    stretched = np.concatenate([np.repeat(base[:, :1], 140, axis=1), base], axis=1)  # 141 boxes in one cell
+    stretched[0, 150, 0] = 1.0e6                                                      # an outlier stretches the grid
+    _first_hit(pts, stretched, "long cell lists / stretched grid")
+
     many = np.stack([synth.random_boxes(4500, 4320 + k, c3["point_cloud_range"]).numpy() for k in range(2)])
     _first_hit(pts[:, :1500], many, "t > 4096")
 
