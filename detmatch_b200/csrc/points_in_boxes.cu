@@ -130,7 +130,7 @@ static_assert(sizeof(RBox) == 16, "RBox must be 16 bytes");
 // uniform xy grid over a frame's boxes (first-hit assignment, see pib_grid_build_kernel)
 constexpr int kGridN = 64, kGridCells = kGridN * kGridN, kGridMaxSpan = 8, kGridMaxBoxes = 4096;
 constexpr int kGridMaxList = 128;  // boxes per cell: longer lists (an outlier box stretching the grid) -> brute force
-constexpr int kGridThreads = 256;
+constexpr int kGridThreads = 1024;
 
 struct __align__(16) GridHdr {
   float x0, y0, sx, sy;  // origin, cells per unit length
@@ -339,13 +339,11 @@ pib_all_generic_kernel(const PBox* __restrict__ pboxes, const float* __restrict_
 template <bool BOXMAJOR>
 __global__ void __launch_bounds__(256)
 pib_point_kernel(const PBox* __restrict__ pboxes, const RBox* __restrict__ rboxes,
-                 const float* __restrict__ points, int t, long long m, int32_t* __restrict__ out,
-                 const GridHdr* __restrict__ skip_if_grid = nullptr) {
+                 const float* __restrict__ points, int t, long long m, int32_t* __restrict__ out) {
   __shared__ __align__(16) PBox sboxes[kPointChunk];
   __shared__ __align__(16) RBox srej[kPointChunk];
   __shared__ __align__(8) uint64_t bar;
   const int b = blockIdx.y;
-  if (skip_if_grid && skip_if_grid[b].ok) return;  // the frame was assigned through its grid
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float x = 0.f, y = 0.f, z = 0.f;
   if (p < m) {
@@ -519,34 +517,77 @@ pib_grid_build_kernel(const RBox* __restrict__ rboxes, const int t, GridHdr* __r
   if (tid == 0) *hdr = GridHdr{xlo, ylo, sx, sy, 1, 0, 0, 0};
 }
 
-// thread = one point of a frame with a grid
+// thread = two points (256 apart) of a frame: their grid look-ups are issued together, which doubles
+// the loads in flight of a kernel that is all dependent loads (cell -> list -> box).  A frame without
+// a grid is tested against all boxes straight from global memory (every lane reads the same box:
+// uniform, L1-resident loads).
+constexpr int kGridPointsPerThread = 2;
+
 __global__ void __launch_bounds__(256)
-pib_point_grid_kernel(const PBox* __restrict__ pboxes, const GridHdr* __restrict__ hdrs,
-                      const uint32_t* __restrict__ starts_base, const uint16_t* __restrict__ entries_base,
-                      const float* __restrict__ points, const int t, const long long m, int32_t* __restrict__ out) {
+pib_point_grid_kernel(const PBox* __restrict__ pboxes, const RBox* __restrict__ rboxes,
+                      const GridHdr* __restrict__ hdrs, const uint32_t* __restrict__ starts_base,
+                      const uint16_t* __restrict__ entries_base, const float* __restrict__ points, const int t,
+                      const long long m, int32_t* __restrict__ out) {
   const int b = blockIdx.y;
   const GridHdr h = hdrs[b];
-  if (!h.ok) return;  // pib_point_kernel takes the frame
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= m) return;
-  const float* gp = points + ((size_t)b * m + p) * 3;
-  const float x = __ldg(gp), y = __ldg(gp + 1), z = __ldg(gp + 2);
-  const int cell = grid_cell(y, h.y0, h.sy) * kGridN + grid_cell(x, h.x0, h.sx);
-  const uint32_t* starts = starts_base + (size_t)b * (kGridCells + 1);
-  const uint16_t* entries = entries_base + (size_t)b * t * (kGridMaxSpan * kGridMaxSpan);
-  const uint32_t lo = __ldg(starts + cell), hi = __ldg(starts + cell + 1);
+  const long long p0 = (long long)blockIdx.x * (256 * kGridPointsPerThread) + threadIdx.x;
   const float4* pb4 = reinterpret_cast<const float4*>(pboxes + (size_t)b * t);
-  int first = -1;
-  for (uint32_t i = lo; i < hi; ++i) {
-    const int k = (int)__ldg(entries + i);
-    const float4 a = __ldg(pb4 + 2 * k), c = __ldg(pb4 + 2 * k + 1);
-    const PBox bx{a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-    if (in_box(x, y, z, bx)) {
-      first = k;
-      break;
+  float x[kGridPointsPerThread], y[kGridPointsPerThread], z[kGridPointsPerThread];
+#pragma unroll
+  for (int j = 0; j < kGridPointsPerThread; ++j) {
+    const long long p = p0 + 256 * j;
+    x[j] = y[j] = z[j] = 0.f;
+    if (p < m) {
+      const float* gp = points + ((size_t)b * m + p) * 3;
+      x[j] = __ldg(gp); y[j] = __ldg(gp + 1); z[j] = __ldg(gp + 2);
     }
   }
-  out[(size_t)b * m + p] = first;
+  if (!h.ok) {  // brute force, first hit wins
+    const RBox* rb = rboxes + (size_t)b * t;
+#pragma unroll
+    for (int j = 0; j < kGridPointsPerThread; ++j) {
+      const long long p = p0 + 256 * j;
+      if (p >= m) continue;
+      int first = -1;
+      for (int k = 0; k < t; ++k) {
+        const float4 rr = __ldg(reinterpret_cast<const float4*>(rb + k));
+        if (xy_reject(x[j], y[j], RBox{rr.x, rr.y, rr.z, rr.w})) continue;
+        const float4 a = __ldg(pb4 + 2 * k), c = __ldg(pb4 + 2 * k + 1);
+        const PBox bx{a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        if (in_box(x[j], y[j], z[j], bx)) {
+          first = k;
+          break;
+        }
+      }
+      out[(size_t)b * m + p] = first;
+    }
+    return;
+  }
+  const uint32_t* starts = starts_base + (size_t)b * (kGridCells + 1);
+  const uint16_t* entries = entries_base + (size_t)b * t * (kGridMaxSpan * kGridMaxSpan);
+  uint32_t lo[kGridPointsPerThread], hi[kGridPointsPerThread];
+#pragma unroll
+  for (int j = 0; j < kGridPointsPerThread; ++j) {
+    const int cell = grid_cell(y[j], h.y0, h.sy) * kGridN + grid_cell(x[j], h.x0, h.sx);
+    lo[j] = __ldg(starts + cell);
+    hi[j] = __ldg(starts + cell + 1);
+  }
+#pragma unroll
+  for (int j = 0; j < kGridPointsPerThread; ++j) {
+    const long long p = p0 + 256 * j;
+    if (p >= m) continue;
+    int first = -1;
+    for (uint32_t i = lo[j]; i < hi[j]; ++i) {
+      const int k = (int)__ldg(entries + i);
+      const float4 a = __ldg(pb4 + 2 * k), c = __ldg(pb4 + 2 * k + 1);
+      const PBox bx{a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      if (in_box(x[j], y[j], z[j], bx)) {
+        first = k;
+        break;
+      }
+    }
+    out[(size_t)b * m + p] = first;
+  }
 }
 
 __global__ void fill_kernel(int32_t* out, long long n, int32_t v) {
@@ -630,9 +671,9 @@ static int part_impl(const float* boxes, const float* points, int b, int t, int6
     uint16_t* entries = (uint16_t*)(gbase + grid_hdr_bytes(b) + grid_starts_bytes(b));
     pib_grid_build_kernel<<<b, kGridThreads, 0, st>>>(rb, t, hdrs, starts, entries);
     PCFE_LAUNCH_CHECK();
-    pib_point_grid_kernel<<<grid, 256, 0, st>>>(pb, hdrs, starts, entries, points, t, (long long)m, out);
-    PCFE_LAUNCH_CHECK();
-    pib_point_kernel<false><<<grid, 256, 0, st>>>(pb, rb, points, t, (long long)m, out, hdrs);
+    const int per_cta = 256 * kGridPointsPerThread;
+    dim3 ggrid((unsigned)((m + per_cta - 1) / per_cta), (unsigned)b);
+    pib_point_grid_kernel<<<ggrid, 256, 0, st>>>(pb, rb, hdrs, starts, entries, points, t, (long long)m, out);
     PCFE_LAUNCH_CHECK();
     return PCFE_OK;
   }
