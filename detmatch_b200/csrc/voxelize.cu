@@ -467,7 +467,8 @@ extern "C" int pcfe_debug_axis_sweep(float lo, float vs, float hi, uint64_t* out
 // kernels instead of the record path), "hv_expand_variant" (1: un-pipelined expansion kernels),
 // "hv_expand_prefetch" (frames of L2 prefetch distance), "hv_no_fast_div", "hv_pdl",
 // "hv_expand_ctas" (persistent expansion), "hv_expand_vpw", "mega_*" (pipeline offsets / ring /
-// CTAs / stage statistics).  Returns PCFE_ERR_SHAPE for an unknown name.
+// CTAs / stage statistics), "pib_grid" (0: brute-force first-hit point-in-box assignment).  Returns
+// PCFE_ERR_SHAPE for an unknown name.
 extern "C" int pcfe_debug_set(const char* name, int value) {
   if (!name) return PCFE_ERR_NULL;
   if (!strcmp(name, "hv_path")) g_opt_hv_path = value;

@@ -64,7 +64,8 @@ int pcfe_profile_report(char* buf, size_t cap);
  * "hv_path" 0 auto | 1 global-memory path | 2 shared-memory bucket path | 3 persistent pipeline;
  * "hv_force_overflow" 1 = every frame also takes the overflow fallback; "hv_bucket_avg" = target
  * points per bucket; "hv_bucket_variant", "hv_expand_variant", "hv_pdl", ... select kernel
- * variants (see pcfe_debug_set in csrc/voxelize.cu). */
+ * variants (see pcfe_debug_set in csrc/voxelize.cu); "pib_grid" 0 = first-hit point-in-box
+ * assignment by brute force over all boxes instead of the per-frame box grid. */
 int pcfe_debug_set(const char* name, int value);
 
 /* grid[j] = (int)roundf((range[3+j]-range[j])/voxel_size[j]) in float32, x y z order.
