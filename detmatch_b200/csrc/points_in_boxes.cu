@@ -354,9 +354,13 @@ pib_point_kernel(const PBox* __restrict__ pboxes, const RBox* __restrict__ rboxe
   __syncthreads();
   int first = -1;
   uint32_t parity = 0;
-  for (int t0 = 0; t0 < t; t0 += kPointChunk) {
-    const int cnt = min(kPointChunk, t - t0);
-    if (t0 > 0) __syncthreads();  // everyone is done with the previous chunk
+  // box-major layout: gridDim.z slices of the boxes (a single frame of points alone does not fill
+  // the GPU); the first-hit layout needs all boxes in order and runs with gridDim.z == 1
+  const int per_z = BOXMAJOR ? (t + (int)gridDim.z - 1) / (int)gridDim.z : t;
+  const int t_begin = BOXMAJOR ? (int)blockIdx.z * per_z : 0, t_end = min(t, t_begin + per_z);
+  for (int t0 = t_begin; t0 < t_end; t0 += kPointChunk) {
+    const int cnt = min(kPointChunk, t_end - t0);
+    if (t0 > t_begin) __syncthreads();  // everyone is done with the previous chunk
     stage_boxes(sboxes, srej, pboxes + (size_t)b * t + t0, rboxes + (size_t)b * t + t0, cnt, &bar, parity);
     parity ^= 1u;
     if (p < m) {
@@ -704,7 +708,10 @@ static int boxmajor_impl(const float* boxes, const float* points, int t, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   PBox* pb = (PBox*)ws;
   if ((rc = prepare(boxes, t, ws, st, pcdet, margin)) != PCFE_OK) return rc;
-  dim3 grid((unsigned)((n + 255) / 256), 1);
+  // enough CTAs for ~8 per SM: slices of at least 32 boxes
+  const long long tiles = (n + 255) / 256;
+  const int zs = (int)std::max<long long>(1, std::min<long long>((t + 31) / 32, (148 * 8 + tiles - 1) / tiles));
+  dim3 grid((unsigned)tiles, 1, (unsigned)zs);
   pib_point_kernel<true><<<grid, 256, 0, st>>>(pb, rbox_base(ws, t), points, t, (long long)n, out);
   PCFE_LAUNCH_CHECK();
   return PCFE_OK;
