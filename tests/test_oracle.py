@@ -196,3 +196,44 @@ def test_oracle_dynamic_scatter_vs_reference_test_construction():
             assert np.allclose(out, g["mean"], atol=1e-2, rtol=1e-5)
             assert np.abs(out - g["mean"]).max() < 1e-5
         assert cnt.sum() == (mp >= 0).sum() and (mp >= 0).sum() == (g["coors"] >= 0).all(axis=1).sum()
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(24))
+def test_oracle_vs_reference_random_configs(seed):
+    """Randomised grids, caps and feature counts: the C restatement against the reference's own
+    compiled CPU ops (hard and dynamic voxelization, point in box), bit for bit."""
+    import torch
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(0, 4000))
+    c = int(rng.integers(3, 7))
+    vs = [float(rng.choice([0.05, 0.1, 0.16, 0.2, 0.32, 0.5, 1.0])) for _ in range(3)]
+    lo = [float(rng.uniform(-60, 0)) for _ in range(3)]
+    ext = [vs[j] * int(rng.integers(1, 400 if j < 2 else 40)) for j in range(3)]
+    rg = lo + [lo[j] + ext[j] for j in range(3)]
+    p = int(rng.choice([1, 2, 3, 5, 8, 35]))
+    v = int(rng.integers(1, 600))
+    pts = rng.uniform(-1.0, 1.0, size=(n, c)).astype(np.float32)
+    for j in range(3):  # most points inside, some outside, some exactly on the faces
+        pts[:, j] = (lo[j] + (pts[:, j] * 0.6 + 0.5) * ext[j]).astype(np.float32)
+    if n > 10:
+        pts[0, 0], pts[1, 1], pts[2, 2] = rg[3], rg[1], rg[5]
+        pts[3, int(rng.integers(0, 3))] = np.nan
+        pts[4:8] = pts[8:9]  # duplicates
+    tp = torch.from_numpy(pts)
+    rv, rc, rn = ref.voxelization(tp, vs, rg, p, v)
+    ov, oc, on = oracle.hard_voxelize(pts, vs, rg, p, v)
+    assert_same_bits(oc, rc.numpy(), "coors")
+    assert_same_bits(on, rn.numpy(), "num")
+    assert_same_bits(ov, rv.numpy(), "voxels")
+    assert_same_bits(oracle.dynamic_voxelize(pts, vs, rg), ref.voxelization(tp, vs, rg, -1, -1).numpy(), "dynamic")
+    t = int(rng.integers(1, 40))
+    bxs = synth.random_boxes(t, 2000 + seed, rg).numpy()
+    if n:
+        k = min(t, n)
+        bxs[:k, 0:3] = pts[:k, 0:3]
+    exp = ref.points_in_boxes_cpu(torch.from_numpy(pts[:, :3].copy()), torch.from_numpy(bxs)).numpy()
+    assert_same_bits(oracle.points_in_boxes_cpu(pts[:, :3].copy(), bxs), exp, "pib")
+    if ref.pcdet_available():
+        exp = ref.pcdet_points_in_boxes_cpu(torch.from_numpy(pts[:, :3].copy()), torch.from_numpy(bxs)).numpy()
+        assert_same_bits(oracle.pcdet_points_in_boxes_cpu(pts[:, :3].copy(), bxs), exp, "pcdet pib")
