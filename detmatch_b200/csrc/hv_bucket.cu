@@ -31,8 +31,7 @@
 // The launches after hvb_zero are programmatic dependents of their predecessor.
 //
 // General path (any max_points / C / alignment): hvb_bin -> hvb_bucket_small<5|8> (P <= 8: chains +
-// register sort) or hvb_bucket_rank (any P: bitonic sort of (cell, point) keys) or hvb_bucket (the
-// first version: counts + atomicMin lists, kept as a cross-check) -> cells + list arena ->
+// register sort) or hvb_bucket_rank (any P: bitonic sort of (cell, point) keys) -> cells + list arena ->
 // hv_scan_flags -> hvb_order (cell -> voxel-id order) -> hvb_expand / _fixed / _pipe / _words.
 #include <algorithm>
 #include <mutex>
@@ -51,13 +50,14 @@ int hvg_launch_slow(const HvBatch& b, int frames, uint32_t* overflow, size_t ove
                     int stage, const int32_t* vn_all, int f_first);
 
 int g_opt_bucket_avg = 1024;  // target points per bucket (tunable through pcfe_debug_set)
-int g_opt_bucket_variant = 0;  // 1: general path with the first-version (atomicMin lists) bucket kernel
+int g_opt_bucket_variant = 0;  // 1: general kernels (cells + list arena) even where the record path applies
 int g_opt_no_fast_div = 0;      // 1: __fdiv_rn for every point (no hoisted reciprocal)
 int g_opt_expand_variant = 0;  // 1: un-pipelined fixed-P expansion kernel
 int g_opt_expand_prefetch = 1;  // frames of L2 prefetch distance in the expansion (0 = off)
 int g_opt_expand_vpw = 4;       // long-voxel expansion: voxels per warp
 int g_opt_pdl = 1;              // programmatic dependent launch between the record path's kernels
 int g_opt_expand_ctas = 0;      // > 0: persistent expansion with this many CTAs per SM
+int g_opt_cluster = 0;          // 1: record path with one thread-block cluster per frame (hv_cluster.cuh) -- measured slower, see profiles/r02_cluster_*
 
 namespace {
 
@@ -270,124 +270,6 @@ constexpr int kBucketThreads = PCFE_BUCKET_THREADS;
 #define PCFE_TABLE_DEN 1
 #endif
 constexpr int kMaxCap = 2048;  // entries per bucket (list offsets are packed into 16 bits)
-
-// dynamic shared memory (words): hkey[S] | hval[S] | eidx[cap] | lists[cap] | eslot[cap] (u16) |
-// slotlist[cap] (u16)
-__global__ void __launch_bounds__(kBucketThreads)
-hvb_bucket_kernel(const HvbWork w, const int pe /* max(max_points, 1) */) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ uint32_t warp_sums[33];
-  __shared__ uint32_t s_nclaimed, s_list_base, s_cell_base;
-
-  const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
-  uint32_t* ctl = w.ctl(f);
-  if (ctl[w.nb + kCtlOverflow]) return;  // set by the bin kernel: the frame takes the fallback
-  const int S = w.slots, cap = w.cap;
-  uint32_t* hkey = smem;
-  uint32_t* hval = hkey + S;   // pass 1: point count; after the scan: (list offset << 16) | list len
-  uint32_t* eidx = hval + S;
-  uint32_t* lists = eidx + cap;
-  uint16_t* eslot = reinterpret_cast<uint16_t*>(lists + cap);
-  uint16_t* slotlist = eslot + cap;
-
-  const int ne = (int)min(ctl[b], (uint32_t)cap);
-  if (ne == 0) return;
-  {  // hkey = kEmpty, hval = 0 (S is a multiple of 4; the two arrays are contiguous)
-    uint4* k4 = reinterpret_cast<uint4*>(hkey);
-    uint4* v4 = reinterpret_cast<uint4*>(hval);
-    for (int s = tid; s < S / 4; s += kBucketThreads) {
-      k4[s] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-      v4[s] = make_uint4(0u, 0u, 0u, 0u);
-    }
-  }
-  if (tid == 0) s_nclaimed = 0u;
-  __syncthreads();
-
-  // pass 1: find-or-claim the cell's slot, count its points
-  const uint2* __restrict__ ent = w.ent(f) + (size_t)b * cap;
-  const uint32_t smask = (uint32_t)S - 1u;
-  const int sshift = 32 - w.log2_nb - w.log2_slots;  // hash bits right below the bucket bits
-  for (int e = tid; e < ne; e += kBucketThreads) {
-    const uint2 en = __ldcs(&ent[e]);
-    uint32_t s = ((en.x * kGold) >> sshift) & smask;
-    while (true) {
-      uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&hkey[s]);
-      if (cur == en.x) break;
-      if (cur == kEmpty) {
-        cur = atomicCAS(&hkey[s], kEmpty, en.x);
-        if (cur == kEmpty) {
-          slotlist[atomicAdd(&s_nclaimed, 1u)] = (uint16_t)s;
-          break;
-        }
-        if (cur == en.x) break;
-      }
-      s = (s + 1u) & smask;
-    }
-    atomicAdd(&hval[s], 1u);
-    eslot[e] = (uint16_t)s;
-    eidx[e] = en.y;
-  }
-  __syncthreads();
-
-  // size the per-cell lists (min(count, P) entries each, in claim order) with a block scan; cell
-  // j of chunk q is handled by thread j - q * kBucketThreads, which also initialises its list
-  const int nv = (int)s_nclaimed;
-  uint32_t run_lists = 0;
-#pragma unroll 1
-  for (int j0 = 0; j0 < nv; j0 += kBucketThreads) {
-    const int j = j0 + tid;
-    uint32_t len = 0;
-    int s = 0;
-    if (j < nv) {
-      s = slotlist[j];
-      len = min(hval[s], (uint32_t)pe);
-    }
-    uint32_t tot;
-    const uint32_t off = run_lists + block_exscan(len, warp_sums, &tot);
-    if (j < nv) {
-      hval[s] = (off << 16) | len;
-      for (uint32_t t = 0; t < len; ++t) lists[off + t] = kEmpty;
-    }
-    run_lists += tot;
-    __syncthreads();  // warp_sums is reused by the next chunk
-  }
-  if (tid == 0) {
-    s_list_base = atomicAdd(&ctl[w.nb + kCtlList], run_lists);
-    s_cell_base = atomicAdd(&ctl[w.nb + kCtlCell], (uint32_t)nv);
-  }
-  __syncthreads();
-
-  // pass 2: sorted lists of the first P point indices of every cell
-  for (int e = tid; e < ne; e += kBucketThreads) {
-    const uint32_t hv = hval[eslot[e]];
-    sorted_insert<false>(lists + (hv >> 16), (int)(hv & 0xFFFFu), eidx[e]);
-  }
-  __syncthreads();
-
-  // emit: the CTA's lists are contiguous in shared memory in claim order, so the list arena gets
-  // one coalesced copy; every cell becomes one 16-byte record; first points are flagged
-  const uint32_t list_base = s_list_base, cell_base = s_cell_base;
-  if (list_base + run_lists > w.arena_cap || cell_base + (uint32_t)nv > w.arena_cap) {
-    if (tid == 0) ctl[w.nb + kCtlOverflow] = 1u;  // cannot happen: arenas hold one entry per point
-    return;
-  }
-  uint32_t* __restrict__ glst = w.lst(f) + list_base;
-  for (uint32_t i = tid; i < run_lists; i += kBucketThreads) glst[i] = lists[i];
-  Cell* __restrict__ cells = w.cells(f) + cell_base;
-  uint32_t* __restrict__ bitmask = w.bitmask(f);
-  for (int j = tid; j < nv; j += kBucketThreads) {
-    const int s = slotlist[j];
-    const uint32_t hv = hval[s];
-    const uint32_t off = hv >> 16;
-    Cell cl;
-    cl.key = hkey[s];
-    cl.len = hv & 0xFFFFu;  // >= 1: every claimed cell has a point and pe >= 1
-    cl.list_off = list_base + off;
-    cl.first = lists[off];  // lists are ascending: entry 0 is the cell's first point
-    cells[j] = cl;
-    atomicOr(&bitmask[cl.first >> 5], 1u << (cl.first & 31));
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // B': the same job for P <= PT (PT = 5 or 8): cells keep their points in a linked list built with
@@ -1621,6 +1503,54 @@ int launch_expand(dim3 grid, cudaStream_t st, const HvBatch& b, const HvbWork& w
   return PCFE_OK;
 }
 
+#include "hv_cluster.cuh"
+
+// One cluster of kCS CTAs per frame, as many clusters as the device keeps resident (each loops over
+// frames cluster, cluster + n, ...).  Returns PCFE_ERR_SHAPE when the device cannot run the cluster
+// shape at all: the caller then takes the multi-launch sequence.
+struct HvcDevice {
+  int tried = 0, max_clusters = 0;
+};
+HvcDevice g_hvc_dev[64][3];
+
+template <int CT>
+int hvc_launch(int device, cudaStream_t st, bool pdl, const HvBatch& b, const HvbWork& w, const GridParams& g,
+               int c, int fdiv, int max_voxels, int32_t* voxel_num, int frames) {
+  auto kern = hvc_group_kernel<CT>;
+  HvcDevice& d = g_hvc_dev[device][CT == 4 ? 0 : CT == 5 ? 1 : 2];
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kCT);
+  cfg.dynamicSmemBytes = sizeof(HvcSmem);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  if (!d.tried) {
+    d.tried = 1;
+    d.max_clusters = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HvcSmem)) == cudaSuccess &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cfg.gridDim = dim3(kCS * 8);
+      cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess) d.max_clusters = nc;
+    }
+    (void)cudaGetLastError();
+  }
+  if (d.max_clusters < 1) return PCFE_ERR_SHAPE;
+  const int ncl = std::min(d.max_clusters, frames);
+  cfg.gridDim = dim3((unsigned)(kCS * ncl));
+  cfg.numAttrs = pdl ? 2 : 1;
+  PCFE_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, b, w, g, c, fdiv, max_voxels, voxel_num, frames));
+  PCFE_LAUNCH_CHECK();
+  return PCFE_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1659,7 +1589,7 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   const size_t vmax = (size_t)std::min<int64_t>(max_voxels, std::max<int64_t>(n_max, 1));
   p->vcell_b = align256(std::max<size_t>(vmax, 1) * sizeof(Cell));
   p->word_b = align256((size_t)p->words * sizeof(uint32_t));
-  p->cnt_b = align256((size_t)(p->nb + 16) * sizeof(uint32_t)) + 256;  // also covers hv_mega.cu's ctl + ticket
+  p->cnt_b = align256((size_t)(p->nb + 16) * sizeof(uint32_t)) + 256;
   p->rec_b = align256((size_t)p->npad * 16 * PCFE_REC_STRIDE);
   p->firsts_b = align256(std::max<size_t>(vmax, 1) * sizeof(uint32_t));
   const size_t fast = std::max(p->ent_b + p->lst_b + p->cells_b + p->vcell_b, p->ent_b + p->rec_b + p->firsts_b);
@@ -1732,8 +1662,6 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
   w.nb = p.nb; w.log2_nb = p.log2_nb; w.cap = p.cap; w.slots = p.slots; w.log2_slots = p.log2_slots;
   w.arena_cap = (uint32_t)p.npad;
 
-  PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)p.smem_bucket));
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)p.smem_bucket));
   PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1768,7 +1696,20 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     if ((mean || pack) && !(max_points == 5 && (c == 4 || c == 5) && vec_ok && max_voxels < (1 << 24) && wn_max < 0xFFFFFF &&
                   g_opt_bucket_variant != 1))
       return PCFE_ERR_SHAPE;
-    {
+    // P == 5 with 16-byte aligned rows: the record-at-first-point variant (no order pass)
+    const bool use_rec = max_points == 5 && (c == 4 || c == 5) && vec_ok && max_voxels < (1 << 24) && wn_max < 0xFFFFFF &&
+                         g_opt_bucket_variant != 1;
+    // ... whose partition + grouping + voxel numbering is ONE cluster kernel when the frames fit
+    bool clustered = false;
+    if (use_rec && g_opt_cluster && wn_max <= kCMaxPoints && device >= 0 && device < 64) {
+      ProfScope ps("hvc_group", st);
+      const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
+      int rcc = c == 4 ? hvc_launch<4>(device, st, g_opt_pdl != 0, b, w, p.g, c, fdiv, max_voxels, voxel_num + f0, wv)
+                       : hvc_launch<5>(device, st, g_opt_pdl != 0, b, w, p.g, c, fdiv, max_voxels, voxel_num + f0, wv);
+      if (rcc == PCFE_OK) clustered = true;
+      else if (rcc != PCFE_ERR_SHAPE) return rcc;
+    }
+    if (!clustered) {
       ProfScope ps("memset_ctl", st);
       if (g_opt_pdl) {  // a kernel instead of a memset node, so that the bin kernel can be its
                         // programmatic dependent (zero_per is a multiple of 256 bytes)
@@ -1781,7 +1722,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       }
     }
     const int wnpad = std::max((int)((wn_max + 31) / 32 * 32), 32);
-    {
+    if (!clustered) {
       ProfScope ps("hvb_bin", st);
       const dim3 grid((unsigned)((wn_max + kBinTile - 1) / kBinTile), (unsigned)wv);
       const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
@@ -1790,12 +1731,9 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       else PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<0>, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c, fdiv));
       PCFE_LAUNCH_CHECK();
     }
-    // P == 5 with 16-byte aligned rows: the record-at-first-point variant (no order pass)
-    const bool use_rec = max_points == 5 && (c == 4 || c == 5) && vec_ok && max_voxels < (1 << 24) && wn_max < 0xFFFFFF &&
-                         g_opt_bucket_variant != 1;
     int rc = PCFE_OK;
     if (use_rec) {
-      {
+      if (!clustered) {
         ProfScope ps("hvb_bucket", st);
         const dim3 grid((unsigned)p.nb, (unsigned)wv);
         const size_t smem_rec = (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)p.cap * 2;
@@ -1805,7 +1743,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         PCFE_CUDA_TRY(launch_pdl(hvb_bucket_rec_kernel, grid, dim3(kBucketThreads), smem_rec, st, g_opt_pdl != 0, w, pe, spec));
         PCFE_LAUNCH_CHECK();
       }
-      {
+      if (!clustered) {
         ProfScope ps("hvb_scan_firsts", st);
         PCFE_CUDA_TRY(launch_pdl(hvb_scan_firsts_kernel, dim3((unsigned)((wnpad / 32 + kFirstsThreads - 1) / kFirstsThreads), (unsigned)wv),
                                  dim3(kFirstsThreads), 0, st, g_opt_pdl != 0, w, wnpad / 32, max_voxels, voxel_num + f0));
@@ -1850,13 +1788,11 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       const dim3 grid((unsigned)p.nb, (unsigned)wv);
       // chains are indexed with 16 bits (0xFFFF = end): cap <= kMaxCap = 2048 always fits
       const size_t smem_small = (size_t)(2 * p.slots + p.cap) * 4 + (size_t)(2 * p.cap) * 2;
-      if (pe <= 5 && g_opt_bucket_variant != 1)
+      if (pe <= 5)
         hvb_bucket_small_kernel<5><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
-      else if (pe <= 8 && g_opt_bucket_variant != 1)
+      else if (pe <= 8)
         hvb_bucket_small_kernel<8><<<grid, kBucketThreads, smem_small, st>>>(w, pe);
-      else if (g_opt_bucket_variant == 1 || wn_max >= (1 << 21)) {  // sort keys hold 21-bit point indices
-        hvb_bucket_kernel<<<grid, kBucketThreads, p.smem_bucket, st>>>(w, pe);
-      } else {
+      else {  // (sort keys hold 21-bit point indices: the plan admits at most 1024 x 2048 points)
         // table: the smallest power of two above cap (the plan's `slots` keeps the load under 0.8
         // even for a full bucket of distinct cells; here a full bucket is allowed to probe longer
         // in exchange for one more resident CTA)

@@ -413,20 +413,6 @@ int hvg_launch_slow(const HvBatch& b, int frames, uint32_t* overflow, size_t ove
   return PCFE_OK;
 }
 
-// hv_mega.cu: `ring` scratch regions shared by frames f, f + ring, ...
-int hvg_launch_slow_ring(const HvBatch& b, int frames, int ring, uint32_t* overflow,
-                         size_t overflow_stride, int force, char* scratch_base, size_t scratch_stride,
-                         const HvGlobalPlan& p, uint32_t* bitmask, size_t bitmask_stride,
-                         uint32_t* prefix, size_t prefix_stride, int c, int max_points,
-                         int max_voxels, int32_t* voxel_num, cudaStream_t st) {
-  ProfScope ps("hv_slow_fallback", st);
-  hvg_slow_frame_kernel<<<std::min(frames, ring), kSlowThreads, 0, st>>>(
-      b, overflow, overflow_stride, force, scratch_base, scratch_stride, p, bitmask, bitmask_stride,
-      prefix, prefix_stride, c, max_points, max_voxels, voxel_num, frames, ring, 0, 0, nullptr, 0);
-  PCFE_LAUNCH_CHECK();
-  return PCFE_OK;
-}
-
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------

@@ -49,12 +49,12 @@ extern int g_opt_bucket_avg;
 extern int g_opt_bucket_variant;
 extern int g_opt_expand_variant;
 extern int g_opt_expand_ctas;
+extern int g_opt_cluster;
 extern int g_opt_pdl;
 extern int g_opt_pib_grid;
 extern int g_opt_expand_vpw;
 extern int g_opt_no_fast_div;
 extern int g_opt_expand_prefetch;
-extern int g_opt_mega_d1, g_opt_mega_d2, g_opt_mega_d3, g_opt_mega_ring, g_opt_mega_ctas, g_opt_mega_stats;
 
 namespace {
 
@@ -279,17 +279,9 @@ static int hv_batch_impl(const pcfe_frame_t* frames, int num_frames, int c, cons
     wave = (int)std::min<size_t>(wave, fit);
   }
   if (mode) {  // mean epilogue / packed output: record path of the bucket launch sequence only
-    if (!ch.bucket || g_opt_hv_path == 3) return PCFE_ERR_SHAPE;
+    if (!ch.bucket) return PCFE_ERR_SHAPE;
     return hvb_run(frames, num_frames, c, ch.bp, max_points, max_voxels, voxel_num, workspace, wave, nbuf,
                    device, st, mode);
-  }
-  if (ch.bucket && g_opt_hv_path == 3) {
-    // experimental: the persistent frame pipeline (hv_mega.cu); measured slower than the launch
-    // sequence on B200 (0.73 vs 0.56 ms per C4 step: dependency waits + register-limited occupancy)
-    int ring = 0;
-    if (hvm_eligible(frames, num_frames, c, ch.bp, max_points, max_voxels, workspace_bytes, &ring))
-      return hvm_run(frames, num_frames, c, ch.bp, max_points, max_voxels, voxel_num, workspace, ring,
-                     device, st);
   }
   if (ch.bucket)
     return hvb_run(frames, num_frames, c, ch.bp, max_points, max_voxels, voxel_num, workspace, wave,
@@ -461,13 +453,12 @@ extern "C" int pcfe_debug_axis_sweep(float lo, float vs, float hi, uint64_t* out
 }
 
 // Test / tuning knobs (every setting computes the same, bit-exact results; they select code paths
-// and launch parameters): "hv_path" (0 auto, 1 global-memory path, 2 bucket path, 3 persistent
-// pipeline), "hv_force_overflow" (1: every frame also runs the overflow fallback), "hv_bucket_avg"
+// and launch parameters): "hv_path" (0 auto, 1 global-memory path, 2 bucket path),
+// "hv_cluster" (0: record path as a launch sequence instead of one cluster per frame), "hv_force_overflow" (1: every frame also runs the overflow fallback), "hv_bucket_avg"
 // (target points per bucket), "hv_wave" (frames per launch sequence), "hv_bucket_variant" (1: general
 // kernels instead of the record path), "hv_expand_variant" (1: un-pipelined expansion kernels),
 // "hv_expand_prefetch" (frames of L2 prefetch distance), "hv_no_fast_div", "hv_pdl",
-// "hv_expand_ctas" (persistent expansion), "hv_expand_vpw", "mega_*" (pipeline offsets / ring /
-// CTAs / stage statistics), "pib_grid" (0: brute-force first-hit point-in-box assignment).  Returns
+// "hv_expand_ctas" (persistent expansion), "hv_expand_vpw", "pib_grid" (0: brute-force first-hit point-in-box assignment).  Returns
 // PCFE_ERR_SHAPE for an unknown name.
 extern "C" int pcfe_debug_set(const char* name, int value) {
   if (!name) return PCFE_ERR_NULL;
@@ -483,12 +474,7 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_pdl")) g_opt_pdl = value;
   else if (!strcmp(name, "pib_grid")) g_opt_pib_grid = value;
   else if (!strcmp(name, "hv_expand_ctas")) g_opt_expand_ctas = value;
-  else if (!strcmp(name, "mega_d1")) g_opt_mega_d1 = value;
-  else if (!strcmp(name, "mega_d2")) g_opt_mega_d2 = value;
-  else if (!strcmp(name, "mega_d3")) g_opt_mega_d3 = value;
-  else if (!strcmp(name, "mega_ring")) g_opt_mega_ring = value;
-  else if (!strcmp(name, "mega_ctas")) g_opt_mega_ctas = value;
-  else if (!strcmp(name, "mega_stats")) g_opt_mega_stats = value;
+  else if (!strcmp(name, "hv_cluster")) g_opt_cluster = value;
   else return PCFE_ERR_SHAPE;
   return PCFE_OK;
 }

@@ -13,9 +13,10 @@ from tests.helpers import assert_same_bits
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["record", "fallback", "general", "global", "waves"])
+@pytest.fixture(params=["record", "cluster", "fallback", "general", "global", "waves"])
 def pack_mode(request):
-    """record: packed rows from the expansion kernel; fallback: every frame through the two-stage
+    """record: packed rows from the expansion kernel; cluster: the same with the frame's partition +
+    grouping done by one thread-block cluster (hv_cluster.cuh); fallback: every frame through the two-stage
     overflow fallback; general / global: paths without packed output (the wrapper concatenates);
     waves: two frames per launch sequence, so offsets cross waves."""
     mode = request.param
@@ -23,9 +24,11 @@ def pack_mode(request):
     _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "general" else 0)
     _cabi.debug_set("hv_wave", 2 if mode == "waves" else 0)
+    _cabi.debug_set("hv_cluster", 1 if mode == "cluster" else 0)
     yield mode
     for k in ("hv_path", "hv_force_overflow", "hv_bucket_variant", "hv_wave"):
         _cabi.debug_set(k, 0)
+    _cabi.debug_set("hv_cluster", 0)
 
 
 def _reference_flow(frames, vs, rg, P, V, mean):

@@ -61,18 +61,21 @@ def test_standalone_device_side_row_limit_and_empty():
     assert e.shape == (0, 4)
 
 
-@pytest.fixture(params=["record", "fallback", "general", "global"])
+@pytest.fixture(params=["record", "cluster", "fallback", "general", "global"])
 def mean_mode(request):
-    """record: the fused epilogue of the expansion kernel; fallback: every frame forced through the
+    """record: the fused epilogue of the expansion kernel; cluster: the same with the frame's partition +
+    grouping done by one thread-block cluster (hv_cluster.cuh); fallback: every frame forced through the
     overflow fallback (its own mean epilogue); general / global: paths without the epilogue, where
     the wrapper runs voxelization + the stand-alone kernel."""
     mode = request.param
     _cabi.debug_set("hv_path", 1 if mode == "global" else 0)
     _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "general" else 0)
+    _cabi.debug_set("hv_cluster", 1 if mode == "cluster" else 0)
     yield mode
     for k in ("hv_path", "hv_force_overflow", "hv_bucket_variant"):
         _cabi.debug_set(k, 0)
+    _cabi.debug_set("hv_cluster", 0)
 
 
 @pytest.mark.parametrize("cfg_name,ci,cap", [("C4", 4, None), ("C1", 1, None), ("C4", 4, 3000), ("C5", 5, 2000)])

@@ -15,20 +15,23 @@ pytestmark = pytest.mark.gpu
 KITTI = [0, -40, -3, 70.4, 40, 1]
 
 
-@pytest.fixture(autouse=True, params=["bucket", "bucket_general", "global", "fallback", "pipeline", "pipeline_fallback"])
+@pytest.fixture(autouse=True, params=["launches", "cluster", "bucket_general", "global", "fallback"])
 def hv_mode(request):
     """Every test runs against all hard-voxelize implementations behind the one entry point: the
-    shared-memory bucket path (default: register-sorted chains for P <= 8, atomicMin lists
-    otherwise), the bucket path with the general kernel forced, the global-memory path, the bucket
-    path with every frame forced through its overflow fallback, and the experimental persistent
-    frame pipeline (hv_mega.cu) with and without forced fallback."""
+    bucket path as a launch sequence (default; record kernels where P == 5 and C = 4 / 5), the record
+    path with one thread-block cluster per frame (hv_cluster.cuh: measured slower, kept as the
+    round-2 DSMEM experiment), the general bucket kernels (register-sorted chains for P <= 8, bitonic ranks
+    otherwise), the global-memory path, and the default path with every frame forced through its
+    overflow fallback."""
     from detmatch_b200 import _cabi
     mode = request.param
-    _cabi.debug_set("hv_path", {"global": 1, "pipeline": 3, "pipeline_fallback": 3}.get(mode, 0))
-    _cabi.debug_set("hv_force_overflow", 1 if mode in ("fallback", "pipeline_fallback") else 0)
+    _cabi.debug_set("hv_path", 1 if mode == "global" else 0)
+    _cabi.debug_set("hv_cluster", 1 if mode == "cluster" else 0)
+    _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "bucket_general" else 0)
     yield mode
     _cabi.debug_set("hv_path", 0)
+    _cabi.debug_set("hv_cluster", 0)
     _cabi.debug_set("hv_force_overflow", 0)
     _cabi.debug_set("hv_bucket_variant", 0)
 
@@ -353,7 +356,7 @@ def test_unaligned_buffers(c):
 def test_fast_division_equals_ieee_divide_exhaustive(lo, vs, hi, hv_mode):
     """The bin kernel divides with a hoisted reciprocal + three fused steps (ptxas's own fast path)
     instead of __fdiv_rn per point: checked for ALL 2^32 float32 values of a coordinate."""
-    if hv_mode != "bucket":
+    if hv_mode != "launches":
         pytest.skip("path-independent")
     from detmatch_b200 import _cabi
     out = torch.zeros(2, dtype=torch.int64, device="cuda")
