@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's headline metric: M points/s of Waymo-shape hard voxelization
-(config C4: 64 frames x 180 000 points x 5 features per GPU, voxel [0.1,0.1,0.15], range
+(config C4: 64 frames x 180 000 points x 5 features, voxel [0.1,0.1,0.15], range
 [-75.2,-75.2,-2,75.2,75.2,4], max_points 5, max_voxels 150 000) on N B200s, next to the HBM
 roofline and the reference's CPU op timed on the same host.
 
@@ -8,11 +8,14 @@ roofline and the reference's CPU op timed on the same host.
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N GPUs)
     python bench.py --impl reference --gpus N --steps K --warmup W    (reference CPU arm)
 
-A step = one pass of the hot path over one batch of 64 synthetic frames per GPU.  Frames shard
-across GPUs with no collective (weak scaling: every rank voxelizes its own 64 frames); the only
-communication is a barrier and a MAX over the ranks' device times.  Prints ONE JSON line.
+A step = one pass of the hot path over the config's batch of 64 synthetic frames.  Frames shard
+across GPUs with no collective: STRONG scaling (contiguous blocks of 64 / N frames
+per GPU; `--scaling weak` gives every rank its own 64 frames).  The only communication is a
+barrier and a MAX over the ranks' device times, on the host (gloo): no NCCL on this path.
+Prints ONE JSON line.
 """
 import argparse
+import glob
 import json
 import os
 import statistics
@@ -26,14 +29,33 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOAD = "C4"
-# DRAM traffic per 64-frame step from the committed ncu capture (profiles/r01_v14_ncu_summary.txt):
-# hvb_bin 288.7 MB + hvb_bucket_rec 174.3 MB + hvb_scan_firsts 3.1 MB + hvb_expand_rec 1042.4 MB
-NCU_TRAFFIC_BYTES_PER_STEP = {"C4": 1_510_900_000}
-NCU_EXPAND_TRAFFIC = {"C4": 1_045_500_000}
-NCU_PROFILE = "profiles/r01_v14_ncu_summary.txt"
 KEPT_POINTS_PER_FRAME = {"C4": 156_000}  # points surviving the max_points cap (oracle, seed 4000)
 METRIC = "hard_voxelize_throughput"
 UNIT = "Mpoints/s"
+# ProfScope name of the library (pcfe_profile_report) -> kernel name in an ncu report
+SCOPE_TO_KERNEL = {"memset_ctl": "hvb_zero_kernel", "hvb_bin": "hvb_bin_kernel", "hvb_bucket": "hvb_bucket_rec_kernel",
+                   "hvb_scan_firsts": "hvb_scan_firsts_kernel", "hvb_expand": "hvb_expand_rec_kernel",
+                   "hv_slow_fallback": "hvg_slow_frame_kernel", "hvc_group": "hvc_group_kernel"}
+
+
+def ncu_traffic(workload, scopes):
+    """DRAM bytes per step from the newest committed ncu capture of this workload
+    (profiles/*_traffic_<workload>.json, written by tests/native/ncu_traffic.py from an
+    `ncu --set full` report).  Returns (bytes or None, per-kernel dict, source): None when the
+    capture's kernel list does not cover the kernels this run launched -- a stale capture must not
+    pass for a measurement."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_traffic_{workload}.json")))
+    if not files:
+        return None, {}, "no profiles/*_traffic_%s.json" % workload
+    d = json.load(open(files[-1]))
+    per = d.get("kernels", {})
+    missing = [sc for sc in scopes if SCOPE_TO_KERNEL.get(sc) not in per and sc not in ("hv_slow_fallback", "memset_ctl")]
+    src = os.path.relpath(files[-1], ROOT) + " <- " + d.get("source", "?")
+    if missing:
+        return None, per, src + " (STALE: no capture of " + ", ".join(missing) + ")"
+    tot = sum(v["dram_read"] + v["dram_write"] for k, v in per.items()
+              if k in [SCOPE_TO_KERNEL.get(sc) for sc in scopes])
+    return int(tot), per, src
 
 
 def parse_args():
@@ -42,7 +64,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the config's 64)")
+    ap.add_argument("--frames", type=int, default=0, help="frames per step over all GPUs (default: the config's 64)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the step's frames are split over the GPUs (default); weak: every GPU gets all of them")
     ap.add_argument("--workload", default=WORKLOAD, choices=["C1", "C4", "C5"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-chunk", type=int, default=8, help="frames per pipelined chunk of the e2e measurement")
@@ -55,6 +79,8 @@ def parse_args():
     ap.add_argument("--debug", action="append", default=[], metavar="NAME=VALUE",
                     help="tuning: pcfe_debug_set knob (repeatable), e.g. --debug mega_d1=3")
     ap.add_argument("--ref-procs", type=int, default=0, help="reference arm: worker processes (default: all cores, <= 64)")
+    ap.add_argument("--sample-frames", type=int, default=0,
+                    help="reference arm: frames per step (default: the whole batch; the cpu_baseline leg of our line uses 32)")
     return ap.parse_args()
 
 
@@ -63,6 +89,8 @@ def workload_config(args):
     cfg = dict(synth.CONFIGS[args.workload])
     if args.frames > 0:
         cfg["frames"] = args.frames
+    elif args.workload == "C1":
+        cfg["frames"] = 16  # the config is a single frame; 16 is the batch the survey profiles it on
     cfg["index"] = int(args.workload[1])
     return cfg
 
@@ -125,8 +153,9 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU op (oracle/_ref) on the host cores
 # --------------------------------------------------------------------------------------------
-def _ref_worker(conn, cfg, frame_id, use_ref):
-    """One single-threaded worker: owns one frame, voxelizes it with the reference op on demand."""
+def _ref_worker(conn, cfg, frame_ids, use_ref):
+    """One single-threaded worker: owns a block of the step's frames, voxelizes them with the
+    reference op on demand."""
     import torch
     torch.set_num_threads(1)
     from detmatch_b200 import synth
@@ -136,23 +165,27 @@ def _ref_worker(conn, cfg, frame_id, use_ref):
     else:
         from oracle import oracle
         oracle.lib()
-    pts = synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(cfg["index"], frame_id), cfg["r_max"])
+    frames = [synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(cfg["index"], fid), cfg["r_max"]) for fid in frame_ids]
     conn.send("ready")
     while True:
         cmd = conn.recv()
         if cmd != "run":
             break
-        if use_ref:
-            # voxelize.py:46-58 call pattern, including the three new_zeros
-            v, c, n = ref.voxelization(pts, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], cfg["max_voxels"])
-        else:
-            v, c, n = oracle.hard_voxelize(pts.numpy(), cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], cfg["max_voxels"])
-        conn.send(int(n.shape[0]))
+        m = 0
+        for pts in frames:
+            if use_ref:
+                # voxelize.py:46-58 call pattern, including the three new_zeros
+                v, c, n = ref.voxelization(pts, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], cfg["max_voxels"])
+            else:
+                v, c, n = oracle.hard_voxelize(pts.numpy(), cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], cfg["max_voxels"])
+            m += int(n.shape[0])
+        conn.send(m)
 
 
-def run_reference(args, quiet=False):
-    """Times the reference's CPU hard_voxelize on this host: one single-threaded worker process
-    per core, one frame per worker per step (a bounded sample of the workload)."""
+def run_reference(args, quiet=False, sample_frames=0):
+    """Times the reference's CPU hard_voxelize on this host: one single-threaded worker process per
+    core; a step is the SAME batch our arm voxelizes (all of the config's frames, split evenly over
+    the workers) unless `sample_frames` bounds it (the cpu_baseline leg of our own line)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
@@ -160,17 +193,21 @@ def run_reference(args, quiet=False):
     cfg = workload_config(args)
     from oracle import ref
     use_ref = ref.available()
+    if use_ref:
+        ref.module()  # the parent loads oracle/_ref too: the workers are forked children
     try:
         cores = len(os.sched_getaffinity(0))
     except Exception:
         cores = os.cpu_count() or 1
+    frames_total = sample_frames if sample_frames > 0 else cfg["frames"]
     procs = args.ref_procs if args.ref_procs > 0 else min(cores, 64)
-    procs = max(1, min(procs, cfg["frames"] * max(args.gpus, 1)))
+    procs = max(1, min(procs, frames_total))
+    blocks = [list(range(k * frames_total // procs, (k + 1) * frames_total // procs)) for k in range(procs)]
     ctx = mp.get_context("fork")
     workers = []
     for k in range(procs):
         parent, child = ctx.Pipe()
-        p = ctx.Process(target=_ref_worker, args=(child, cfg, k, use_ref), daemon=True)
+        p = ctx.Process(target=_ref_worker, args=(child, cfg, blocks[k], use_ref), daemon=True)
         p.start()
         workers.append((p, parent))
     for _, conn in workers:
@@ -193,18 +230,19 @@ def run_reference(args, quiet=False):
         conn.send("stop")
         p.join(timeout=5)
     t_step = sum(times) / len(times)
-    pts_per_step = procs * cfg["n"]
+    pts_per_step = frames_total * cfg["n"]
     value = pts_per_step / t_step / 1e6
     kind = "reference" if use_ref else "port"
-    sample = (f"{procs} frames/step ({cfg['n']} pts x {cfg['c']}), one single-threaded worker process per core, "
-              f"{len(times)} steps; {'oracle/_ref = reference voxelization_cpu.cpp compiled in place' if use_ref else 'oracle C port'}")
+    sample = (f"{frames_total} frames/step ({cfg['n']} pts x {cfg['c']}) over {procs} single-threaded worker processes "
+              f"(one per core), {len(times)} steps; "
+              f"{'oracle/_ref = reference voxelization_cpu.cpp compiled in place' if use_ref else 'oracle C port'}")
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": max(args.warmup, 1), "ms_per_step": round(t_step * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": _config_dict(cfg, args, frames_per_step=procs),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": _config_dict(cfg, args, frames_per_step=frames_total),
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": procs, "kind": kind, "sample": sample,
-                         "host_cores_visible": cores, "mean_voxels_per_frame": round(sum(ms) / len(ms), 1)},
+                         "host_cores_visible": cores, "mean_voxels_per_frame": round(sum(ms) / frames_total, 1)},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -215,30 +253,34 @@ def run_reference(args, quiet=False):
 
 def _config_dict(cfg, args, frames_per_step):
     return {"workload": f"{args.workload}: Waymo-shape hard voxelization" if args.workload == "C4" else args.workload,
-            "frames_per_gpu_per_step": frames_per_step, "points_per_frame": cfg["n"], "features": cfg["c"],
+            "frames_per_step": frames_per_step, "points_per_frame": cfg["n"], "features": cfg["c"],
             "voxel_size": cfg["voxel_size"], "point_cloud_range": cfg["point_cloud_range"],
             "max_num_points": cfg["max_num_points"], "max_voxels": cfg["max_voxels"],
             "generator": "LiDAR-like (SURVEY 8(d)), seed = 1000*config + frame",
-            "l2": "inputs+outputs per step (~0.94 GB) exceed the 126 MB L2; no explicit flush",
-            "sharding": "frames, no collective"}
+            "l2": "inputs+outputs per step (~0.94 GB at 64 C4 frames) exceed the 126 MB L2; no explicit flush",
+            "sharding": "frames split over the GPUs in contiguous blocks, no collective"}
 
 
 # --------------------------------------------------------------------------------------------
-# multi-GPU plumbing (no data-path collective: frames shard, only times are reduced)
+# multi-GPU plumbing (no data-path collective: frames shard, only times are reduced, on the host)
 # --------------------------------------------------------------------------------------------
+def frame_block(total_frames, rank, world):
+    """Global frame ids owned by `rank` under strong scaling: contiguous blocks, disjoint, balanced."""
+    return list(range(rank * total_frames // world, (rank + 1) * total_frames // world))
+
+
 def frame_seeds(cfg_index, rank, frames_per_rank):
-    """Global frame ids owned by `rank`: a contiguous block, disjoint across ranks."""
+    """Weak scaling: every rank its own `frames_per_rank` frames (contiguous, disjoint across ranks)."""
     return [rank * frames_per_rank + k for k in range(frames_per_rank)]
 
 
 def max_over_ranks(value, device=None):
-    """MAX of a python float over all ranks (identity when not distributed).  Works with nccl
-    (device tensor) and gloo (CPU tensor)."""
+    """MAX of a python float over all ranks (identity when not distributed), reduced on the host."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return float(value)
-    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    t = torch.tensor([float(value)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
@@ -260,10 +302,19 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # host-side process group: the path has no exchange step, only the ranks' times are reduced
+        dist.init_process_group("gloo")
     cfg = workload_config(args)
-    F, N, C = cfg["frames"], cfg["n"], cfg["c"]
+    N, C = cfg["n"], cfg["c"]
     P, V = cfg["max_num_points"], cfg["max_voxels"]
+    F_total = cfg["frames"]
+    if args.scaling == "strong":
+        frame_ids = frame_block(F_total, rank, world)
+        total_frames = F_total
+    else:
+        frame_ids = frame_seeds(cfg["index"], rank, F_total)
+        total_frames = F_total * world
+    F = len(frame_ids)
     if args.hv_wave:
         _cabi.debug_set("hv_wave", args.hv_wave)
     if args.hv_bucket_avg:
@@ -272,9 +323,8 @@ def run_ours(args):
         name, _, val = kv.partition("=")
         _cabi.debug_set(name, int(val))
 
-    # synthetic frames, generated on the host; each rank has its own 64 frames
-    host = [synth.lidar_frame(N, C, synth.seed_for(cfg["index"], fid), cfg["r_max"]).pin_memory()
-            for fid in frame_seeds(cfg["index"], rank, F)]
+    # synthetic frames, generated on the host
+    host = [synth.lidar_frame(N, C, synth.seed_for(cfg["index"], fid), cfg["r_max"]).pin_memory() for fid in frame_ids]
     pts = [h.to(dev, non_blocking=True) for h in host]
     torch.cuda.synchronize(dev)
     plan = HardVoxelizeBatchPlan([N] * F, C, cfg["voxel_size"], cfg["point_cloud_range"], P, V, dev,
@@ -315,8 +365,8 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         clocks = sampler.stop()
         clocks["note"] = "timed region < sampling period; sampled during an identical untimed loop right after"
-    ms_step = max_over_ranks(ms_total, dev) / args.steps
-    total_points = world * F * N
+    ms_step = max_over_ranks(ms_total) / args.steps
+    total_points = total_frames * N
     value = total_points / (ms_step * 1e-3) / 1e6
 
     # ---- per-kernel attribution (separate, untimed pass) -------------------------------------
@@ -332,10 +382,15 @@ def run_ours(args):
         kernels = {k: {"ms_per_step": round(v[0] / 3, 4), "launches_per_step": v[1] // 3, "share": round(v[0] / tot, 3)}
                    for k, v in rep.items()}
 
-    # ---- end to end through the public API with HOST buffers --------------------------------
+    # ---- end to end through the package's host-buffer API -----------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, cfg, plan, host, pts, dev, world, barrier)
+        e2e = run_e2e(args, cfg, host, dev, total_frames, barrier)
+
+    # ---- the other scaling mode, a few steps (extra key, not the headline) -------------------
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_extras:
+        weak = run_weak_extra(cfg, rank, world, dev, barrier)
 
     if rank != 0:
         if world > 1:
@@ -348,15 +403,18 @@ def run_ours(args):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    algo = algorithmic_bytes(N, C, P, m_list)  # one rank's step
+    algo = algorithmic_bytes(N, C, P, m_list)  # this rank's share of the step
     achieved = algo / (ms_step * 1e-3) / 1e9
+    traffic, per_kernel, traffic_src = ncu_traffic(args.workload, list(kernels or {}))
+    if traffic is not None and F != 64:
+        traffic = int(traffic * F / 64)  # the capture is a 64-frame step
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_BYTES_PER_STEP.get(args.workload),
+                "frac": round(achieved / peak, 4), "traffic": traffic,
                 "kernel": "hard-voxelize launch sequence per GPU (" + ", ".join(k for k in (kernels or {})) + "); "
-                          "achieved = algorithmic bytes of the step / CUDA-event step time",
+                          "achieved = algorithmic bytes of the rank's step / CUDA-event step time",
                 "algorithmic_bytes_per_step": algo, "peak_source": peak_src + " (of measured)",
-                "traffic_source": "sum of dram__bytes_read+write over the step's kernels, ncu --set full, " + NCU_PROFILE,
-                "mean_voxels_per_frame": round(sum(m_list) / len(m_list), 1)}
+                "traffic_source": "sum of dram__bytes_read+write over the step's kernels, ncu --set full: " + traffic_src,
+                "mean_voxels_per_frame": round(sum(m_list) / max(len(m_list), 1), 1)}
     if kernels and "hvb_expand" in kernels:
         # dominant kernel (the expansion): writes every returned element once, reads the kept rows and
         # one first-point index per voxel (the records of multi-point voxels are not counted)
@@ -364,15 +422,19 @@ def run_ours(args):
         m_tot = sum(m_list)
         k_bytes = m_tot * (P * C * 4 + 16) + m_tot * 4 + (kept * F * C * 4 if kept else 0)
         k_ms = kernels["hvb_expand"]["ms_per_step"]
+        kt = per_kernel.get("hvb_expand_rec_kernel")
         roofline["dominant_kernel"] = {"name": "hvb_expand", "ms_per_launch": k_ms,
                                        "algorithmic_bytes_per_launch": k_bytes,
                                        "achieved": round(k_bytes / (k_ms * 1e-3) / 1e9, 1),
                                        "frac": round(k_bytes / (k_ms * 1e-3) / 1e9 / peak, 4),
-                                       "traffic": NCU_EXPAND_TRAFFIC.get(args.workload)}
+                                       "traffic": int((kt["dram_read"] + kt["dram_write"]) * F / 64) if kt else None}
 
     fused = None
     if not args.no_extras and P == 5 and C in (4, 5):
         fused = run_fused_extras(cfg, pts, plan, dev)
+    latency = None
+    if not args.no_extras and world == 1:
+        latency = run_latency_extras(cfg, pts, dev)
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -380,15 +442,79 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
-        "config": _config_dict(cfg, args, frames_per_step=F),
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "ours",
+        "config": dict(_config_dict(cfg, args, frames_per_step=total_frames), frames_per_gpu_per_step=F),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "kernels": kernels, "fused": fused,
+        "clocks": clocks, "kernels": kernels, "fused": fused, "latency": latency, "weak": weak,
+        "comm": "gloo (host): barrier + MAX of the ranks' device times; no data-path collective, no NCCL" if world > 1 else None,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_weak_extra(cfg, rank, world, dev, barrier, steps=20):
+    """Weak-scaling figure next to the strong-scaling headline: every rank voxelizes its own full
+    batch (the config's 64 frames).  Device time, MAX over ranks."""
+    import torch
+    from detmatch_b200 import synth
+    from detmatch_b200.ops.voxel import HardVoxelizeBatchPlan
+    F, N, C = cfg["frames"], cfg["n"], cfg["c"]
+    pts = [synth.lidar_frame(N, C, synth.seed_for(cfg["index"], fid), cfg["r_max"]).to(dev)
+           for fid in frame_seeds(cfg["index"], rank, F)]
+    plan = HardVoxelizeBatchPlan([N] * F, C, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"],
+                                 cfg["max_voxels"], dev).bind(pts)
+    for _ in range(5):
+        plan.run()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        plan.run()
+    b.record()
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b)) / steps
+    return {"scaling": "weak", "frames_per_gpu_per_step": F, "ms_per_step": round(ms, 4),
+            "value": round(world * F * N / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "steps": steps}
+
+
+def run_latency_extras(cfg, pts, dev, reps=100):
+    """Not the headline metric: what a detector that keeps the reference's call pattern sees.
+    batch_B: device time per step of the pre-allocated batched call at B frames (DetMatch trains with
+    B = 4 labeled + unlabeled frames per GPU, configs/detmatch/001/detmatch/split_0.py:108-112);
+    forward_wall_us: host wall time of the unchanged per-frame API, Voxelization.forward (output
+    allocation + launch sequence + the voxel_num read-back that sizes the returned views)."""
+    import torch
+    from detmatch_b200.ops import Voxelization
+    from detmatch_b200.ops.voxel import HardVoxelizeBatchPlan
+    N, C, P, V = cfg["n"], cfg["c"], cfg["max_num_points"], cfg["max_voxels"]
+    out = {}
+    for B in (1, 4, 8):
+        if B > len(pts):
+            continue
+        plan = HardVoxelizeBatchPlan([N] * B, C, cfg["voxel_size"], cfg["point_cloud_range"], P, V, dev).bind(pts[:B])
+        for _ in range(5):
+            plan.run()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            plan.run()
+        b.record()
+        torch.cuda.synchronize(dev)
+        out[f"batch_{B}_ms_per_step"] = round(a.elapsed_time(b) / reps, 4)
+        del plan
+    layer = Voxelization(cfg["voxel_size"], cfg["point_cloud_range"], P, V).eval()
+    for _ in range(5):
+        layer(pts[0])
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        layer(pts[0])
+    torch.cuda.synchronize(dev)
+    out["forward_wall_us"] = round((time.perf_counter() - t0) / reps * 1e6, 1)
+    return out
 
 
 def run_fused_extras(cfg, pts, plan, dev, reps=50):
@@ -436,102 +562,40 @@ def run_fused_extras(cfg, pts, plan, dev, reps=50):
     return out
 
 
-def run_e2e(args, cfg, plan, host, pts, dev, world, barrier):
-    """Same metric through the public batched call with HOST buffers: every step copies the 64
-    frames from pinned host memory to the device, voxelizes, reads voxel_num back and brings the
-    returned rows of every frame -- voxels[:M], coors[:M], num_points[:M], concatenated over the
-    frames exactly as the reference's voxelize() loop returns them (voxelnet.py:60-67) -- into
-    pinned host memory.
-
-    The batch is cut into chunks of 8 frames on three streams (H2D, compute, D2H) so that the
-    upload of chunk i+1, the kernels of chunk i and the download of chunk i-1 overlap; the
-    device-to-host size of a chunk is only known once its voxel_num has reached the host, which
-    is the one host synchronisation per chunk.  The rows of a chunk are concatenated on the device
-    (torch.cat into a staging buffer) and leave with three copies per chunk instead of three per
-    frame: the copy engine no longer idles between 192 small transfers."""
+def run_e2e(args, cfg, host, dev, total_frames, barrier):
+    """Same metric through the package's public host-buffer call (detmatch_b200.ops.HostVoxelizePipeline,
+    the pre-allocated form of voxelize_batch_host): every step copies this rank's frames from pinned host
+    memory to the device, voxelizes them with the packed C-ABI call and brings the returned rows --
+    voxels[:M], num_points[:M], (batch, z, y, x) coordinates, concatenated over the frames exactly as the
+    reference's voxelize() loop returns them (voxelnet.py:60-67) -- into pinned host memory.  Wall
+    clock around the calls, MAX over ranks."""
     import torch
-    from detmatch_b200.ops.voxel import HardVoxelizeBatchPlan
-    F, N, C = cfg["frames"], cfg["n"], cfg["c"]
-    P, V = cfg["max_num_points"], cfg["max_voxels"]
-    CH = args.e2e_chunk if F % args.e2e_chunk == 0 else F
-    chunks = [list(range(i, i + CH)) for i in range(0, F, CH)]
-    plans = [HardVoxelizeBatchPlan([N] * CH, C, cfg["voxel_size"], cfg["point_cloud_range"], P, V, dev).bind(
-        [pts[k] for k in ch]) for ch in chunks]
-    cap_rows = F * min(V, N)
-    out_vox = torch.empty((cap_rows, P, C), dtype=torch.float32).pin_memory()
-    out_coors = torch.empty((cap_rows, 3), dtype=torch.int32).pin_memory()
-    out_num = torch.empty((cap_rows,), dtype=torch.int32).pin_memory()
-    stage = [(torch.empty((CH * min(V, N), P, C), dtype=torch.float32, device=dev),
-              torch.empty((CH * min(V, N), 3), dtype=torch.int32, device=dev),
-              torch.empty((CH * min(V, N),), dtype=torch.int32, device=dev)) for _ in range(2)]
-    cnt_host = [torch.empty((CH,), dtype=torch.int32).pin_memory() for _ in chunks]
-    s_in, s_comp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    h2d = F * N * C * 4
-    offsets = []
-
-    def step():
-        ev_c = []
-        for i, ch in enumerate(chunks):
-            with torch.cuda.stream(s_in):
-                for k in ch:
-                    pts[k].copy_(host[k], non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(s_in)
-            with torch.cuda.stream(s_comp):
-                s_comp.wait_event(ev_in)
-                plans[i].run()
-                cnt_host[i].copy_(plans[i].voxel_num, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(s_comp)
-                ev_c.append(ev)
-        d2h = 0
-        row0 = 0
-        offsets.clear()
-        for i, ch in enumerate(chunks):
-            ev_c[i].synchronize()  # the caller needs M to size what it reads back
-            counts = cnt_host[i].tolist()
-            tot = sum(counts)
-            d2h += len(ch) * 4 + tot * (P * C * 4 + 16)
-            sv, sc, sn = stage[i & 1]
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_c[i])
-                torch.cat([plans[i].voxels[j, :m] for j, m in enumerate(counts)], dim=0, out=sv[:tot])
-                torch.cat([plans[i].coors[j, :m] for j, m in enumerate(counts)], dim=0, out=sc[:tot])
-                torch.cat([plans[i].num_points[j, :m] for j, m in enumerate(counts)], dim=0, out=sn[:tot])
-                out_vox[row0:row0 + tot].copy_(sv[:tot], non_blocking=True)
-                out_coors[row0:row0 + tot].copy_(sc[:tot], non_blocking=True)
-                out_num[row0:row0 + tot].copy_(sn[:tot], non_blocking=True)
-            offsets.append((row0, counts))
-            row0 += tot
-        s_out.synchronize()
-        return d2h
-
+    from detmatch_b200.ops import HostVoxelizePipeline
+    N, C = cfg["n"], cfg["c"]
+    pipe = HostVoxelizePipeline([N] * len(host), C, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"],
+                                cfg["max_voxels"], device=dev, chunk=args.e2e_chunk)
     torch.cuda.synchronize(dev)
-    step()
+    pipe.run(host)
     barrier()
     t0 = time.perf_counter()
-    d2h = 0
     for _ in range(args.e2e_steps):
-        d2h = step()
+        v, n, c = pipe.run(host)
     torch.cuda.synchronize(dev)
-    dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps, dev)
-    # the downloaded rows are the device results (spot check, outside the timed region)
-    row0, counts = offsets[-1]
-    last0 = row0 + sum(counts[:-1])
-    m = counts[-1]
-    assert torch.equal(out_vox[last0:last0 + m], plans[-1].voxels[CH - 1, :m].cpu())
-    assert torch.equal(out_coors[last0:last0 + m], plans[-1].coors[CH - 1, :m].cpu())
-    return {"value": round(world * F * N / dt / 1e6, 1), "unit": UNIT, "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": int(d2h), "ms_per_step": round(dt * 1e3, 3), "steps": args.e2e_steps,
-            "api": "HardVoxelizeBatchPlan.run (pcfe_hard_voxelize_batch_f32), pinned host in/out buffers, "
-                   f"{CH}-frame chunks pipelined on H2D / compute / D2H streams, rows concatenated over frames "
-                   "on the device (as the reference's voxelize() returns them) before the read-back"}
+    dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+    assert v.size(0) == sum(pipe.counts) and n.size(0) == v.size(0) and c.size(0) == v.size(0)
+    return {"value": round(total_frames * N / dt / 1e6, 1), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
+            "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": round(dt * 1e3, 3), "steps": args.e2e_steps,
+            "rows": int(v.size(0)),
+            "api": "detmatch_b200.ops.HostVoxelizePipeline.run (voxelize_batch_host): pinned host frames in, "
+                   f"concatenated (voxels, num_points, coors_batch) out in pinned host memory; {args.e2e_chunk}-frame chunks "
+                   "pipelined on H2D / compute / D2H streams, pcfe_hard_voxelize_packed_batch_f32 per chunk; bytes are "
+                   "this rank's per step"}
 
 
 def cpu_baseline_subprocess(args):
     """The reference arm on a bounded sample, in a fresh process (fork-safe: no CUDA there)."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
-           "--workload", args.workload, "--gpus", "1"]
+           "--workload", args.workload, "--gpus", "1", "--sample-frames", "32"]
     try:
         env = dict(os.environ)
         for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
@@ -548,7 +612,7 @@ def cpu_baseline_subprocess(args):
 def main():
     args = parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, sample_frames=args.sample_frames)
     else:
         run_ours(args)
 

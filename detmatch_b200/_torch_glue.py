@@ -1,4 +1,6 @@
 """torch-side plumbing shared by the op wrappers: device placement, current stream, scratch."""
+import threading
+
 import torch
 
 from . import _cabi
@@ -27,9 +29,11 @@ def stream_ptr(device):
 
 
 def workspace(device, nbytes):
-    """Scratch owned by torch's caching allocator, cached per (device, stream) and grown on
-    demand.  256-byte aligned (the caching allocator aligns to 512)."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    """Scratch owned by torch's caching allocator, cached per (device, stream, host thread) and
+    grown on demand.  256-byte aligned (the caching allocator aligns to 512).  The thread is part of
+    the key because ctypes releases the GIL during the native call: two Python threads enqueueing
+    multi-kernel sequences on the same stream must not share prepared-box / bitmap scratch."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

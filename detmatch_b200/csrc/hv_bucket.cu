@@ -54,7 +54,6 @@ int g_opt_bucket_variant = 0;  // 1: general kernels (cells + list arena) even w
 int g_opt_no_fast_div = 0;      // 1: __fdiv_rn for every point (no hoisted reciprocal)
 int g_opt_expand_variant = 0;  // 1: un-pipelined fixed-P expansion kernel
 int g_opt_expand_prefetch = 1;  // frames of L2 prefetch distance in the expansion (0 = off)
-int g_opt_expand_vpw = 4;       // long-voxel expansion: voxels per warp
 int g_opt_pdl = 1;              // programmatic dependent launch between the record path's kernels
 int g_opt_expand_ctas = 0;      // > 0: persistent expansion with this many CTAs per SM
 int g_opt_cluster = 0;          // 1: record path with one thread-block cluster per frame (hv_cluster.cuh) -- measured slower, see profiles/r02_cluster_*
@@ -577,38 +576,68 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
 // with block barriers -- 6 of the 55 stages for N = 1024.  All comparators point the same way: the
 // first stage of every merge pairs i with its mirror image inside the block (i ^ (kk - 1)), the
 // following ones pair i with i ^ d.
+// Only the in-register parts are unrolled; the merges across threads are ONE rolled loop over
+// (kk, d) whose shuffle masks and partners are run-time values.  (Fully unrolled, the kernel was 7800
+// instructions = 125 KB of code and 27 % of its stall samples were instruction fetches,
+// profiles/r02_c5_ncu_summary.txt.)
 template <int E>
-__device__ __forceinline__ void bitonic_sort_256(uint32_t (&v)[E], uint32_t* K, const int tid) {
-  constexpr int N = kBucketThreads * E;
+__device__ __forceinline__ void bitonic_local_sort(uint32_t (&v)[E]) {  // merges kk = 2 .. E inside the thread
 #pragma unroll
-  for (int kk = 2; kk <= N; kk <<= 1) {
+  for (int kk = 2; kk <= E; kk <<= 1) {
 #pragma unroll
     for (int d = kk >> 1; d > 0; d >>= 1) {
       const bool flip = d == (kk >> 1);
-      if (flip ? (kk <= E) : (d < E)) {  // both elements in this thread
 #pragma unroll
-        for (int r = 0; r < E; ++r) {
-          const int q = flip ? (r ^ (kk - 1)) : (r ^ d);
-          if (r < q) {
-            const uint32_t a = v[r], b = v[q];
-            v[r] = min(a, b);
-            v[q] = max(a, b);
-          }
+      for (int r = 0; r < E; ++r) {
+        const int q = flip ? (r ^ (kk - 1)) : (r ^ d);
+        if (r < q) {
+          const uint32_t a = v[r], b = v[q];
+          v[r] = min(a, b);
+          v[q] = max(a, b);
         }
-      } else if (flip ? (kk <= 32 * E) : (d < 32 * E)) {  // partner in another lane of this warp
-        const int lmask = flip ? (kk / E - 1) : (d / E);
-        const bool lower = flip ? !(tid & (kk / 2 / E)) : !(tid & (d / E));
+      }
+    }
+  }
+}
+template <int E>
+__device__ __forceinline__ void bitonic_local_merge(uint32_t (&v)[E]) {  // distances E / 2 .. 1 of a merge
+#pragma unroll
+  for (int d = E >> 1; d > 0; d >>= 1) {
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      const int q = r ^ d;
+      if (r < q) {
+        const uint32_t a = v[r], b = v[q];
+        v[r] = min(a, b);
+        v[q] = max(a, b);
+      }
+    }
+  }
+}
+template <int E>
+__device__ __forceinline__ void bitonic_sort_256(uint32_t (&v)[E], uint32_t* K, const int tid) {
+  constexpr int T = kBucketThreads;
+  bitonic_local_sort<E>(v);
+#pragma unroll 1
+  for (int tk = 2; tk <= T; tk <<= 1) {  // merge of blocks of tk threads (kk = tk E elements)
+#pragma unroll 1
+    for (int td = tk >> 1; td > 0; td >>= 1) {  // partner thread distance (d = td E)
+      const bool flip = td == (tk >> 1);
+      const int pmask = flip ? (tk - 1) : td;  // partner thread = tid ^ pmask
+      const bool lower = !(tid & td);
+      if (pmask < 32) {  // partner in another lane of this warp
         uint32_t o[E];
 #pragma unroll
-        for (int r = 0; r < E; ++r) o[r] = __shfl_xor_sync(0xFFFFFFFFu, v[flip ? E - 1 - r : r], lmask);
+        for (int r = 0; r < E; ++r) {
+          o[r] = __shfl_xor_sync(0xFFFFFFFFu, flip ? v[E - 1 - r] : v[r], pmask);
+        }
 #pragma unroll
         for (int r = 0; r < E; ++r) v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
       } else {  // partner in another warp: through shared memory
 #pragma unroll
         for (int r = 0; r < E; ++r) K[tid * E + r] = v[r];
         __syncthreads();
-        const int pt = flip ? (tid ^ (kk / E - 1)) : (tid ^ (d / E));
-        const bool lower = tid < pt;
+        const int pt = tid ^ pmask;
 #pragma unroll
         for (int r = 0; r < E; ++r) {
           const uint32_t o = K[pt * E + (flip ? E - 1 - r : r)];
@@ -617,6 +646,7 @@ __device__ __forceinline__ void bitonic_sort_256(uint32_t (&v)[E], uint32_t* K, 
         __syncthreads();
       }
     }
+    bitonic_local_merge<E>(v);
   }
 }
 
@@ -973,6 +1003,16 @@ struct KeyDecode {
   uint32_t m_plane, m_gx;      // floor(2^32 / plane), floor(2^32 / gx)
 };
 
+// (a divisor of 1 would need m = 2^32: 2^32 - 1 is within the two correction steps as well)
+inline KeyDecode make_key_decode(const GridParams& g) {
+  KeyDecode kd;
+  kd.plane = (uint32_t)g.gx * (uint32_t)g.gy;
+  kd.gx = (uint32_t)g.gx;
+  kd.m_plane = (uint32_t)std::min<uint64_t>(0x100000000ull / kd.plane, 0xFFFFFFFFull);
+  kd.m_gx = (uint32_t)std::min<uint64_t>(0x100000000ull / kd.gx, 0xFFFFFFFFull);
+  return kd;
+}
+
 __device__ __forceinline__ uint32_t div_small_err(uint32_t n, uint32_t d, uint32_t m) {
   uint32_t q = __umulhi(n, m);  // true quotient - 2 <= q <= true quotient
   uint32_t r = n - q * d;
@@ -1226,7 +1266,14 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
   const uint2 mine = wd < words ? bm[wd] : make_uint2(0u, 0u);
   uint32_t bits = mine.x;
   uint32_t sum = 0;
-  for (int i = tid; i < lo; i += kFirstsThreads) sum += __popc(bm[i].x);
+  // every load of the re-count is issued before the first popcount (one L2 round trip, not lo / 256)
+  for (int i0 = tid; i0 < lo; i0 += 8 * kFirstsThreads) {
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = i0 + k * kFirstsThreads < lo ? __ldg(&bm[i0 + k * kFirstsThreads].x) : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += __popc(t[k]);
+  }
   uint32_t before;
   block_exscan(sum, warp_sums, &before);
   __syncthreads();  // warp_sums is reused below
@@ -1440,16 +1487,29 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
 }
 
 // ---- expansion for long voxels (pillars: P * C = 320 words, a multiple of 4) -----------------------
-// A warp writes one voxel after the other as float4 streaming stores: lane i owns words 4 i .. 4 i + 3
-// (+ 128 per trip); only the float4s below len * C carry data -- word w belongs to slot w / C,
-// feature w % C -- everything else is stored as zeros directly: no shared memory, no zero-fill
-// pass.  The next voxel's record is fetched while the current one is written.  C == 0: features per
-// point at run time.  Needs 16-byte aligned voxel buffers.
+// A warp owns kWordsVox consecutive voxels.  Lane = voxel for the cell records (one coalesced load),
+// the key decoding (host-computed reciprocals, all lanes busy) and the coordinate / count stores; then
+// the voxels are written one after the other with lane = output word: the len * C real words of a
+// voxel -- word w belongs to slot w / C, feature w % C -- are gathered through the voxel's list and
+// leave as coalesced streaming stores, everything behind them is stored as float4 zeros directly: no
+// shared memory, no zero-fill pass.  The two dependent loads of a voxel's first 32 words (list entry
+// -> row word) are software-pipelined over the voxels: the list entries of voxel j + 2 and the row
+// words of voxel j + 1 are in flight while voxel j is stored (a pillar holds 6 points on average, so
+// those 32 words are usually all it has).  C == 0: features per point at run time.  Needs 16-byte
+// aligned voxel buffers.  (First version -- one voxel per lane-0 decode, four voxels per warp, idx and
+// row fetched per float4 element: 211 warp-instructions per voxel, 0.191 ms per 16-frame C5 step at 64 %
+// issue-active and 57 % DRAM, profiles/r02_c5_ncu_summary.txt.)
+#ifndef PCFE_WORDS_VOX
+#define PCFE_WORDS_VOX 8
+#endif
+// voxels per warp: short warp tasks keep the voxels in flight on the chip within about one frame, whose
+// rows then stay in L2 between the two touches every 32-byte sector of a shuffled frame gets on average
+// (32 voxels per warp: 0.298 ms and 2.4 x the DRAM reads, profiles/r02_c5_words_ncu.txt)
+constexpr int kWordsVox = PCFE_WORDS_VOX;
 template <int C>
 __global__ void __launch_bounds__(kExpThreads)
-hvb_expand_words_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
-                        const int c_rt, const int max_points, const int vpw /* voxels per warp */,
-                        const int32_t* __restrict__ voxel_num) {
+hvb_expand_words_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const KeyDecode kd,
+                        const int c_rt, const int max_points, const int32_t* __restrict__ voxel_num) {
   const int f = blockIdx.y;
   pdl_wait();
   if (w.ctl(f)[w.nb + kCtlOverflow]) return;
@@ -1461,36 +1521,85 @@ hvb_expand_words_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, 
   const uint4* __restrict__ vcell = reinterpret_cast<const uint4*>(w.vcell(f));
   const uint32_t* __restrict__ lst = w.lst(f);
   const float* __restrict__ pts = fr.pts;
-  const int v0 = (blockIdx.x * kExpWarps + wid) * vpw;
+  const int v0 = (blockIdx.x * kExpWarps + wid) * kWordsVox;
   if (v0 >= m) return;
-  const int v1 = min(v0 + vpw, m);
-  uint4 cl = __ldg(vcell + v0);  // key, len, list_off, first (same address for the whole warp)
+  const int nvox = min(kWordsVox, m - v0);
+  uint4 cl = make_uint4(0u, 0u, 0u, 0u);  // key, len, list_off, first
+  if (lane < nvox) {
+    cl = __ldg(vcell + v0 + lane);
+    const uint32_t cz = div_small_err(cl.x, kd.plane, kd.m_plane);
+    const uint32_t rem = cl.x - cz * kd.plane;
+    const uint32_t cy = div_small_err(rem, kd.gx, kd.m_gx);
+    int32_t* co = fr.coors + (size_t)(v0 + lane) * 3;
+    co[0] = (int32_t)cz;
+    co[1] = (int32_t)cy;
+    co[2] = (int32_t)(rem - cy * kd.gx);
+    fr.num[v0 + lane] = (int32_t)min(cl.y, (uint32_t)max_points);
+  }
+  const int sl0 = lane / c, q0 = lane - sl0 * c;  // slot and feature of word `lane`
+  // The list of voxel j (its first 64 entries) lives in two registers per lane, fetched two voxels
+  // ahead; every row word of the voxel is then addressed through shuffles, so all of a voxel's row
+  // loads are independent of each other (a full pillar is 10 loads per lane in flight at once).
+  auto len_of = [&](int j) { return (int)min(__shfl_sync(0xFFFFFFFFu, cl.y, j & 31), (uint32_t)max_points); };
+  auto load_list = [&](int j, int len, uint32_t& a, uint32_t& b) {
+    const uint32_t off = __shfl_sync(0xFFFFFFFFu, cl.z, j & 31);
+    a = (j < nvox && lane < len) ? __ldg(lst + off + lane) : kEmpty;
+    b = (j < nvox && lane + 32 < len) ? __ldg(lst + off + 32 + lane) : kEmpty;
+  };
+  auto first_val = [&](uint32_t a) {  // word `lane` of a voxel: slot sl0 <= 10
+    const uint32_t idx = __shfl_sync(0xFFFFFFFFu, a, sl0);
+    return idx != kEmpty ? __ldg(pts + (size_t)idx * c + q0) : 0.0f;
+  };
+  int len_c = len_of(0), len_n = len_of(1), len_nn = 0;
+  uint32_t la_c, lb_c, la_n, lb_n, la_nn = kEmpty, lb_nn = kEmpty;
+  load_list(0, len_c, la_c, lb_c);
+  load_list(1, len_n, la_n, lb_n);
+  float val_c = first_val(la_c);
+  constexpr int kTail = 4;  // 32-word groups fetched together behind the first one
 #pragma unroll 1
-  for (int v = v0; v < v1; ++v) {
-    const uint4 cur = cl;
-    if (v + 1 < v1) cl = __ldg(vcell + v + 1);
-    const uint32_t len = min(cur.y, (uint32_t)max_points);
-    const int nreal = (int)len * c;
-    float4* __restrict__ dst = reinterpret_cast<float4*>(fr.voxels + (size_t)v * W);
-    if (lane == 0) {
-      decode_key(cur.x, g, fr.coors + (size_t)v * 3);
-      fr.num[v] = (int32_t)len;
-    }
-    for (int i4 = lane; i4 < W4; i4 += 32) {
-      float o[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      const int ow = i4 * 4;
-      if (ow < nreal) {
+  for (int j = 0; j < nvox; ++j) {
+    // lists of voxel j + 2, first row words of voxel j + 1
+    len_nn = len_of(j + 2);
+    load_list(j + 2, len_nn, la_nn, lb_nn);
+    const float val_n = first_val(la_n);
+    const int nreal = len_c * c;
+    const int nreal4 = (nreal + 3) & ~3;  // <= W
+    const uint32_t off = __shfl_sync(0xFFFFFFFFu, cl.z, j);
+    float* __restrict__ dst = fr.voxels + (size_t)(v0 + j) * W;
+    float o[kTail];
+    auto tail_load = [&](const int w0) {  // row words w0 .. w0 + 32 kTail - 1, all loads independent
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (ow + t < nreal) {
-            const int sl = (ow + t) / c;
-            const uint32_t idx = __ldg(lst + cur.z + sl);
-            o[t] = __ldg(pts + (size_t)idx * c + (ow + t - sl * c));
-          }
+      for (int k = 0; k < kTail; ++k) {
+        const int wd = w0 + 32 * k + lane;
+        const int sl = wd / c;
+        const uint32_t xa = __shfl_sync(0xFFFFFFFFu, la_c, sl & 31), xb = __shfl_sync(0xFFFFFFFFu, lb_c, sl & 31);
+        o[k] = 0.0f;
+        if (wd < nreal) {
+          const uint32_t idx = sl < 32 ? xa : sl < 64 ? xb : __ldg(lst + off + sl);
+          o[k] = __ldg(pts + (size_t)idx * c + (wd - sl * c));
         }
       }
-      __stcs(dst + i4, make_float4(o[0], o[1], o[2], o[3]));
+    };
+    auto tail_store = [&](const int w0) {
+#pragma unroll
+      for (int k = 0; k < kTail; ++k) {
+        const int wd = w0 + 32 * k + lane;
+        if (wd < nreal4) __stcs(dst + wd, o[k]);
+      }
+    };
+    // loads first, then the stores that depend on nothing (the zero padding), then the data
+    if (32 < nreal4) tail_load(32);  // voxels with more than 32 real words (warp-uniform)
+    float4* __restrict__ dst4 = reinterpret_cast<float4*>(dst);
+    for (int i4 = (nreal4 >> 2) + lane; i4 < W4; i4 += 32) __stcs(dst4 + i4, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (lane < nreal4) __stcs(dst + lane, val_c);  // words nreal .. nreal4 - 1 are zero padding
+    if (32 < nreal4) tail_store(32);
+#pragma unroll 1
+    for (int w0 = 32 + 32 * kTail; w0 < nreal4; w0 += 32 * kTail) {
+      tail_load(w0);
+      tail_store(w0);
     }
+    len_c = len_n; la_c = la_n; lb_c = lb_n; val_c = val_n;
+    len_n = len_nn; la_n = la_nn; lb_n = lb_nn;
   }
 }
 
@@ -1630,11 +1739,25 @@ static int get_aux(int device, AuxStreams** out) {
   return PCFE_OK;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) and size, not per call
+static int ensure_dyn_smem(const void* kernel, int slot, int device, size_t bytes) {
+  static size_t g_set[8][64] = {};
+  if (device < 0 || device >= 64 || slot < 0 || slot >= 8) return PCFE_ERR_DEVICE;
+  if (g_set[slot][device] >= bytes) return PCFE_OK;
+  PCFE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  g_set[slot][device] = bytes;
+  return PCFE_OK;
+}
+
+static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPlan& p,
+                         int max_points, int max_voxels, int32_t* voxel_num, void* workspace, int wave,
+                         int device, cudaStream_t user_st, int mode, bool overlap, AuxStreams* aux);
+
 int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPlan& p,
             int max_points, int max_voxels, int32_t* voxel_num, void* workspace, int wave,
             int nbuf, int device, cudaStream_t user_st, int mode) {
   std::lock_guard<std::mutex> lk(g_aux_mu);
-  const int mean = mode & kHvMean, pack = (mode & kHvPack) ? 1 : 0;
+  const int pack = (mode & kHvPack) ? 1 : 0;
   const int nwaves = (num_frames + wave - 1) / wave;
   // (packed output: a wave places its rows behind those of the waves before it -- one stream)
   const bool overlap = nbuf >= 2 && nwaves >= 2 && !pack;
@@ -1645,6 +1768,24 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     PCFE_CUDA_TRY(cudaEventRecord(aux->fork, user_st));
     for (int k = 0; k < 2; ++k) PCFE_CUDA_TRY(cudaStreamWaitEvent(aux->s[k], aux->fork, 0));
   }
+  const int rc = hvb_run_waves(frames, num_frames, c, p, max_points, max_voxels, voxel_num, workspace, wave, device,
+                               user_st, mode, overlap, aux);
+  if (overlap) {
+    // always joined, also after an error inside the wave loop: work already enqueued on the auxiliary
+    // streams stays ordered before whatever the caller enqueues next on its stream
+    for (int k = 0; k < 2; ++k) {
+      const cudaError_t e1 = cudaEventRecord(aux->join[k], aux->s[k]);
+      const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(user_st, aux->join[k], 0) : e1;
+      if (e2 != cudaSuccess && rc == PCFE_OK) return (int)e2;
+    }
+  }
+  return rc;
+}
+
+static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPlan& p,
+                         int max_points, int max_voxels, int32_t* voxel_num, void* workspace, int wave,
+                         int device, cudaStream_t user_st, int mode, bool overlap, AuxStreams* aux) {
+  const int mean = mode & kHvMean, pack = (mode & kHvPack) ? 1 : 0;
   // scratch layout per wave buffer: [frame regions] x wave | [bitmask | ctl] x wave (zeroed per
   // wave) | [wordprefix pairs] x wave
   const size_t buf_bytes = (size_t)wave * p.per_frame;
@@ -1662,12 +1803,14 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
   w.nb = p.nb; w.log2_nb = p.log2_nb; w.cap = p.cap; w.slots = p.slots; w.log2_slots = p.log2_slots;
   w.arena_cap = (uint32_t)p.npad;
 
-  PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)p.smem_bucket));
-  PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)p.smem_bucket));
-  PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_rec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2)));
+  {
+    int rc = ensure_dyn_smem((const void*)hvb_bucket_small_kernel<5>, 0, device, p.smem_bucket);
+    if (rc == PCFE_OK) rc = ensure_dyn_smem((const void*)hvb_bucket_small_kernel<8>, 1, device, p.smem_bucket);
+    if (rc == PCFE_OK)
+      rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel, 2, device,
+                           (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2);
+    if (rc != PCFE_OK) return rc;
+  }
   const int pe = std::max(max_points, 1);
   int vec_ok = 1;  // float4 tile stream / vector row loads need 16-byte aligned buffers
   for (int k = 0; k < num_frames && vec_ok; ++k)
@@ -1724,7 +1867,8 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
     const int wnpad = std::max((int)((wn_max + 31) / 32 * 32), 32);
     if (!clustered) {
       ProfScope ps("hvb_bin", st);
-      const dim3 grid((unsigned)((wn_max + kBinTile - 1) / kBinTile), (unsigned)wv);
+      // (a wave of empty frames still runs the sequence: one idle tile, voxel_num = 0 from the scan)
+      const dim3 grid((unsigned)std::max<int64_t>((wn_max + kBinTile - 1) / kBinTile, 1), (unsigned)wv);
       const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
       if (c == 4) PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<4>, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c, fdiv));
       else if (c == 5) PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<5>, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c, fdiv));
@@ -1739,7 +1883,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         const size_t smem_rec = (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)p.cap * 2;
         // speculative first copy: the average bucket fill of the largest frame, rounded up to 64
         // entries, never more than the region
-        const int spec = (int)std::min<int64_t>(p.cap, (((wn_max + p.nb - 1) / p.nb) + 63) / 64 * 64);
+        const int spec = (int)std::min<int64_t>(p.cap, std::max<int64_t>((((wn_max + p.nb - 1) / p.nb) + 63) / 64 * 64, 64));
         PCFE_CUDA_TRY(launch_pdl(hvb_bucket_rec_kernel, grid, dim3(kBucketThreads), smem_rec, st, g_opt_pdl != 0, w, pe, spec));
         PCFE_LAUNCH_CHECK();
       }
@@ -1800,8 +1944,11 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         while (rslots <= p.cap) rslots <<= 1;
         rslots = std::min(rslots, p.slots);
         const size_t smem_rank = (size_t)p.cap * 16 + (size_t)rslots * 8;
-        const int spec = (int)std::min<int64_t>(p.cap, (((wn_max + p.nb - 1) / p.nb) + 63) / 64 * 64);
-        PCFE_CUDA_TRY(cudaFuncSetAttribute(hvb_bucket_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rank));
+        const int spec = (int)std::min<int64_t>(p.cap, std::max<int64_t>((((wn_max + p.nb - 1) / p.nb) + 63) / 64 * 64, 64));
+        {
+          const int rca = ensure_dyn_smem((const void*)hvb_bucket_rank_kernel, 3, device, smem_rank);
+          if (rca != PCFE_OK) return rca;
+        }
         hvb_bucket_rank_kernel<<<grid, kBucketThreads, smem_rank, st>>>(w, pe, spec, rslots);
       }
       PCFE_LAUNCH_CHECK();
@@ -1822,11 +1969,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
       const dim3 grid((unsigned)((vmax + per_cta - 1) / per_cta), (unsigned)wv);
       const int32_t* vn = voxel_num + f0;
       if (max_points == 5 && (c == 4 || c == 5) && max_voxels < (1 << 24)) {
-        KeyDecode kd;
-        kd.plane = (uint32_t)p.g.gx * (uint32_t)p.g.gy;
-        kd.gx = (uint32_t)p.g.gx;
-        kd.m_plane = (uint32_t)(0x100000000ull / kd.plane);
-        kd.m_gx = (uint32_t)(0x100000000ull / kd.gx);
+        const KeyDecode kd = make_key_decode(p.g);
         const int per = kExpWarps * kExpTilesPerWarp * 32;
         const dim3 fgrid((unsigned)((vmax + per - 1) / per), (unsigned)wv);
         const int pper = kExpWarps * kPipeTiles * 32;
@@ -1838,12 +1981,12 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
         else hvb_expand_fixed_kernel<5, 5><<<fgrid, kExpThreads, 0, st>>>(b, w, kd, vn, vec_ok);
         PCFE_LAUNCH_CHECK();
       } else if (max_points * c >= 64 && (max_points * c) % 4 == 0 && vec_ok && g_opt_expand_variant == 0) {
-        // long voxels: lane = output word, one voxel after the other per warp
-        const int vpw = g_opt_expand_vpw;
-        const dim3 wgrid((unsigned)((vmax + kExpWarps * vpw - 1) / (kExpWarps * vpw)), (unsigned)wv);
-        if (c == 4) hvb_expand_words_kernel<4><<<wgrid, kExpThreads, 0, st>>>(b, w, p.g, c, max_points, vpw, vn);
-        else if (c == 5) hvb_expand_words_kernel<5><<<wgrid, kExpThreads, 0, st>>>(b, w, p.g, c, max_points, vpw, vn);
-        else hvb_expand_words_kernel<0><<<wgrid, kExpThreads, 0, st>>>(b, w, p.g, c, max_points, vpw, vn);
+        // long voxels: lane = output word, 32 voxels per warp, one after the other
+        const KeyDecode kd = make_key_decode(p.g);
+        const dim3 wgrid((unsigned)((vmax + kExpWarps * kWordsVox - 1) / (kExpWarps * kWordsVox)), (unsigned)wv);
+        if (c == 4) hvb_expand_words_kernel<4><<<wgrid, kExpThreads, 0, st>>>(b, w, kd, c, max_points, vn);
+        else if (c == 5) hvb_expand_words_kernel<5><<<wgrid, kExpThreads, 0, st>>>(b, w, kd, c, max_points, vn);
+        else hvb_expand_words_kernel<0><<<wgrid, kExpThreads, 0, st>>>(b, w, kd, c, max_points, vn);
         PCFE_LAUNCH_CHECK();
       } else if (c == 4) rc = launch_expand<4>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
       else if (c == 5) rc = launch_expand<5>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
@@ -1856,12 +1999,6 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
                          w.zero_stride, w.wordprefix, w.word_stride, c, max_points, max_voxels,
                          voxel_num + f0, st, mean, pack ? 2 : 0, pack ? voxel_num : nullptr, f0);
     if (rc != PCFE_OK) return rc;
-  }
-  if (overlap) {
-    for (int k = 0; k < 2; ++k) {
-      PCFE_CUDA_TRY(cudaEventRecord(aux->join[k], aux->s[k]));
-      PCFE_CUDA_TRY(cudaStreamWaitEvent(user_st, aux->join[k], 0));
-    }
   }
   return PCFE_OK;
 }

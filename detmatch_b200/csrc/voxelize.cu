@@ -52,7 +52,6 @@ extern int g_opt_expand_ctas;
 extern int g_opt_cluster;
 extern int g_opt_pdl;
 extern int g_opt_pib_grid;
-extern int g_opt_expand_vpw;
 extern int g_opt_no_fast_div;
 extern int g_opt_expand_prefetch;
 
@@ -218,7 +217,9 @@ extern "C" size_t pcfe_hard_voxelize_workspace_bytes(int64_t n_max, int num_fram
                                                      const float rg[6], int max_points,
                                                      int max_voxels) {
   HvChoice ch;
-  if (choose_path(n_max, 4, vs, rg, max_points, max_voxels, &ch) != PCFE_OK) return 0;
+  // c = 3: the most permissive row length (the bucket plan's eligibility shrinks with c, its scratch
+  // size does not depend on it), so the size covers whichever plan the call with the real c selects
+  if (choose_path(n_max, 3, vs, rg, max_points, max_voxels, &ch) != PCFE_OK) return 0;
   // sized for whichever path needs more, so a later pcfe_debug_set cannot invalidate it
   const size_t per = std::max(ch.per_frame, ch.gp.per_frame);
   int w = frames_in_flight > 0 ? std::min(frames_in_flight, kMaxWave) : auto_wave(per, num_frames, ch.bucket);
@@ -239,7 +240,8 @@ static int hv_batch_impl(const pcfe_frame_t* frames, int num_frames, int c, cons
     const pcfe_frame_t& fr = frames[k];
     if (fr.n < 0) return PCFE_ERR_SHAPE;
     if (fr.n > 0 && !fr.points) return PCFE_ERR_NULL;
-    if (max_voxels > 0 && (!fr.coors || !fr.num_points || (max_points > 0 && !fr.voxels)))
+    // (an empty frame produces no rows: its output pointers are never dereferenced)
+    if (max_voxels > 0 && fr.n > 0 && (!fr.coors || !fr.num_points || (max_points > 0 && !fr.voxels)))
       return PCFE_ERR_NULL;
     if (((uintptr_t)fr.points & 3) || ((uintptr_t)fr.voxels & 3) || ((uintptr_t)fr.coors & 3) ||
         ((uintptr_t)fr.num_points & 3))
@@ -458,7 +460,7 @@ extern "C" int pcfe_debug_axis_sweep(float lo, float vs, float hi, uint64_t* out
 // (target points per bucket), "hv_wave" (frames per launch sequence), "hv_bucket_variant" (1: general
 // kernels instead of the record path), "hv_expand_variant" (1: un-pipelined expansion kernels),
 // "hv_expand_prefetch" (frames of L2 prefetch distance), "hv_no_fast_div", "hv_pdl",
-// "hv_expand_ctas" (persistent expansion), "hv_expand_vpw", "pib_grid" (0: brute-force first-hit point-in-box assignment).  Returns
+// "hv_expand_ctas" (persistent expansion), "pib_grid" (0: brute-force first-hit point-in-box assignment).  Returns
 // PCFE_ERR_SHAPE for an unknown name.
 extern "C" int pcfe_debug_set(const char* name, int value) {
   if (!name) return PCFE_ERR_NULL;
@@ -470,7 +472,6 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_expand_variant")) g_opt_expand_variant = value;
   else if (!strcmp(name, "hv_expand_prefetch")) g_opt_expand_prefetch = value;
   else if (!strcmp(name, "hv_no_fast_div")) g_opt_no_fast_div = value;
-  else if (!strcmp(name, "hv_expand_vpw")) g_opt_expand_vpw = value > 0 ? value : 4;
   else if (!strcmp(name, "hv_pdl")) g_opt_pdl = value;
   else if (!strcmp(name, "pib_grid")) g_opt_pib_grid = value;
   else if (!strcmp(name, "hv_expand_ctas")) g_opt_expand_ctas = value;

@@ -113,9 +113,12 @@ def voxelize_batch_packed(points, voxel_size, coors_range, max_points, max_voxel
         assert p.device == dev and p.size(1) == c
     nf = len(points)
     packed_ok = max_points == 5 and c in (4, 5) and all(p.data_ptr() % 16 == 0 for p in points)
+    cap = sum(min(p.size(0), max_voxels) for p in points)
+    if cap == 0:  # every frame empty (or max_voxels == 0): the reference's loop concatenates empty tensors
+        return (torch.empty((0, c) if mean else (0, max_points, c), dtype=torch.float32, device=dev),
+                torch.empty((0,), dtype=torch.int32, device=dev), torch.empty((0, 4), dtype=torch.int32, device=dev))
     if packed_ok:
         with torch.no_grad():
-            cap = sum(min(p.size(0), max_voxels) for p in points)
             shape = (cap, c) if mean else (cap, max_points, c)
             voxels = torch.empty(shape, dtype=torch.float32, device=dev)
             coors = torch.empty((cap, 4), dtype=torch.int32, device=dev)

@@ -59,3 +59,27 @@ def test_reference_arm_under_torchrun_prints_one_line():
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 2
     assert d["value"] > 0 and d["unit"] == "Mpoints/s"
+
+
+def test_strong_scaling_frame_blocks():
+    """contiguous blocks of F / G frames per GPU, disjoint, covering the batch."""
+    for total, world in ((64, 1), (64, 2), (64, 8), (128, 8), (10, 4)):
+        blocks = [bench.frame_block(total, r, world) for r in range(world)]
+        flat = [f for b in blocks for f in b]
+        assert flat == list(range(total))
+        assert max(len(b) for b in blocks) - min(len(b) for b in blocks) <= 1
+
+
+def test_traffic_lookup_rejects_stale_capture(tmp_path, monkeypatch):
+    """roofline.traffic comes from a committed ncu capture and is null when that capture does not
+    contain the kernels the run launched."""
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    (prof / "r99_traffic_C4.json").write_text(json.dumps({"workload": "C4", "source": "x", "kernels": {
+        "hvb_bin_kernel": {"dram_read": 10, "dram_write": 1}, "hvb_expand_rec_kernel": {"dram_read": 5, "dram_write": 7}}}))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    tot, per, src = bench.ncu_traffic("C4", ["hvb_bin", "hvb_expand", "hv_slow_fallback"])
+    assert tot == 23 and "r99_traffic_C4.json" in src
+    tot, per, src = bench.ncu_traffic("C4", ["hvb_bin", "hvb_bucket", "hvb_expand"])
+    assert tot is None and "STALE" in src
+    assert bench.ncu_traffic("C5", ["hvb_bin"])[0] is None

@@ -118,3 +118,42 @@ def test_full_c4_batch_packed_equals_concatenation():
     means, num2, coors2 = voxelize_batch_packed(pts, vs, rg, P, V, mean=True)
     assert torch.equal(coors2, coors_batch) and torch.equal(num2, num_cat)
     assert torch.equal(means.view(torch.int32), hard_simple_vfe(vox_cat, num_cat).view(torch.int32))
+
+
+def test_packed_all_frames_empty(pack_mode):
+    """The reference's voxelize() loop over empty frames returns empty concatenated tensors."""
+    empty = [torch.zeros((0, 5)).cuda(), torch.zeros((0, 5)).cuda()]
+    for mean in (False, True):
+        v, n, c = voxelize_batch_packed(empty, [0.1, 0.1, 0.15], [-75.2, -75.2, -2, 75.2, 75.2, 4], 5, 1000, mean=mean)
+        assert v.shape == ((0, 5) if mean else (0, 5, 5)) and n.shape == (0,) and c.shape == (0, 4)
+
+
+@pytest.mark.parametrize("cfg_name,ci,chunk", [("C4", 4, 2), ("C1", 1, 3), ("C5", 5, 2)])
+def test_host_buffer_pipeline_vs_oracle(cfg_name, ci, chunk, pack_mode):
+    """voxelize_batch_host: HOST frames in, the reference's concatenated tensors out in HOST memory
+    (chunks pipelined on three streams, packed outputs read back at their final offsets), every frame
+    against the oracle; C5 (P = 64) takes the per-frame outputs + concatenation branch."""
+    from detmatch_b200.ops import HostVoxelizePipeline, voxelize_batch_host
+    cfg = synth.CONFIGS[cfg_name]
+    sizes = [cfg["n"] // 3, 0, cfg["n"] // 5, 4097, cfg["n"] // 4]
+    frames = [synth.lidar_frame(n, cfg["c"], synth.seed_for(ci, 40 + k), cfg["r_max"]) for k, n in enumerate(sizes)]
+    V = min(cfg["max_voxels"], 30000)
+    P = cfg["max_num_points"]
+    exp = [oracle.hard_voxelize(p.numpy(), cfg["voxel_size"], cfg["point_cloud_range"], P, V) for p in frames]
+    ev = np.concatenate([e[0] for e in exp])
+    en = np.concatenate([e[2] for e in exp])
+    ec = np.concatenate([np.pad(e[1], ((0, 0), (1, 0)), constant_values=k) for k, e in enumerate(exp)]).astype(np.int32)
+    v, n, c = voxelize_batch_host(frames, cfg["voxel_size"], cfg["point_cloud_range"], P, V, chunk=chunk)
+    assert not v.is_cuda and not n.is_cuda and not c.is_cuda
+    assert_same_bits(v.numpy(), ev, "host voxels")
+    assert_same_bits(n.numpy(), en, "host num")
+    assert_same_bits(c.numpy(), ec, "host coors_batch")
+    # the reusable pipeline: pinned inputs, two runs give the same views
+    pipe = HostVoxelizePipeline(sizes, cfg["c"], cfg["voxel_size"], cfg["point_cloud_range"], P, V, chunk=chunk)
+    pinned = [p.pin_memory() for p in frames]
+    for _ in range(2):
+        v2, n2, c2 = pipe.run(pinned)
+        assert_same_bits(v2.numpy(), ev, "pipeline voxels")
+        assert_same_bits(c2.numpy(), ec, "pipeline coors_batch")
+    assert pipe.counts == [len(e[2]) for e in exp]
+    assert pipe.d2h_bytes == sum(len(e[2]) for e in exp) * (P * cfg["c"] * 4 + 20) + 4 * len(sizes)

@@ -124,8 +124,8 @@ def test_reject_margin_adversarial():
 
 
 def test_c3_frame_vs_oracle():
-    """BASELINE config C3 shape: 120k points x 200 boxes (2 of the 16 frames against the oracle,
-    every frame for cross-op consistency)."""
+    """BASELINE config C3: 16 frames x 120k points x 200 boxes, every frame against the oracle, plus
+    the cross-op consistency of the three layouts."""
     c3 = synth.CONFIGS["C3"]
     B = 16
     pts = torch.stack([synth.lidar_frame(c3["n"], 3, synth.seed_for(3, k), c3["r_max"]) for k in range(B)])
@@ -135,7 +135,7 @@ def test_c3_frame_vs_oracle():
     tp, tb = pts.cuda(), bxs.cuda()
     got = points_in_boxes_batch(tp, tb)
     assert got.shape == (B, c3["n"], c3["boxes"])
-    for k in (0, 15):
+    for k in range(B):
         exp = oracle.points_in_boxes_cpu(pts[k].numpy(), bxs[k].numpy())
         assert exp.sum() > 1000
         assert_same_bits(got[k].t().contiguous().cpu().numpy(), exp, f"C3 frame {k}")
@@ -272,3 +272,42 @@ def test_first_hit_random_vs_oracle(t):
     bxs[:, :k, 2] -= 0.4
     got = _first_hit(pts, bxs, f"t={t}")
     assert (got >= 0).sum() >= k
+
+
+def test_depth_boxes_points_in_boxes_reference_literal():
+    """tests/test_utils/test_box3d.py:1157-1209: DepthInstance3DBoxes(th_boxes, box_dim=6, with_yaw=False)
+    rotated by -0.04599790655000615 (the tensor the reference test asserts at :1161-1173), queried with
+    the test's five points: no point lies in a box."""
+    from detmatch_b200.ops.roiaware_pool3d import depth_boxes_points_in_boxes
+    boxes = torch.tensor([[0.64884546, 0.78390356, 0.10563634, 1.50373348, 0.23795205, 0.27956772, 0],
+                          [1.45139421, 0.43169443, 0.93829232, 0.11967964, 0.93380373, 1.89191735, 0]])
+    points = torch.tensor([[0.6762, 1.2559, -1.4658], [0.8784, 4.7814, -1.3857], [-0.2517, 6.7053, -0.9697],
+                           [0.5520, 0.6533, -0.5265], [-0.5358, 4.5870, -1.4741]])
+    got = depth_boxes_points_in_boxes(boxes, points.cuda())
+    assert got.dtype == torch.int32 and got.device.type == "cuda"
+    assert torch.all(got == torch.zeros((5, 2), dtype=torch.int32, device="cuda"))
+    assert depth_boxes_points_in_boxes(boxes, points.cuda()[None]).shape == (5, 2)
+
+
+def test_box_structure_adapters_vs_oracle():
+    """depth_box3d.py:251-277 / lidar_box3d.py:258-270 flows on random boxes with points inside: the
+    axis swap + DEPTH -> LIDAR conversion happen in torch, the masks equal points_in_boxes_cpu of the
+    oracle on the converted inputs."""
+    from detmatch_b200.ops.roiaware_pool3d import (depth_boxes_points_in_boxes, depth_boxes_to_lidar,
+                                                   lidar_boxes_points_in_boxes)
+    g = torch.Generator().manual_seed(31337)
+    T, M = 40, 20000
+    boxes = torch.cat([torch.rand((T, 3), generator=g) * 8 - 4, torch.rand((T, 3), generator=g) * 2 + 0.3,
+                       (torch.rand((T, 1), generator=g) * 2 - 1) * 3.14159], dim=1)
+    points = torch.rand((M, 3), generator=g) * 10 - 5
+    points[:T] = boxes[:, :3] + torch.tensor([0.0, 0.0, 0.1])  # depth boxes are bottom-centred like LiDAR ones
+    got = depth_boxes_points_in_boxes(boxes, points.cuda())
+    pl = points[:, [1, 0, 2]].clone()
+    pl[:, 1] *= -1
+    exp = oracle.points_in_boxes_cpu(pl.numpy(), depth_boxes_to_lidar(boxes).numpy())
+    assert exp.sum() > T
+    assert_same_bits(got.t().contiguous().cpu().numpy(), exp, "depth flow")
+    first = lidar_boxes_points_in_boxes(boxes, points.cuda())
+    e = oracle.points_in_boxes_cpu(points.numpy(), boxes.numpy())  # (T, M)
+    want = np.where(e.any(axis=0), e.argmax(axis=0), -1).astype(np.int32)
+    assert_same_bits(first.cpu().numpy(), want, "lidar flow")

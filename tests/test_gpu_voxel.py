@@ -36,6 +36,13 @@ def hv_mode(request):
     _cabi.debug_set("hv_bucket_variant", 0)
 
 
+def _oracle_frame(cfg_name, ci, k):
+    """Oracle outputs of frame k of a BASELINE config (LiDAR-like generator; ~0.1 s per frame)."""
+    cfg = synth.CONFIGS[cfg_name]
+    p = synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(ci, k), cfg["r_max"]).numpy()
+    return oracle.hard_voxelize(p, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], cfg["max_voxels"])
+
+
 def _gpu_hard(pts, vs, rg, p, v):
     out = voxelization(torch.from_numpy(np.ascontiguousarray(pts)).cuda(), list(vs), list(rg), int(p), int(v))
     return [o.cpu().numpy() for o in out]
@@ -257,7 +264,7 @@ def test_many_frames_more_than_one_wave():
 
 def test_full_c4_batch_properties():
     """BASELINE config C4 at full size (64 x 180k x 5): size-independent properties on every frame
-    (computed on the GPU with torch ops), plus bit-exact oracle comparison on three frames."""
+    (computed on the GPU with torch ops), plus the bit-exact oracle comparison of EVERY frame ."""
     cfg = synth.CONFIGS["C4"]
     F = 64
     pts = [synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(4, k), cfg["r_max"]).cuda() for k in range(F)]
@@ -289,11 +296,29 @@ def test_full_c4_batch_properties():
         pad = vox[k, :m] * (slot >= num[k, :m, None, None]).float()
         assert (pad == 0).all() and (vox[k, :m].view(torch.int32)[(slot >= num[k, :m, None, None]).expand(-1, -1, 5)] == 0).all()
         assert (vox[k, :m, 0] == pts[k][fo]).all()
-    for k in (0, 31, 63):
-        ev, ec, en = oracle.hard_voxelize(pts[k].cpu().numpy(), cfg["voxel_size"], cfg["point_cloud_range"], P, V)
+    for k in range(F):
+        ev, ec, en = _oracle_frame("C4", 4, k)
+        assert counts[k] == len(en)
         assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"frame {k} voxels")
         assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"frame {k} coors")
         assert_same_bits(num[k, :counts[k]].cpu().numpy(), en, f"frame {k} num")
+
+
+def test_full_c5_batch_16_frames_vs_oracle():
+    """BASELINE config C5 at its per-GPU size at 8 GPUs (128 / 8 = 16 frames x 300k x 5, P = 64,
+    V = 40 000): every frame bit-exact against the oracle, one batched call."""
+    cfg = synth.CONFIGS["C5"]
+    F = 16
+    pts = [synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(5, k), cfg["r_max"]).cuda() for k in range(F)]
+    P, V = cfg["max_num_points"], cfg["max_voxels"]
+    vox, coors, num, vnum = voxelize_batch(pts, cfg["voxel_size"], cfg["point_cloud_range"], P, V, sync=False)
+    counts = vnum.cpu().tolist()
+    for k in range(F):
+        ev, ec, en = _oracle_frame("C5", 5, k)
+        assert counts[k] == len(en) and counts[k] > 10000
+        assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"frame {k} coors")
+        assert_same_bits(num[k, :counts[k]].cpu().numpy(), en, f"frame {k} num")
+        assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"frame {k} voxels")
 
 
 def test_c2_dynamic_batch_16_frames():
@@ -394,3 +419,34 @@ def test_fused_points_range_filter(cfg_name, ci):
             assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"{cfg_name} frame {k} coors")
             assert_same_bits(num[k, :counts[k]].cpu().numpy(), en, f"{cfg_name} frame {k} num")
             assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"{cfg_name} frame {k} voxels")
+
+
+def test_empty_frames_in_their_own_wave():
+    """A wave whose frames are all empty (hv_wave = 1 with empty frames in the middle and at the end)
+    must not launch a zero-sized grid: voxel_num = 0 for those frames, the others unaffected."""
+    from detmatch_b200 import _cabi
+    cfg = synth.CONFIGS["C1"]
+    full = synth.lidar_frame(6000, 4, 123, 80.0)
+    empty = torch.zeros((0, 4))
+    frames = [full, empty, full[:777], empty]
+    _cabi.debug_set("hv_wave", 1)
+    try:
+        vox, coors, num, vnum = voxelize_batch([p.cuda() for p in frames], cfg["voxel_size"], cfg["point_cloud_range"], 5, 900,
+                                               sync=False)
+        counts = vnum.cpu().tolist()
+    finally:
+        _cabi.debug_set("hv_wave", 0)
+    assert counts[1] == 0 and counts[3] == 0
+    for k in (0, 2):
+        ev, ec, en = oracle.hard_voxelize(frames[k].numpy(), cfg["voxel_size"], cfg["point_cloud_range"], 5, 900)
+        assert counts[k] == len(en)
+        assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"frame {k}")
+        assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"frame {k}")
+
+
+def test_workspace_query_covers_three_feature_rows():
+    """The size query has no row length argument: with C = 3 and 257 <= max_points <= 341 the call
+    selects the bucket plan (larger scratch) and must fit what the query returned."""
+    rng = np.random.default_rng(5)
+    pts = rng.uniform([0, -4, -3], [8, 4, 1], size=(5000, 3)).astype(np.float32)
+    _check_hard(pts, [0.5, 0.5, 0.5], KITTI, 300, 50, "C=3 P=300")
