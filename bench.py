@@ -439,6 +439,9 @@ def run_ours(args):
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         cpu_baseline = cpu_baseline_subprocess(args)
+    reference_cuda = None
+    if not args.no_cpu_baseline and not args.no_extras and world == 1:
+        reference_cuda = run_reference_cuda(cfg, pts, plan, m_list, dev)
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -447,6 +450,7 @@ def run_ours(args):
         "config": dict(_config_dict(cfg, args, frames_per_step=total_frames), frames_per_gpu_per_step=F),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "kernels": kernels, "fused": fused, "latency": latency, "weak": weak,
+        "reference_cuda": reference_cuda,
         "comm": "gloo (host): barrier + MAX of the ranks' device times; no data-path collective, no NCCL" if world > 1 else None,
     }
     print(json.dumps(line), flush=True)
@@ -477,6 +481,39 @@ def run_weak_extra(cfg, rank, world, dev, barrier, steps=20):
     ms = max_over_ranks(a.elapsed_time(b)) / steps
     return {"scaling": "weak", "frames_per_gpu_per_step": F, "ms_per_step": round(ms, 4),
             "value": round(world * F * N / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "steps": steps}
+
+
+def run_reference_cuda(cfg, pts, plan, m_list, dev, frames=2):
+    """Third column (optional): the reference's OWN CUDA op -- hard_voxelize_gpu,
+    voxelization_cuda.cu:184-326, compiled unmodified for sm_100a into oracle/_ref/detmatch_ref_cuda.so --
+    per frame on the same GPU, called as the reference's wrapper calls it (three new_zeros + the op,
+    voxelize.py:46-58).  A baseline next to the CPU arm, not a product path; its output is also compared
+    with ours on the frames it runs."""
+    import torch
+    try:
+        from oracle import ref
+        if not ref.cuda_available():
+            return {"unavailable": "oracle/_ref/detmatch_ref_cuda.so not built"}
+        ref.cuda_module()
+        P, V = cfg["max_num_points"], cfg["max_voxels"]
+        frames = min(frames, len(pts))
+        ref.cuda_voxelization(pts[0], cfg["voxel_size"], cfg["point_cloud_range"], P, V)  # warm-up
+        torch.cuda.synchronize(dev)
+        same = True
+        t0 = time.perf_counter()
+        outs = [ref.cuda_voxelization(pts[k], cfg["voxel_size"], cfg["point_cloud_range"], P, V) for k in range(frames)]
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / frames
+        for k, (v, c, n) in enumerate(outs):
+            m = m_list[k]
+            same = same and v.size(0) == m and torch.equal(c, plan.coors[k, :m]) and torch.equal(n, plan.num_points[k, :m]) \
+                and torch.equal(v, plan.voxels[k, :m])
+        return {"ms_per_frame": round(dt * 1e3, 3), "value": round(cfg["n"] / dt / 1e6, 2), "unit": UNIT, "frames": frames,
+                "same_output_as_ours": bool(same),
+                "what": "reference hard_voxelize_gpu (voxelization_cuda.cu, unmodified, -arch sm_100a), host wall time per "
+                        "frame incl. its own device syncs, same GPU"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:300]}
 
 
 def run_latency_extras(cfg, pts, dev, reps=100):
@@ -528,7 +565,7 @@ def run_fused_extras(cfg, pts, plan, dev, reps=50):
     import torch
     from detmatch_b200 import _cabi
     from detmatch_b200._torch_glue import ptr, stream_ptr
-    F, N, C = cfg["frames"], cfg["n"], cfg["c"]
+    F, N, C = len(pts), cfg["n"], cfg["c"]
     P, V = cfg["max_num_points"], cfg["max_voxels"]
     L = _cabi.lib()
     cap = F * min(N, V)

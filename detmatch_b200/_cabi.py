@@ -71,6 +71,10 @@ PROTOTYPES = {
                                                    c_size_t, c_int, c_void_p]),
     "pcfe_pcdet_points_in_boxes_cpu_f32": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p,
                                                    c_size_t, c_int, c_void_p]),
+    "pcfe_roiaware_pool3d_forward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int, c_int,
+                                                 c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pcfe_roiaware_pool3d_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                                  c_int64, c_void_p, c_int, c_void_p]),
     "pcfe_debug_sincosf": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "pcfe_debug_axis_sweep": (c_int, [ctypes.c_float, ctypes.c_float, ctypes.c_float, c_void_p, c_int, c_void_p]),
 }

@@ -12,8 +12,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libpcfe.so")
-SOURCES = ["voxelize.cu", "hv_global.cu", "hv_bucket.cu", "points_in_boxes.cu", "scatter.cu"]
-HEADERS = [os.path.join(CSRC, "pcfe_common.cuh"), os.path.join(CSRC, "hv_common.cuh"), os.path.join(CSRC, "hv_cluster.cuh"),
+SOURCES = ["voxelize.cu", "hv_global.cu", "hv_bucket.cu", "points_in_boxes.cu", "roiaware_pool3d.cu", "scatter.cu"]
+HEADERS = [os.path.join(CSRC, "pcfe_common.cuh"), os.path.join(CSRC, "hv_common.cuh"), os.path.join(CSRC, "hv_cluster.cuh"), os.path.join(CSRC, "pib_dev.cuh"),
            os.path.join(ROOT, "include", "pcfe.h")]
 
 NVCC_FLAGS = [

@@ -1,4 +1,4 @@
-"""Drop-in for the hot-path part of the reference's pybind module
+"""Drop-in for the reference's pybind module
 ``mmdet3d.ops.roiaware_pool3d.roiaware_pool3d_ext`` (roiaware_pool3d.cpp:126-136): same names,
 **boxes first** argument order, caller-allocated ``out`` written in place, returns 1.
 
@@ -62,3 +62,44 @@ def points_in_boxes_cpu(boxes, points, out):
     t, n = boxes.shape[0], points.shape[0]
     assert boxes.shape[1] == 7 and points.shape[1] == 3 and out.shape == (t, n)
     return _run("pcfe_points_in_boxes_boxmajor_f32", boxes, points, out, 1, t, n)
+
+
+def forward(rois, pts, pts_feature, argmax, pts_idx_of_voxels, pooled_features, pool_method):
+    """roiaware_pool3d.cpp:49-91 (roiaware_pool3d_gpu): rois (N,7), pts (npoints,3), pts_feature
+    (npoints,C), argmax (N,ox,oy,oz,C) int32, pts_idx_of_voxels (N,ox,oy,oz,max_pts) int32,
+    pooled_features (N,ox,oy,oz,C); pool_method 0 = max, 1 = avg.  Outputs need no pre-zeroing."""
+    for t in (rois, pts, pts_feature, argmax, pts_idx_of_voxels, pooled_features):
+        if not t.is_cuda:
+            raise RuntimeError("roiaware_pool3d_ext.forward: tensors must be CUDA tensors (no CPU fallback)")
+        if not t.is_contiguous():
+            raise RuntimeError("roiaware_pool3d_ext.forward: tensors must be contiguous")
+    if not (rois.dtype == pts.dtype == pts_feature.dtype == pooled_features.dtype == torch.float32):
+        raise TypeError("roiaware_pool3d_ext.forward: float32 only")
+    if argmax.dtype != torch.int32 or pts_idx_of_voxels.dtype != torch.int32:
+        raise TypeError("roiaware_pool3d_ext.forward: argmax / pts_idx_of_voxels must be int32")
+    n, m, c = rois.size(0), pts.size(0), pts_feature.size(1)
+    ox, oy, oz, mp = (pts_idx_of_voxels.size(k) for k in (1, 2, 3, 4))
+    assert (ox < 256) and (oy < 256) and (oz < 256)  # roiaware_pool3d.cpp:72-73
+    assert rois.size(1) == 7 and pts.size(1) == 3 and pts_feature.size(0) == m
+    dev = pts.device
+    rc = _cabi.lib().pcfe_roiaware_pool3d_forward_f32(ptr(rois), ptr(pts), ptr(pts_feature), n, m, c, mp, ox, oy, oz,
+                                                      int(pool_method), ptr(argmax), ptr(pts_idx_of_voxels),
+                                                      ptr(pooled_features), dev.index, stream_ptr(dev))
+    _cabi.check(rc, "pcfe_roiaware_pool3d_forward_f32")
+    return 1
+
+
+def backward(pts_idx_of_voxels, argmax, grad_out, grad_in, pool_method):
+    """roiaware_pool3d.cpp:93-123 (roiaware_pool3d_gpu_backward): grad_in (npoints, C) is overwritten."""
+    for t in (pts_idx_of_voxels, argmax, grad_out, grad_in):
+        if not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError("roiaware_pool3d_ext.backward: tensors must be contiguous CUDA tensors")
+    n = pts_idx_of_voxels.size(0)
+    ox, oy, oz, mp = (pts_idx_of_voxels.size(k) for k in (1, 2, 3, 4))
+    c = grad_out.size(4)
+    dev = grad_out.device
+    rc = _cabi.lib().pcfe_roiaware_pool3d_backward_f32(ptr(pts_idx_of_voxels), ptr(argmax), ptr(grad_out), n, ox, oy, oz, c, mp,
+                                                       int(pool_method), grad_in.size(0), ptr(grad_in), dev.index,
+                                                       stream_ptr(dev))
+    _cabi.check(rc, "pcfe_roiaware_pool3d_backward_f32")
+    return 1

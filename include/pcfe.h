@@ -282,6 +282,36 @@ int pcfe_points_in_boxes_boxmajor_f32(const float* boxes, const float* points, i
                                       int32_t* out, void* workspace, size_t workspace_bytes,
                                       int device, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * RoI-aware point pooling (PartA2's RoI head)
+ * Replaces: roiaware_pool3d_ext.forward / backward
+ *           mmdet3d/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:49-123 (bindings :127-128),
+ *           roiaware_pool3d_kernel.cu:44-361; call sites mmdet3d/ops/roiaware_pool3d/roiaware_pool3d.py:80-82,105-106.
+ * rois (boxes_num, 7) = (cx, cy, cz_bottom, w, l, h, rz), pts (pts_num, 3), pts_feature (pts_num, channels), float32.
+ * _forward_: pts_idx_of_voxels (boxes_num, out_x, out_y, out_z, max_pts_each_voxel) int32: entry 0 of a
+ *   voxel = number of points kept (at most max_pts_each_voxel - 1), entries 1.. = their indices in
+ *   ascending point order, the rest UNSPECIFIED (the reference zero-fills; nothing reads them);
+ *   pooled_features (boxes_num, out_x, out_y, out_z, channels): max (pool_method 0: first point of the
+ *   list with the strictly largest feature; 0 for an empty voxel) or average in list order
+ *   (pool_method 1); argmax (same shape, int32, pool_method 0 only): that point's index or -1.
+ *   Every element of pooled_features / argmax and every counter is written: no pre-zeroed tensors.
+ *   Point -> RoI membership is the CPU inside test of points_in_boxes (above) bit for bit; the voxel
+ *   inside the RoI follows roiaware_pool3d_kernel.cu:60-78 in float32.  out_* <= 255 (:72-73).
+ * _backward_: grad_in (pts_num, channels) is zeroed and receives grad_out routed to argmax (max) or
+ *   grad_out / max(count, 1) to every listed point (average) with float atomicAdd, as in :264-341
+ *   (summation order unspecified there and here).
+ * Returns 0 / <0 / >0 as everywhere; no workspace, no allocation, no host synchronisation.
+ * ------------------------------------------------------------------------------------------- */
+int pcfe_roiaware_pool3d_forward_f32(const float* rois, const float* pts, const float* pts_feature,
+                                     int boxes_num, int64_t pts_num, int channels, int max_pts_each_voxel,
+                                     int out_x, int out_y, int out_z, int pool_method, int32_t* argmax,
+                                     int32_t* pts_idx_of_voxels, float* pooled_features, int device,
+                                     void* stream);
+int pcfe_roiaware_pool3d_backward_f32(const int32_t* pts_idx_of_voxels, const int32_t* argmax,
+                                      const float* grad_out, int boxes_num, int out_x, int out_y, int out_z,
+                                      int channels, int max_pts_each_voxel, int pool_method, int64_t pts_num,
+                                      float* grad_in, int device, void* stream);
+
 /* OpenPCDet variant -- what PV-RCNN's point head calls (pcdet/models/dense_heads/
  * point_head_template.py:82-89).
  * Replaces: roiaware_pool3d_cuda.points_in_boxes_gpu / points_in_boxes_cpu,

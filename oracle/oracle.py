@@ -44,6 +44,12 @@ def lib():
                                                     ctypes.c_int, ctypes.c_int, _f32p, _i32p, _i32p]
         L.pcfe_oracle_hard_voxelize_f64.argtypes = [_f64p, ctypes.c_int64, ctypes.c_int, _f32p, _f32p,
                                                     ctypes.c_int, ctypes.c_int, _f64p, _i32p, _i32p]
+        L.pcfe_oracle_roiaware_pool3d_forward.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int64, _f32p, ctypes.c_int,
+                                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                          _i32p, _i32p, _f32p]
+        L.pcfe_oracle_roiaware_pool3d_backward.argtypes = [_i32p, _i32p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                           ctypes.c_int64, _f32p]
         L.pcfe_oracle_points_in_boxes_cpu.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int64, _i32p]
         L.pcfe_oracle_points_in_boxes_restated.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int64, _i32p]
         L.pcfe_oracle_pcdet_points_in_boxes.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int64, ctypes.c_float, _i32p]
@@ -197,3 +203,34 @@ def sincosf_sweep(lo_bits, hi_bits, stride=1):
     bad = ctypes.c_uint32(0)
     n = lib().pcfe_oracle_sincosf_sweep(lo_bits, hi_bits, stride, ctypes.byref(bad))
     return int(n), int(bad.value)
+
+
+def roiaware_pool3d_forward(rois, pts, pts_feature, out_size, max_pts_per_voxel, mode):
+    """RoIAwarePool3dFunction.forward (roiaware_pool3d.py:46-88) on numpy arrays: returns
+    (pooled_features, argmax, pts_idx_of_voxels).  mode 0 = max, 1 = avg."""
+    ox, oy, oz = (out_size,) * 3 if isinstance(out_size, int) else out_size
+    r = np.ascontiguousarray(rois, dtype=np.float32)
+    p = np.ascontiguousarray(pts, dtype=np.float32)
+    f = np.ascontiguousarray(pts_feature, dtype=np.float32)
+    n, m, c = r.shape[0], p.shape[0], f.shape[1]
+    pooled = np.zeros((n, ox, oy, oz, c), dtype=np.float32)
+    argmax = np.zeros((n, ox, oy, oz, c), dtype=np.int32)
+    lists = np.zeros((n, ox, oy, oz, max_pts_per_voxel), dtype=np.int32)
+    rc = lib().pcfe_oracle_roiaware_pool3d_forward(_p(r, _f32p), n, _p(p, _f32p), m, _p(f, _f32p), c, max_pts_per_voxel,
+                                                   ox, oy, oz, int(mode), _p(argmax, _i32p), _p(lists, _i32p), _p(pooled, _f32p))
+    assert rc == 1, rc
+    return pooled, argmax, lists
+
+
+def roiaware_pool3d_backward(pts_idx_of_voxels, argmax, grad_out, num_pts, mode):
+    """RoIAwarePool3dFunction.backward (roiaware_pool3d.py:90-106): grad_in (num_pts, C)."""
+    lists = np.ascontiguousarray(pts_idx_of_voxels, dtype=np.int32)
+    am = np.ascontiguousarray(argmax, dtype=np.int32)
+    g = np.ascontiguousarray(grad_out, dtype=np.float32)
+    n, ox, oy, oz, mp = lists.shape
+    c = g.shape[4]
+    grad_in = np.zeros((num_pts, c), dtype=np.float32)
+    rc = lib().pcfe_oracle_roiaware_pool3d_backward(_p(lists, _i32p), _p(am, _i32p), _p(g, _f32p), n, ox, oy, oz, c, mp,
+                                                    int(mode), num_pts, _p(grad_in, _f32p))
+    assert rc == 1, rc
+    return grad_in

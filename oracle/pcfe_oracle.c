@@ -388,6 +388,125 @@ int pcfe_oracle_points_in_boxes_cpu(const float* boxes, int t,
   return pib_impl(boxes, t, points, n, out, 0);
 }
 
+/* ------------------------------------------------------------------------- */
+/* RoI-aware point pooling: mmdet3d/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:44-361,   */
+/* restated for the CPU.  The reference has NO CPU implementation of this op; its CUDA kernel   */
+/* evaluates the inside test of :26-42 (the text of points_in_boxes_cpu.cpp:16-40) with device  */
+/* cos / sin and FMA contraction.  This restatement uses the CPU arithmetic of that text (host  */
+/* libm cosf / sinf, no contraction) -- the library's convention for every point-in-box entry -- */
+/* and is pinned against the reference test's own expectations                                  */
+/* (tests/test_models/test_common_modules/test_roiaware_pool3d.py:9-40) and, on the GPU box,    */
+/* against the reference kernel itself compiled for sm_100a (oracle/_ref/detmatch_ref_roiaware.so). */
+/* ------------------------------------------------------------------------- */
+/* int(float) as the op's only implementation -- a CUDA kernel -- performs it: cvt.rzi.s32.f32 saturates
+ * and maps NaN to 0 (a C cast of such values is undefined; x86 gives INT_MIN). */
+static inline int cuda_f2i_rz(float q) {
+  if (q != q) return 0;
+  if (q >= 2147483648.0f) return 2147483647;
+  if (q <= -2147483648.0f) return (-2147483647 - 1);
+  return (int)q;
+}
+
+static inline int rap_check(const float* pt, const float* box3d, float* local_x, float* local_y) {
+  float x = pt[0], y = pt[1], z = pt[2];
+  float cx = box3d[0], cy = box3d[1], cz = box3d[2];
+  float w = box3d[3], l = box3d[4], h = box3d[5], rz = box3d[6];
+  cz += h / 2.0;                           /* :34 */
+  if (fabsf(z - cz) > h / 2.0) return 0;   /* :36 */
+  float shift_x = x - cx, shift_y = y - cy;
+  float rot_angle = rz + M_PI / 2;         /* :20 */
+  float cosa = cosf(rot_angle), sina = sinf(rot_angle);
+  *local_x = shift_x * cosa + shift_y * (-sina); /* :22-23 */
+  *local_y = shift_x * sina + shift_y * cosa;
+  float in_flag = (*local_x > -l / 2.0) & (*local_x < l / 2.0) & (*local_y > -w / 2.0) & (*local_y < w / 2.0); /* :38-40 */
+  return (int)in_flag;
+}
+
+/* forward: pts_idx_of_voxels (N, ox, oy, oz, mp) zero-filled here like the reference's wrapper does
+ * (roiaware_pool3d.py:72-78), argmax / pooled (N, ox, oy, oz, C).  pool_method 0 = max, 1 = avg. */
+int pcfe_oracle_roiaware_pool3d_forward(const float* rois, int boxes_num, const float* pts, int64_t pts_num,
+                                        const float* pts_feature, int channels, int mp, int out_x, int out_y,
+                                        int out_z, int pool_method, int32_t* argmax, int32_t* pts_idx_of_voxels,
+                                        float* pooled) {
+  const int64_t nvox = (int64_t)out_x * out_y * out_z;
+  memset(pts_idx_of_voxels, 0, sizeof(int32_t) * (size_t)(boxes_num * nvox * mp));
+  memset(pooled, 0, sizeof(float) * (size_t)(boxes_num * nvox * channels));
+  if (argmax) memset(argmax, 0, sizeof(int32_t) * (size_t)(boxes_num * nvox * channels));
+  const int max_num_pts = mp - 1; /* index 0 is the counter (:97) */
+  for (int b = 0; b < boxes_num; ++b) {
+    const float* roi = rois + (int64_t)b * 7;
+    int32_t* pv = pts_idx_of_voxels + (int64_t)b * nvox * mp;
+    for (int64_t k = 0; k < pts_num; ++k) { /* mask (:44-90) + collect (:92-119), point order */
+      float local_x = 0, local_y = 0;
+      if (!rap_check(pts + k * 3, roi, &local_x, &local_y)) continue;
+      float local_z = pts[k * 3 + 2] - roi[2];
+      float w = roi[3], l = roi[4], h = roi[5];
+      float x_res = l / out_x, y_res = w / out_y, z_res = h / out_z;
+      unsigned int x_idx = (unsigned int)cuda_f2i_rz((local_x + l / 2) / x_res);
+      unsigned int y_idx = (unsigned int)cuda_f2i_rz((local_y + w / 2) / y_res);
+      unsigned int z_idx = (unsigned int)cuda_f2i_rz(local_z / z_res);
+      /* min(max(idx, 0), out - 1) on unsigned values (:73-75) */
+      if (x_idx > (unsigned int)(out_x - 1)) x_idx = (unsigned int)(out_x - 1);
+      if (y_idx > (unsigned int)(out_y - 1)) y_idx = (unsigned int)(out_y - 1);
+      if (z_idx > (unsigned int)(out_z - 1)) z_idx = (unsigned int)(out_z - 1);
+      int64_t base = (((int64_t)x_idx * out_y + y_idx) * out_z + z_idx) * mp;
+      int cnt = pv[base];
+      if (cnt < max_num_pts) {
+        pv[base + cnt + 1] = (int32_t)k;
+        pv[base]++;
+      }
+    }
+    for (int64_t v = 0; v < nvox; ++v) {
+      const int32_t* lst = pv + v * mp;
+      int total = lst[0];
+      for (int c = 0; c < channels; ++c) {
+        int64_t o = ((int64_t)b * nvox + v) * channels + c;
+        if (pool_method == 0) { /* :121-175 */
+          int arg = -1;
+          float max_val = -1e50; /* -inf as float */
+          for (int k = 1; k <= total; ++k) {
+            float f = pts_feature[(int64_t)lst[k] * channels + c];
+            if (f > max_val) {
+              max_val = f;
+              arg = lst[k];
+            }
+          }
+          if (arg != -1) pooled[o] = max_val;
+          argmax[o] = arg;
+        } else { /* :177-215 */
+          float sum_val = 0;
+          for (int k = 1; k <= total; ++k) sum_val += pts_feature[(int64_t)lst[k] * channels + c];
+          if (total > 0) pooled[o] = sum_val / total;
+        }
+      }
+    }
+  }
+  return 1;
+}
+
+/* backward (:264-341) with the additions done in voxel order, double accumulators are NOT used: the
+ * reference accumulates float atomicAdds in an unspecified order; tests bound the difference. */
+int pcfe_oracle_roiaware_pool3d_backward(const int32_t* pts_idx_of_voxels, const int32_t* argmax,
+                                         const float* grad_out, int boxes_num, int out_x, int out_y, int out_z,
+                                         int channels, int mp, int pool_method, int64_t pts_num, float* grad_in) {
+  const int64_t nvox = (int64_t)boxes_num * out_x * out_y * out_z;
+  memset(grad_in, 0, sizeof(float) * (size_t)(pts_num * channels));
+  for (int64_t v = 0; v < nvox; ++v)
+    for (int c = 0; c < channels; ++c) {
+      int64_t e = v * channels + c;
+      if (pool_method == 0) {
+        if (argmax[e] == -1) continue;
+        grad_in[(int64_t)argmax[e] * channels + c] += grad_out[e] * 1;
+      } else {
+        const int32_t* lst = pts_idx_of_voxels + v * mp;
+        int total = lst[0];
+        float cur_grad = 1 / fmaxf((float)total, 1.0);
+        for (int k = 1; k <= total; ++k) grad_in[(int64_t)lst[k] * channels + c] += grad_out[e] * cur_grad;
+      }
+    }
+  return 1;
+}
+
 /* OpenPCDet variant: thirdparty/Spconv-OpenPCDet/pcdet/ops/roiaware_pool3d/src/
  * roiaware_pool3d.cpp:121-140 (check_pt_in_box3d_cpu, MARGIN = 1e-2) and its CUDA twin
  * roiaware_pool3d_kernel.cu:16-37 (MARGIN = 1e-5): boxes (x, y, z_CENTRE, dx, dy, dz, heading). */

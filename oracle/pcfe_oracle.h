@@ -80,6 +80,16 @@ int pcfe_oracle_points_in_boxes_restated(const float* boxes, int t,
                                          const float* points, int64_t n,
                                          int32_t* out);
 
+/* RoI-aware point pooling, roiaware_pool3d_kernel.cu:44-361 restated with the CPU inside test
+ * (see pcfe_oracle.c).  pts_idx_of_voxels (N,ox,oy,oz,mp), argmax / pooled (N,ox,oy,oz,C). */
+int pcfe_oracle_roiaware_pool3d_forward(const float* rois, int boxes_num, const float* pts, int64_t pts_num,
+                                        const float* pts_feature, int channels, int mp, int out_x, int out_y,
+                                        int out_z, int pool_method, int32_t* argmax, int32_t* pts_idx_of_voxels,
+                                        float* pooled);
+int pcfe_oracle_roiaware_pool3d_backward(const int32_t* pts_idx_of_voxels, const int32_t* argmax,
+                                         const float* grad_out, int boxes_num, int out_x, int out_y, int out_z,
+                                         int channels, int mp, int pool_method, int64_t pts_num, float* grad_in);
+
 /* glibc >= 2.28 sinf/cosf (ARM optimized-routines algorithm), restated.
  * sysdeps/ieee754/flt-32/{s_sinf.c,s_cosf.c,sincosf.h,s_sincosf_data.c}. */
 void pcfe_oracle_sincosf(float x, float* sinp, float* cosp);

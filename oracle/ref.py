@@ -73,3 +73,61 @@ def pcdet_points_in_boxes_cpu(points, boxes):
     out = points.new_zeros((boxes.shape[0], points.shape[0]), dtype=torch.int)
     _pcdet.points_in_boxes_cpu(boxes.float().contiguous(), points.float().contiguous(), out)
     return out
+
+
+_CUDA_SO = os.path.join(_HERE, "_ref", "detmatch_ref_cuda.so")
+_cuda = None
+
+
+def cuda_available():
+    return os.path.exists(_CUDA_SO)
+
+
+def cuda_module():
+    """oracle/_ref/detmatch_ref_cuda.so: the reference's UNMODIFIED voxelization_cuda.cu and
+    points_in_boxes_cuda.cu compiled for sm_100a (oracle/build_ref_cuda.py) -- the GPU-vs-GPU column."""
+    global _cuda
+    if _cuda is None:
+        import torch  # noqa: F401
+        spec = importlib.util.spec_from_file_location("detmatch_ref_cuda", _CUDA_SO)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        _cuda = m
+    return _cuda
+
+
+def cuda_voxelization(points, voxel_size, coors_range, max_points=35, max_voxels=20000):
+    """voxelize.py:13-58 (_Voxelization.forward) on CUDA tensors through the reference's own CUDA op."""
+    import torch
+    ext = cuda_module()
+    if max_points == -1 or max_voxels == -1:
+        coors = points.new_zeros(size=(points.size(0), 3), dtype=torch.int)
+        ext.dynamic_voxelize(points, coors, list(voxel_size), list(coors_range), 3)
+        return coors
+    voxels = points.new_zeros(size=(max_voxels, max_points, points.size(1)))
+    coors = points.new_zeros(size=(max_voxels, 3), dtype=torch.int)
+    num = points.new_zeros(size=(max_voxels,), dtype=torch.int)
+    voxel_num = ext.hard_voxelize(points, voxels, coors, num, list(voxel_size), list(coors_range),
+                                  max_points, max_voxels, 3)
+    return voxels[:voxel_num], coors[:voxel_num], num[:voxel_num]
+
+
+_ROIAWARE_SO = os.path.join(_HERE, "_ref", "detmatch_ref_roiaware.so")
+_roiaware = None
+
+
+def roiaware_available():
+    return os.path.exists(_ROIAWARE_SO)
+
+
+def roiaware_module():
+    """oracle/_ref/detmatch_ref_roiaware.so: the reference's own roiaware_pool3d_ext (forward / backward /
+    points_in_boxes_*) compiled for sm_100a from its unmodified sources (oracle/build_ref_roiaware.py)."""
+    global _roiaware
+    if _roiaware is None:
+        import torch  # noqa: F401
+        spec = importlib.util.spec_from_file_location("detmatch_ref_roiaware", _ROIAWARE_SO)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        _roiaware = m
+    return _roiaware

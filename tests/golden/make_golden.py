@@ -262,8 +262,28 @@ def scatter_cases():
           mean=torch.stack(mean).numpy(), max=torch.stack(mx).numpy())
 
 
+def roiaware_cases():
+    """RoIAwarePool3d: the reference TEST's literals and expectations
+    (tests/test_models/test_common_modules/test_roiaware_pool3d.py:9-40).  The reference has no CPU
+    implementation of the op (and this container has no GPU), so the golden holds the inputs, the two
+    sums the reference test asserts (rtol 1e-3) and the membership of every point derived with the
+    reference's compiled points_in_boxes_cpu -- the same inside-test text the pooling kernel carries
+    (roiaware_pool3d_kernel.cu:26-42)."""
+    rois = np.float32([[1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 0.3], [-10.0, 23.0, 16.0, 10, 20, 20, 0.5]])
+    pts = np.float32([[1, 2, 3.3], [1.2, 2.5, 3.0], [0.8, 2.1, 3.5], [1.6, 2.6, 3.6], [0.8, 1.2, 3.9], [-9.2, 21.0, 18.2],
+                      [3.8, 7.9, 6.3], [4.7, 3.5, -12.2], [3.8, 7.6, -2], [-10.6, -12.9, -20], [-16, -18, 9],
+                      [-21.3, -52, -5], [0, 0, 0], [6, 7, 8], [-2, -3, -4]])
+    inside = ref.points_in_boxes_cpu(torch.from_numpy(pts), torch.from_numpy(rois)).numpy()
+    print("roiaware KAT: points inside per RoI:", inside.sum(axis=1))
+    _save("roiaware_pool3d_kat", rois=rois, pts=pts, inside=inside, out_size=np.int32(4), max_pts_per_voxel=np.int32(128),
+          expected_sum_max=np.float32(51.100), expected_sum_avg=np.float32(49.750))
+
+
 if __name__ == "__main__":
     assert ref.available(), "run oracle/build_ref.py first"
+    if len(sys.argv) > 1 and sys.argv[1] == "roiaware":
+        roiaware_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "vfe":
         vfe_cases()
         sys.exit(0)
@@ -278,3 +298,4 @@ if __name__ == "__main__":
     vfe_cases()
     pcdet_cases()
     scatter_cases()
+    roiaware_cases()

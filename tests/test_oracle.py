@@ -237,3 +237,27 @@ def test_oracle_vs_reference_random_configs(seed):
     if ref.pcdet_available():
         exp = ref.pcdet_points_in_boxes_cpu(torch.from_numpy(pts[:, :3].copy()), torch.from_numpy(bxs)).numpy()
         assert_same_bits(oracle.pcdet_points_in_boxes_cpu(pts[:, :3].copy(), bxs), exp, "pcdet pib")
+
+
+def test_roiaware_pool3d_oracle_matches_reference_test_literals():
+    """tests/test_models/test_common_modules/test_roiaware_pool3d.py:9-40: the restatement reproduces the
+    sums the reference test asserts (rtol 1e-3) and puts exactly the points into the RoIs that the
+    reference's compiled points_in_boxes_cpu does."""
+    g = golden("roiaware_pool3d_kat")
+    n = int(g["out_size"])
+    mp = int(g["max_pts_per_voxel"])
+    pm, am, lists = oracle.roiaware_pool3d_forward(g["rois"], g["pts"], g["pts"], n, mp, 0)
+    pa, _, lists2 = oracle.roiaware_pool3d_forward(g["rois"], g["pts"], g["pts"], n, mp, 1)
+    assert pm.shape == (2, n, n, n, 3)
+    assert np.isclose(pm.sum(), g["expected_sum_max"], rtol=1e-3)
+    assert np.isclose(pa.sum(), g["expected_sum_avg"], rtol=1e-3)
+    assert np.array_equal(lists, lists2)
+    for b in range(2):
+        members = sorted(int(i) for v in lists[b].reshape(-1, mp) for i in v[1:1 + v[0]])
+        assert members == list(np.nonzero(g["inside"][b])[0])
+    # backward: max routes every pooled gradient to its argmax point, avg spreads it evenly
+    go = np.ones_like(pm)
+    gi = oracle.roiaware_pool3d_backward(lists, am, go, g["pts"].shape[0], 0)
+    assert gi.sum() == (am != -1).sum()
+    gi = oracle.roiaware_pool3d_backward(lists, am, go, g["pts"].shape[0], 1)
+    assert np.isclose(gi.sum(), 3 * (lists[..., 0] > 0).sum())
