@@ -49,14 +49,15 @@ int hvg_launch_slow(const HvBatch& b, int frames, uint32_t* overflow, size_t ove
                     int c, int max_points, int max_voxels, int32_t* voxel_num, cudaStream_t st, int mean,
                     int stage, const int32_t* vn_all, int f_first);
 
-int g_opt_bucket_avg = 1024;  // target points per bucket (tunable through pcfe_debug_set)
-int g_opt_bucket_variant = 0;  // 1: general kernels (cells + list arena) even where the record path applies
-int g_opt_no_fast_div = 0;      // 1: __fdiv_rn for every point (no hoisted reciprocal)
-int g_opt_expand_variant = 0;  // 1: un-pipelined fixed-P expansion kernel
-int g_opt_expand_prefetch = 1;  // frames of L2 prefetch distance in the expansion (0 = off)
-int g_opt_pdl = 1;              // programmatic dependent launch between the record path's kernels
-int g_opt_expand_ctas = 0;      // > 0: persistent expansion with this many CTAs per SM
-int g_opt_cluster = 0;          // 1: record path with one thread-block cluster per frame (hv_cluster.cuh) -- measured slower, see profiles/r02_cluster_*
+Knob g_opt_bucket_avg{1024};  // target points per bucket (tunable through pcfe_debug_set)
+Knob g_opt_bucket_variant{0};  // 1: general kernels (cells + list arena) even where the record path applies
+Knob g_opt_no_fast_div{0};      // 1: __fdiv_rn for every point (no hoisted reciprocal)
+Knob g_opt_expand_variant{0};  // 1: un-pipelined fixed-P expansion kernel
+Knob g_opt_expand_prefetch{1};  // frames of L2 prefetch distance in the expansion (0 = off)
+Knob g_opt_pdl{1};              // programmatic dependent launch between the record path's kernels
+Knob g_opt_expand_ctas{0};      // > 0: persistent expansion with this many CTAs per SM
+Knob g_opt_overlap{1};          // 0: waves of a multi-wave batch run one after the other on the caller's stream
+Knob g_opt_cluster{0};          // 1: record path with one thread-block cluster per frame (hv_cluster.cuh) -- measured slower, see profiles/r02_cluster_*
 
 namespace {
 
@@ -1303,6 +1304,9 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
 #ifndef PCFE_EXP_REC_MINB
 #define PCFE_EXP_REC_MINB 8
 #endif
+#ifndef PCFE_EXP_SPLIT
+#define PCFE_EXP_SPLIT 1  // > 1: a tile's output words are fetched and stored in that many groups
+#endif
 #ifndef PCFE_EXP_MEAN_MINB  // the mean epilogue keeps C words per lane instead of P * C
 #define PCFE_EXP_MEAN_MINB 8
 #endif
@@ -1398,7 +1402,8 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     }
     __syncwarp();
     // rows of this tile, lane = output word
-    float val[MEAN ? C : W];
+    constexpr int HW = (W + PCFE_EXP_SPLIT - 1) / PCFE_EXP_SPLIT;  // output words per lane fetched together
+    float val[MEAN ? C : HW];
     if (MEAN) {
       // lane = output word of the (32, C) mean tile: word o = lane + 32 r is feature o % C of voxel
       // o / C, whose point indices sit in that lane's registers (shuffles, no shared memory); the
@@ -1424,7 +1429,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
       }
     } else {
 #pragma unroll
-    for (int k = 0; k < W; ++k) {
+    for (int k = 0; k < HW; ++k) {
       const uint32_t src = eff[lane + 32 * k];  // word lane + 32 k of the tile
       val[k] = 0.0f;
       if (src != kEmpty) val[k] = __ldg(pts + src);
@@ -1458,13 +1463,27 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
         if (lane + 32 * r < nvox * C) mdst[lane + 32 * r] = val[r];
     } else {
     float* __restrict__ dst = fr.voxels + (off + v0) * W;
-    if (nvox == 32) {
 #pragma unroll
-      for (int k = 0; k < W; ++k) __stcs(dst + lane + 32 * k, val[k]);
-    } else {
+    for (int h0 = 0; h0 < W; h0 += HW) {
+      if (h0 > 0) {  // PCFE_EXP_SPLIT > 1: the next group of words (fewer live registers per warp)
 #pragma unroll
-      for (int k = 0; k < W; ++k)
-        if (lane + 32 * k < nvox * W) __stcs(dst + lane + 32 * k, val[k]);
+        for (int k = 0; k < HW; ++k) {
+          val[k] = 0.0f;
+          if (h0 + k < W) {
+            const uint32_t src = eff[lane + 32 * (h0 + k)];
+            if (src != kEmpty) val[k] = __ldg(pts + src);
+          }
+        }
+      }
+      if (nvox == 32) {
+#pragma unroll
+        for (int k = 0; k < HW; ++k)
+          if (h0 + k < W) __stcs(dst + lane + 32 * (h0 + k), val[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < HW; ++k)
+          if (h0 + k < W && lane + 32 * (h0 + k) < nvox * W) __stcs(dst + lane + 32 * (h0 + k), val[k]);
+      }
     }
     }
     if (!PACK) {  // coordinates: 3 * nvox words, contiguous; v0 % 32 == 0 keeps the run 16-byte aligned
@@ -1674,7 +1693,7 @@ int hvb_make_plan(int64_t n_max, int c, const float vs[3], const float rg[6], in
   p->g = p->slow.g;
   p->npad = p->slow.npad;
   p->words = p->slow.words;
-  const int target = std::max(64, std::min(g_opt_bucket_avg, 1400));
+  const int target = std::max(64, std::min((int)g_opt_bucket_avg, 1400));
   int lg = 0;
   while ((1 << lg) < kMaxBuckets && ((int64_t)target << lg) < n_max) ++lg;
   p->log2_nb = lg;
@@ -1760,7 +1779,7 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
   const int pack = (mode & kHvPack) ? 1 : 0;
   const int nwaves = (num_frames + wave - 1) / wave;
   // (packed output: a wave places its rows behind those of the waves before it -- one stream)
-  const bool overlap = nbuf >= 2 && nwaves >= 2 && !pack;
+  const bool overlap = nbuf >= 2 && nwaves >= 2 && !pack && g_opt_overlap != 0;
   AuxStreams* aux = nullptr;
   if (overlap) {
     int rc = get_aux(device, &aux);
@@ -1912,7 +1931,7 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
         const bool pdl = g_opt_pdl != 0;
 #define PCFE_LAUNCH_EXPAND_REC(CC, MM, PP)                                                                      \
   PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<CC, MM, PP>, dim3(egrid), dim3(kExpThreads), 0, st, pdl, b, w, p.g, \
-                           fdiv, vn, wv, g_opt_expand_prefetch, coors_vec, tiles_x, (const int32_t*)voxel_num, f0))
+                           fdiv, vn, wv, (int)g_opt_expand_prefetch, coors_vec, tiles_x, (const int32_t*)voxel_num, f0))
 #define PCFE_LAUNCH_EXPAND_REC_C(CC)                                \
   do {                                                              \
     if (mean && pack) PCFE_LAUNCH_EXPAND_REC(CC, true, true);       \

@@ -109,6 +109,9 @@ hvc_group_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const G
   const uint32_t cntmat_saddr = smem_u32(sm.cntmat);
   const uint32_t tot_saddr = smem_u32(sm.tot);
   pdl_wait();  // the scratch written below may still be read by the previous launch sequence
+  // every CTA of the cluster has started (its shared memory exists) before the first remote store
+  cluster_arrive();
+  cluster_wait();
 
 #pragma unroll 1
   for (int f = (int)cluster_id(); f < frames; f += (int)cluster_count()) {

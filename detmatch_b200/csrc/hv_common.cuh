@@ -164,8 +164,8 @@ int hvb_run(const pcfe_frame_t* frames, int num_frames, int c, const HvBucketPla
             int max_points, int max_voxels, int32_t* voxel_num, void* workspace, int wave,
             int nbuf, int device, cudaStream_t st, int mode = 0);
 
-extern int g_opt_hv_path;         // 0 auto, 1 force global path, 2 force bucket path
-extern int g_opt_hv_wave;         // frames per wave (0 = automatic)
-extern int g_opt_force_overflow;  // 1: bucket path treats every frame as overflowed (tests)
+extern Knob g_opt_hv_path;         // 0 auto, 1 force global path, 2 force bucket path
+extern Knob g_opt_hv_wave;         // frames per wave (0 = automatic)
+extern Knob g_opt_force_overflow;  // 1: bucket path treats every frame as overflowed (tests)
 
 }  // namespace pcfe

@@ -17,7 +17,7 @@
 #include "pcfe_common.cuh"
 
 namespace pcfe {
-int g_opt_pib_grid = 1;  // 0: brute-force first-hit assignment for every frame (test knob)
+Knob g_opt_pib_grid{1};  // 0: brute-force first-hit assignment for every frame (test knob)
 namespace {
 
 #include "pib_dev.cuh"

@@ -42,18 +42,19 @@ void prof_end(cudaStream_t st) {
 }
 
 
-int g_opt_hv_path = 0;
-int g_opt_force_overflow = 0;
-int g_opt_hv_wave = 0;
-extern int g_opt_bucket_avg;
-extern int g_opt_bucket_variant;
-extern int g_opt_expand_variant;
-extern int g_opt_expand_ctas;
-extern int g_opt_cluster;
-extern int g_opt_pdl;
-extern int g_opt_pib_grid;
-extern int g_opt_no_fast_div;
-extern int g_opt_expand_prefetch;
+Knob g_opt_hv_path{0};
+Knob g_opt_force_overflow{0};
+Knob g_opt_hv_wave{0};
+extern Knob g_opt_bucket_avg;
+extern Knob g_opt_bucket_variant;
+extern Knob g_opt_expand_variant;
+extern Knob g_opt_expand_ctas;
+extern Knob g_opt_cluster;
+extern Knob g_opt_overlap;
+extern Knob g_opt_pdl;
+extern Knob g_opt_pib_grid;
+extern Knob g_opt_no_fast_div;
+extern Knob g_opt_expand_prefetch;
 
 namespace {
 
@@ -149,7 +150,8 @@ int choose_path(int64_t n_max, int c, const float vs[3], const float rg[6], int 
 // only ~1 % (every kernel already fills the SMs), so overlap is used only when a batch needs
 // more than one wave anyway.
 int auto_wave(size_t per_frame, int num_frames, bool bucket) {
-  if (g_opt_hv_wave > 0) return std::min(std::min(g_opt_hv_wave, kMaxWave), std::max(num_frames, 1));
+  const int knob_wave = g_opt_hv_wave;
+  if (knob_wave > 0) return std::min(std::min(knob_wave, kMaxWave), std::max(num_frames, 1));
   size_t w = kL2ScratchBudget / per_frame;
   w = std::max<size_t>(1, std::min<size_t>(w, (size_t)kMaxWave));
   (void)bucket;
@@ -456,7 +458,8 @@ extern "C" int pcfe_debug_axis_sweep(float lo, float vs, float hi, uint64_t* out
 
 // Test / tuning knobs (every setting computes the same, bit-exact results; they select code paths
 // and launch parameters): "hv_path" (0 auto, 1 global-memory path, 2 bucket path),
-// "hv_cluster" (0: record path as a launch sequence instead of one cluster per frame), "hv_force_overflow" (1: every frame also runs the overflow fallback), "hv_bucket_avg"
+// "hv_cluster" (1: one cluster per frame instead of the record path's launch sequence), "hv_overlap" (0: the
+// waves of a multi-wave batch run one after the other instead of on two internal streams), "hv_force_overflow" (1: every frame also runs the overflow fallback), "hv_bucket_avg"
 // (target points per bucket), "hv_wave" (frames per launch sequence), "hv_bucket_variant" (1: general
 // kernels instead of the record path), "hv_expand_variant" (1: un-pipelined expansion kernels),
 // "hv_expand_prefetch" (frames of L2 prefetch distance), "hv_no_fast_div", "hv_pdl",
@@ -464,6 +467,10 @@ extern "C" int pcfe_debug_axis_sweep(float lo, float vs, float hi, uint64_t* out
 // PCFE_ERR_SHAPE for an unknown name.
 extern "C" int pcfe_debug_set(const char* name, int value) {
   if (!name) return PCFE_ERR_NULL;
+#ifdef PCFE_NO_DEBUG_KNOBS
+  (void)value;
+  return PCFE_ERR_SHAPE;  // production build: the knobs are not reachable
+#endif
   if (!strcmp(name, "hv_path")) g_opt_hv_path = value;
   else if (!strcmp(name, "hv_force_overflow")) g_opt_force_overflow = value;
   else if (!strcmp(name, "hv_bucket_avg")) g_opt_bucket_avg = value;
@@ -476,6 +483,7 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "pib_grid")) g_opt_pib_grid = value;
   else if (!strcmp(name, "hv_expand_ctas")) g_opt_expand_ctas = value;
   else if (!strcmp(name, "hv_cluster")) g_opt_cluster = value;
+  else if (!strcmp(name, "hv_overlap")) g_opt_overlap = value;
   else return PCFE_ERR_SHAPE;
   return PCFE_OK;
 }

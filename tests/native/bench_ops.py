@@ -164,8 +164,46 @@ def pcdet_pib():
     report(f"C3-shape OpenPCDet points_in_boxes_gpu {B}x{M}x{T}", ms, B * M * 16 + B * T * 28, B * M * T, "pairs")
 
 
+def roiaware():
+    """PartA2-shape RoI-aware pooling (128 RoIs, 16 384 points, 128 channels, 14^3 voxels, 128 slots), ours
+    vs the reference's own kernel compiled for sm_100a (oracle/_ref/detmatch_ref_roiaware.so), wrapper
+    allocations included on both sides (the reference zero-fills its three work tensors)."""
+    from oracle import ref
+    g = torch.Generator().manual_seed(1)
+    n, m, c, o, mp = 128, 16384, 128, 14, 128
+    rois = torch.cat([torch.rand((n, 2), generator=g) * 80 - 40, torch.rand((n, 1), generator=g) * 2 - 2,
+                      torch.rand((n, 3), generator=g) * 3 + 1, (torch.rand((n, 1), generator=g) * 2 - 1) * 3.14], dim=1).cuda()
+    pts = torch.cat([torch.rand((m, 2), generator=g) * 80 - 40, torch.rand((m, 1), generator=g) * 4 - 2], dim=1)
+    own = torch.randint(0, n, (m // 2,), generator=g)
+    pts[:m // 2, :2] = rois.cpu()[own, :2] + (torch.rand((m // 2, 2), generator=g) - 0.5)
+    pts = pts.cuda()
+    feats = torch.rand((m, c), generator=g).cuda()
+    for mode in (0, 1):
+        def ours():
+            pooled = torch.empty((n, o, o, o, c), device="cuda")
+            argmax = torch.empty((n, o, o, o, c), dtype=torch.int32, device="cuda")
+            lists = torch.empty((n, o, o, o, mp), dtype=torch.int32, device="cuda")
+            roiaware_pool3d_ext.forward(rois, pts, feats, argmax, lists, pooled, mode)
+        ms = timeit(ours, reps=10, warm=2)
+        nbytes = n * o ** 3 * c * (8 if mode == 0 else 4) + m * (12 + c * 4)
+        report(f"RoIAwarePool3d fwd mode {mode} {n}x{m}x{c} out {o}", ms, nbytes, n * m, "pairs")
+        if ref.roiaware_available():
+            ext = ref.roiaware_module()
+
+            def theirs():
+                pooled = torch.zeros((n, o, o, o, c), device="cuda")
+                argmax = torch.zeros((n, o, o, o, c), dtype=torch.int32, device="cuda")
+                lists = torch.zeros((n, o, o, o, mp), dtype=torch.int32, device="cuda")
+                ext.forward(rois, pts, feats, argmax, lists, pooled, mode)
+            ms_r = timeit(theirs, reps=3, warm=1)
+            print(f"       reference kernel (sm_100a build): {ms_r:.3f} ms  -> {ms_r / ms:.1f}x")
+
+
 if __name__ == "__main__":
     torch.cuda.set_device(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "roiaware":
+        roiaware()
+        sys.exit(0)
     hard("C1", 16)
     dynamic()
     pib()
@@ -174,3 +212,4 @@ if __name__ == "__main__":
     hard("C4")
     hard_mean("C4")
     hard("C5", 16)
+    roiaware()
