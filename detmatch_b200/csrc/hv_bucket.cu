@@ -56,6 +56,7 @@ Knob g_opt_expand_variant{0};  // 1: un-pipelined fixed-P expansion kernel
 Knob g_opt_expand_prefetch{1};  // frames of L2 prefetch distance in the expansion (0 = off)
 Knob g_opt_pdl{1};              // programmatic dependent launch between the record path's kernels
 Knob g_opt_expand_ctas{0};      // > 0: persistent expansion with this many CTAs per SM
+Knob g_opt_bin_small{2};        // partition tile: 0 = 4096 points, 1 = 1024 points, 2 = by batch size
 Knob g_opt_overlap{1};          // 0: waves of a multi-wave batch run one after the other on the caller's stream
 Knob g_opt_cluster{0};          // 1: record path with one thread-block cluster per frame (hv_cluster.cuh) -- measured slower, see profiles/r02_cluster_*
 
@@ -110,6 +111,8 @@ constexpr int kCtlList = 0, kCtlCell = 1, kCtlOverflow = 2;
 constexpr int kBinThreads = PCFE_BIN_THREADS;
 constexpr int kBinPerThread = PCFE_BIN_PER_THREAD;
 constexpr int kBinTile = kBinThreads * kBinPerThread;  // 4096 points
+constexpr int kBinPerThreadSmall = 4;
+constexpr int kBinTileSmall = kBinThreads * kBinPerThreadSmall;  // 1024 points
 constexpr int kMaxBuckets = 1024;
 
 __global__ void hvb_zero_kernel(uint4* __restrict__ p, const size_t n16) {
@@ -117,15 +120,19 @@ __global__ void hvb_zero_kernel(uint4* __restrict__ p, const size_t n16) {
     p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// CT = features per point at compile time (row loads become base + immediate), 0 = run time
-template <int CT>
-__global__ void __launch_bounds__(kBinThreads, PCFE_BIN_MINB)
+// CT = features per point at compile time (row loads become base + immediate), 0 = run time.
+// PT = points per thread: 16 (4096-point tiles) for batches that fill the SMs several times over, 4
+// (1024-point tiles) for small batches, where one CTA's latency chain IS the kernel's duration
+// (8 C4 frames: 14.8 us with 352 CTAs of 4096 points, profiles/r02_b8_launches.csv).
+template <int CT, int PT>
+__global__ void __launch_bounds__(kBinThreads, PT >= 16 ? PCFE_BIN_MINB : 6)
 hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
                const int c_rt, const int use_fast_div) {
   const int c = CT > 0 ? CT : c_rt;
   __shared__ uint32_t hist[kMaxBuckets];   // entries of this tile per bucket
   __shared__ uint32_t soff[kMaxBuckets];   // exclusive prefix of hist (staging offsets)
   __shared__ uint32_t delta[kMaxBuckets];  // (entry position in the frame's ent array) - (staging position)
+  constexpr int kBinPerThread = PT, kBinTile = kBinThreads * PT;
   __shared__ uint2 stage[kBinTile];
   __shared__ uint32_t warp_sums[33];
   __shared__ uint32_t s_overflow;
@@ -1887,11 +1894,23 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
     if (!clustered) {
       ProfScope ps("hvb_bin", st);
       // (a wave of empty frames still runs the sequence: one idle tile, voxel_num = 0 from the scan)
-      const dim3 grid((unsigned)std::max<int64_t>((wn_max + kBinTile - 1) / kBinTile, 1), (unsigned)wv);
+      const int64_t big_tiles = std::max<int64_t>((wn_max + kBinTile - 1) / kBinTile, 1);
+      // small batches: 1024-point tiles, four times the CTAs with a quarter of the latency chain each
+      const int bin_small = g_opt_bin_small;
+      const bool small = bin_small == 1 || (bin_small != 0 && big_tiles * wv < 2 * 148 * PCFE_BIN_MINB);
+      const int tile = small ? kBinTileSmall : kBinTile;
+      const dim3 grid((unsigned)std::max<int64_t>((wn_max + tile - 1) / tile, 1), (unsigned)wv);
       const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
-      if (c == 4) PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<4>, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c, fdiv));
-      else if (c == 5) PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<5>, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c, fdiv));
-      else PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<0>, grid, dim3(kBinThreads), 0, st, g_opt_pdl != 0, b, w, p.g, c, fdiv));
+      const bool pdl = g_opt_pdl != 0;
+#define PCFE_LAUNCH_BIN(CC)                                                                                              \
+  do {                                                                                                                   \
+    if (small) PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<CC, kBinPerThreadSmall>, grid, dim3(kBinThreads), 0, st, pdl, b, w, p.g, c, fdiv)); \
+    else PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<CC, kBinPerThread>, grid, dim3(kBinThreads), 0, st, pdl, b, w, p.g, c, fdiv));            \
+  } while (0)
+      if (c == 4) PCFE_LAUNCH_BIN(4);
+      else if (c == 5) PCFE_LAUNCH_BIN(5);
+      else PCFE_LAUNCH_BIN(0);
+#undef PCFE_LAUNCH_BIN
       PCFE_LAUNCH_CHECK();
     }
     int rc = PCFE_OK;
