@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=0, help="frames per step over all GPUs (default: the config's 64)")
+    ap.add_argument("--order", default="shuffled", choices=["shuffled", "sweep"],
+                    help="point order of the synthetic frames: PointShuffle'd (the configs) or a spinning sensor's firing order")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the step's frames are split over the GPUs (default); weak: every GPU gets all of them")
     ap.add_argument("--workload", default=WORKLOAD, choices=["C1", "C4", "C5"])
@@ -256,7 +258,7 @@ def _config_dict(cfg, args, frames_per_step):
             "frames_per_step": frames_per_step, "points_per_frame": cfg["n"], "features": cfg["c"],
             "voxel_size": cfg["voxel_size"], "point_cloud_range": cfg["point_cloud_range"],
             "max_num_points": cfg["max_num_points"], "max_voxels": cfg["max_voxels"],
-            "generator": "LiDAR-like (SURVEY 8(d)), seed = 1000*config + frame",
+            "generator": "LiDAR-like (SURVEY 8(d)), seed = 1000*config + frame" + ("" if args.order == "shuffled" else ", sweep order"),
             "l2": "inputs+outputs per step (~0.94 GB at 64 C4 frames) exceed the 126 MB L2; no explicit flush",
             "sharding": "frames split over the GPUs in contiguous blocks, no collective"}
 
@@ -324,7 +326,8 @@ def run_ours(args):
         _cabi.debug_set(name, int(val))
 
     # synthetic frames, generated on the host
-    host = [synth.lidar_frame(N, C, synth.seed_for(cfg["index"], fid), cfg["r_max"]).pin_memory() for fid in frame_ids]
+    host = [synth.lidar_frame(N, C, synth.seed_for(cfg["index"], fid), cfg["r_max"], order=args.order).pin_memory()
+            for fid in frame_ids]
     pts = [h.to(dev, non_blocking=True) for h in host]
     torch.cuda.synchronize(dev)
     plan = HardVoxelizeBatchPlan([N] * F, C, cfg["voxel_size"], cfg["point_cloud_range"], P, V, dev,

@@ -56,6 +56,7 @@ Knob g_opt_expand_variant{0};  // 1: un-pipelined fixed-P expansion kernel
 Knob g_opt_expand_prefetch{1};  // frames of L2 prefetch distance in the expansion (0 = off)
 Knob g_opt_pdl{1};              // programmatic dependent launch between the record path's kernels
 Knob g_opt_expand_ctas{0};      // > 0: persistent expansion with this many CTAs per SM
+Knob g_opt_warp_dedup{0};       // 1: warp-level key de-duplication (__match_any_sync) in front of the bucket table
 Knob g_opt_bin_small{2};        // partition tile: 0 = 4096 points, 1 = 1024 points, 2 = by batch size
 Knob g_opt_overlap{1};          // 0: waves of a multi-wave batch run one after the other on the caller's stream
 Knob g_opt_cluster{0};          // 1: record path with one thread-block cluster per frame (hv_cluster.cuh) -- measured slower, see profiles/r02_cluster_*
@@ -434,6 +435,14 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
 //     cursors or block scan.
 // dynamic shared memory: ents[cap] (uint2) | hkey[S] | head[S] | slotlist[cap] (u16)
 // ------------------------------------------------------------------------------------------
+// DEDUP: entries of a warp that carry the same cell key are found with __match_any_sync BEFORE the table is
+// touched: the group's lowest lane probes / claims the slot for all of them (one CAS loop per group), the
+// group links itself into a private chain (lane -> next lower peer, no atomics) and its lowest lane pushes
+// the whole chain with ONE atomicExch.  Pays when neighbouring entries share cells -- un-shuffled
+// (sweep-ordered) frames: 46 % of the points of a 4096-point tile repeat a cell of the tile, and a tile's
+// entries of one bucket sit next to each other -- and costs a few instructions per entry when they do not
+// (PointShuffle'd frames: 0.03 % in-warp repeats); `hv_warp_dedup`, measured in profiles/r02_summary.md.
+template <bool DEDUP>
 __global__ void __launch_bounds__(kBucketThreads)
 hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const int spec /* entries copied before ne is known */) {
   constexpr int PT = 5;
@@ -496,7 +505,13 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
     const uint32_t key = valid ? ents[e].x : 0u;
     uint32_t s = ((key * kGold) >> sshift) & smask;
     bool claimed = false;
-    if (valid) {
+    uint32_t peers = 1u << lane;  // lanes of this warp whose entry has the same key (DEDUP)
+    if (DEDUP) {  // (lanes past the end take part with a dummy value and are masked out of every group)
+      const uint32_t vmask = __ballot_sync(0xFFFFFFFFu, valid);
+      peers = __match_any_sync(0xFFFFFFFFu, valid ? key : (0xFFFFFF00u | lane)) & (valid ? vmask : ~0u);
+    }
+    const int leader = __ffs(peers) - 1;
+    if (valid && (int)lane == leader) {
       while (true) {  // one CAS per probe: claims the slot, finds the cell, or reports a collision
         const uint32_t old = atomicCAS(&hkey[s], kEmpty, key);
         claimed = old == kEmpty;
@@ -504,6 +519,7 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
         s = (s + 1u) & smask;
       }
     }
+    if (DEDUP) s = __shfl_sync(0xFFFFFFFFu, s, leader);
     const uint32_t cm = __ballot_sync(0xFFFFFFFFu, claimed);
     if (cm) {  // claimed slots join the cell list: one shared-memory atomic per warp, issued by the
                // lane elect.sync picks (ptxas re-aggregates an atomic under an ordinary predicate)
@@ -515,7 +531,15 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
       base = __shfl_sync(0xFFFFFFFFu, base, leader);
       if (claimed) slotlist[base + __popc(cm & lane_lt)] = (uint16_t)s;
     }
-    if (valid) ents[e].x = atomicExch(&head[s], (uint32_t)e);  // link: previous head of the cell, or kNil
+    if (valid) {
+      if (!DEDUP) {
+        ents[e].x = atomicExch(&head[s], (uint32_t)e);  // link: previous head of the cell, or kNil
+      } else if ((int)lane == leader) {  // the group's chain: highest lane -> ... -> this lane -> previous head
+        ents[e].x = atomicExch(&head[s], (uint32_t)(e - (int)lane + (31 - __clz(peers))));
+      } else {
+        ents[e].x = (uint32_t)(e - (int)lane + (31 - __clz(peers & lane_lt)));
+      }
+    }
   }
   __syncthreads();
 
@@ -1833,7 +1857,10 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
     int rc = ensure_dyn_smem((const void*)hvb_bucket_small_kernel<5>, 0, device, p.smem_bucket);
     if (rc == PCFE_OK) rc = ensure_dyn_smem((const void*)hvb_bucket_small_kernel<8>, 1, device, p.smem_bucket);
     if (rc == PCFE_OK)
-      rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel, 2, device,
+      rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel<false>, 2, device,
+                           (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2);
+    if (rc == PCFE_OK)
+      rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel<true>, 4, device,
                            (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2);
     if (rc != PCFE_OK) return rc;
   }
@@ -1922,7 +1949,10 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
         // speculative first copy: the average bucket fill of the largest frame, rounded up to 64
         // entries, never more than the region
         const int spec = (int)std::min<int64_t>(p.cap, std::max<int64_t>((((wn_max + p.nb - 1) / p.nb) + 63) / 64 * 64, 64));
-        PCFE_CUDA_TRY(launch_pdl(hvb_bucket_rec_kernel, grid, dim3(kBucketThreads), smem_rec, st, g_opt_pdl != 0, w, pe, spec));
+        if (g_opt_warp_dedup)
+          PCFE_CUDA_TRY(launch_pdl(hvb_bucket_rec_kernel<true>, grid, dim3(kBucketThreads), smem_rec, st, g_opt_pdl != 0, w, pe, spec));
+        else
+          PCFE_CUDA_TRY(launch_pdl(hvb_bucket_rec_kernel<false>, grid, dim3(kBucketThreads), smem_rec, st, g_opt_pdl != 0, w, pe, spec));
         PCFE_LAUNCH_CHECK();
       }
       if (!clustered) {

@@ -52,6 +52,7 @@ extern Knob g_opt_expand_ctas;
 extern Knob g_opt_cluster;
 extern Knob g_opt_overlap;
 extern Knob g_opt_bin_small;
+extern Knob g_opt_warp_dedup;
 extern Knob g_opt_pdl;
 extern Knob g_opt_pib_grid;
 extern Knob g_opt_no_fast_div;
@@ -461,7 +462,8 @@ extern "C" int pcfe_debug_axis_sweep(float lo, float vs, float hi, uint64_t* out
 // and launch parameters): "hv_path" (0 auto, 1 global-memory path, 2 bucket path),
 // "hv_cluster" (1: one cluster per frame instead of the record path's launch sequence), "hv_overlap" (0: the
 // waves of a multi-wave batch run one after the other instead of on two internal streams), "hv_bin_small"
-// (partition tile: 0 = 4096 points, 1 = 1024, 2 = by batch size), "hv_force_overflow" (1: every frame also runs the overflow fallback), "hv_bucket_avg"
+// (partition tile: 0 = 4096 points, 1 = 1024, 2 = by batch size), "hv_warp_dedup" (1: __match_any_sync key
+// de-duplication in front of the bucket table), "hv_force_overflow" (1: every frame also runs the overflow fallback), "hv_bucket_avg"
 // (target points per bucket), "hv_wave" (frames per launch sequence), "hv_bucket_variant" (1: general
 // kernels instead of the record path), "hv_expand_variant" (1: un-pipelined expansion kernels),
 // "hv_expand_prefetch" (frames of L2 prefetch distance), "hv_no_fast_div", "hv_pdl",
@@ -487,6 +489,7 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_cluster")) g_opt_cluster = value;
   else if (!strcmp(name, "hv_overlap")) g_opt_overlap = value;
   else if (!strcmp(name, "hv_bin_small")) g_opt_bin_small = value;
+  else if (!strcmp(name, "hv_warp_dedup")) g_opt_warp_dedup = value;
   else return PCFE_ERR_SHAPE;
   return PCFE_OK;
 }

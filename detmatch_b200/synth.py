@@ -36,8 +36,11 @@ def seed_for(config_index, frame):
     return 1000 * int(config_index) + int(frame)
 
 
-def lidar_frame(n, c, seed, r_max=80.0):
-    """One LiDAR-like frame, float32 (n, c), randomly permuted (mirrors PointShuffle).
+def lidar_frame(n, c, seed, r_max=80.0, order="shuffled"):
+    """One LiDAR-like frame, float32 (n, c), randomly permuted (mirrors PointShuffle; the default and
+    what every BASELINE config uses) or, with ``order="sweep"``, in the firing order of a spinning
+    sensor (azimuth step by azimuth step, the 64 beams of a step together: what an un-shuffled test-time
+    frame looks like -- consecutive points are neighbours and often share a voxel).
 
     64 beams between -24.8 and +2 degrees, uniform azimuth; each return is the nearer of the
     ground plane (sensor 1.73 m above it) and an obstacle at r = 2 + (r_max-2)*u^2.
@@ -59,6 +62,11 @@ def lidar_frame(n, c, seed, r_max=80.0):
         cols.append(torch.rand(n, generator=g, dtype=torch.float64))
     pts = torch.stack(cols, dim=1).to(torch.float32)
     perm = torch.randperm(n, generator=g)
+    if order == "sweep":
+        step = torch.floor((az + math.pi) / (2.0 * math.pi) * 2650.0)  # ~0.136 degree azimuth steps
+        perm = torch.argsort(step * 64.0 + beam, stable=True)
+    else:
+        assert order == "shuffled"
     return pts[perm].contiguous()
 
 

@@ -15,10 +15,11 @@ pytestmark = pytest.mark.gpu
 KITTI = [0, -40, -3, 70.4, 40, 1]
 
 
-@pytest.fixture(autouse=True, params=["launches", "cluster", "bucket_general", "global", "fallback"])
+@pytest.fixture(autouse=True, params=["launches", "dedup", "cluster", "bucket_general", "global", "fallback"])
 def hv_mode(request):
     """Every test runs against all hard-voxelize implementations behind the one entry point: the
     bucket path as a launch sequence (default; record kernels where P == 5 and C = 4 / 5), the record
+    same with warp-level __match_any_sync key de-duplication in front of the bucket table, the record
     path with one thread-block cluster per frame (hv_cluster.cuh: measured slower, kept as the
     round-2 DSMEM experiment), the general bucket kernels (register-sorted chains for P <= 8, bitonic ranks
     otherwise), the global-memory path, and the default path with every frame forced through its
@@ -27,11 +28,13 @@ def hv_mode(request):
     mode = request.param
     _cabi.debug_set("hv_path", 1 if mode == "global" else 0)
     _cabi.debug_set("hv_cluster", 1 if mode == "cluster" else 0)
+    _cabi.debug_set("hv_warp_dedup", 1 if mode == "dedup" else 0)
     _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "bucket_general" else 0)
     yield mode
     _cabi.debug_set("hv_path", 0)
     _cabi.debug_set("hv_cluster", 0)
+    _cabi.debug_set("hv_warp_dedup", 0)
     _cabi.debug_set("hv_force_overflow", 0)
     _cabi.debug_set("hv_bucket_variant", 0)
 
@@ -316,6 +319,24 @@ def test_full_c5_batch_16_frames_vs_oracle():
     for k in range(F):
         ev, ec, en = _oracle_frame("C5", 5, k)
         assert counts[k] == len(en) and counts[k] > 10000
+        assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"frame {k} coors")
+        assert_same_bits(num[k, :counts[k]].cpu().numpy(), en, f"frame {k} num")
+        assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"frame {k} voxels")
+
+
+@pytest.mark.parametrize("cfg_name,ci", [("C4", 4), ("C1", 1)])
+def test_sweep_ordered_frames_vs_oracle(cfg_name, ci):
+    """Un-shuffled frames in a spinning sensor's firing order (test-time input: consecutive points share
+    voxels; the warp-level key de-duplication has real groups to merge here): full-size frames against the
+    oracle on every path."""
+    cfg = synth.CONFIGS[cfg_name]
+    pts = [synth.lidar_frame(cfg["n"], cfg["c"], synth.seed_for(ci, 70 + k), cfg["r_max"], order="sweep") for k in range(3)]
+    P, V = cfg["max_num_points"], cfg["max_voxels"]
+    vox, coors, num, vnum = voxelize_batch([p.cuda() for p in pts], cfg["voxel_size"], cfg["point_cloud_range"], P, V, sync=False)
+    counts = vnum.cpu().tolist()
+    for k, p in enumerate(pts):
+        ev, ec, en = oracle.hard_voxelize(p.numpy(), cfg["voxel_size"], cfg["point_cloud_range"], P, V)
+        assert counts[k] == len(en)
         assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"frame {k} coors")
         assert_same_bits(num[k, :counts[k]].cpu().numpy(), en, f"frame {k} num")
         assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"frame {k} voxels")
