@@ -33,9 +33,13 @@ KEPT_POINTS_PER_FRAME = {"C4": 156_000}  # points surviving the max_points cap (
 METRIC = "hard_voxelize_throughput"
 UNIT = "Mpoints/s"
 # ProfScope name of the library (pcfe_profile_report) -> kernel name in an ncu report
-SCOPE_TO_KERNEL = {"memset_ctl": "hvb_zero_kernel", "hvb_bin": "hvb_bin_kernel", "hvb_bucket": "hvb_bucket_rec_kernel",
-                   "hvb_scan_firsts": "hvb_scan_firsts_kernel", "hvb_expand": "hvb_expand_rec_kernel",
-                   "hv_slow_fallback": "hvg_slow_frame_kernel", "hvc_group": "hvc_group_kernel"}
+SCOPE_TO_KERNEL = {"memset_ctl": ["hvb_zero_kernel"], "hvb_bin": ["hvb_bin_kernel"],
+                   "hvb_bucket": ["hvb_bucket_rec_kernel", "hvb_bucket_rank_kernel", "hvb_bucket_small_kernel"],
+                   "hvb_scan_firsts": ["hvb_scan_firsts_kernel"], "hv_scan_flags": ["hv_scan_flags_kernel"],
+                   "hvb_order": ["hvb_order_kernel"],
+                   "hvb_expand": ["hvb_expand_rec_kernel", "hvb_expand_words_kernel", "hvb_expand_pipe_kernel",
+                                  "hvb_expand_fixed_kernel", "hvb_expand_kernel"],
+                   "hv_slow_fallback": ["hvg_slow_frame_kernel"], "hvc_group": ["hvc_group_kernel"]}
 
 
 def ncu_traffic(workload, scopes):
@@ -49,12 +53,17 @@ def ncu_traffic(workload, scopes):
         return None, {}, "no profiles/*_traffic_%s.json" % workload
     d = json.load(open(files[-1]))
     per = d.get("kernels", {})
-    missing = [sc for sc in scopes if SCOPE_TO_KERNEL.get(sc) not in per and sc not in ("hv_slow_fallback", "memset_ctl")]
     src = os.path.relpath(files[-1], ROOT) + " <- " + d.get("source", "?")
+    tot, missing = 0, []
+    for sc in scopes:
+        hit = [k for k in SCOPE_TO_KERNEL.get(sc, []) if k in per]
+        if hit:
+            tot += sum(per[k]["dram_read"] + per[k]["dram_write"] for k in hit)
+        elif sc not in ("hv_slow_fallback", "memset_ctl"):  # (no-op / counter-zeroing launches: no DRAM traffic)
+            missing.append(sc)
     if missing:
         return None, per, src + " (STALE: no capture of " + ", ".join(missing) + ")"
-    tot = sum(v["dram_read"] + v["dram_write"] for k, v in per.items()
-              if k in [SCOPE_TO_KERNEL.get(sc) for sc in scopes])
+    per = dict(per, _frames_per_step=int(d.get("frames_per_step", 64)))
     return int(tot), per, src
 
 
@@ -242,7 +251,9 @@ def run_reference(args, quiet=False, sample_frames=0):
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": max(args.warmup, 1), "ms_per_step": round(t_step * 1e3, 3), "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": _config_dict(cfg, args, frames_per_step=frames_total),
+        "config": dict(_config_dict(cfg, args, frames_per_step=frames_total),
+                       frames_per_gpu_per_step=len(frame_block(frames_total, 0, max(args.gpus, 1)))
+                       if args.scaling == "strong" else frames_total),
         "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": procs, "kind": kind, "sample": sample,
                          "host_cores_visible": cores, "mean_voxels_per_frame": round(sum(ms) / frames_total, 1)},
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -409,8 +420,9 @@ def run_ours(args):
     algo = algorithmic_bytes(N, C, P, m_list)  # this rank's share of the step
     achieved = algo / (ms_step * 1e-3) / 1e9
     traffic, per_kernel, traffic_src = ncu_traffic(args.workload, list(kernels or {}))
-    if traffic is not None and F != 64:
-        traffic = int(traffic * F / 64)  # the capture is a 64-frame step
+    cap_frames = per_kernel.get("_frames_per_step", 64)
+    if traffic is not None and F != cap_frames:
+        traffic = int(traffic * F / cap_frames)  # scaled from the captured step's frame count
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic,
                 "kernel": "hard-voxelize launch sequence per GPU (" + ", ".join(k for k in (kernels or {})) + "); "
@@ -425,12 +437,12 @@ def run_ours(args):
         m_tot = sum(m_list)
         k_bytes = m_tot * (P * C * 4 + 16) + m_tot * 4 + (kept * F * C * 4 if kept else 0)
         k_ms = kernels["hvb_expand"]["ms_per_step"]
-        kt = per_kernel.get("hvb_expand_rec_kernel")
+        kt = next((per_kernel[k] for k in SCOPE_TO_KERNEL["hvb_expand"] if k in per_kernel), None)
         roofline["dominant_kernel"] = {"name": "hvb_expand", "ms_per_launch": k_ms,
                                        "algorithmic_bytes_per_launch": k_bytes,
                                        "achieved": round(k_bytes / (k_ms * 1e-3) / 1e9, 1),
                                        "frac": round(k_bytes / (k_ms * 1e-3) / 1e9 / peak, 4),
-                                       "traffic": int((kt["dram_read"] + kt["dram_write"]) * F / 64) if kt else None}
+                                       "traffic": int((kt["dram_read"] + kt["dram_write"]) * F / cap_frames) if kt else None}
 
     fused = None
     if not args.no_extras and P == 5 and C in (4, 5):

@@ -1554,7 +1554,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
 #endif
 // voxels per warp: short warp tasks keep the voxels in flight on the chip within about one frame, whose
 // rows then stay in L2 between the two touches every 32-byte sector of a shuffled frame gets on average
-// (32 voxels per warp: 0.298 ms and 2.4 x the DRAM reads, profiles/r02_c5_words_ncu.txt)
+// (32 voxels per warp: 0.298 ms and 2.4 x the DRAM reads, profiles/r02_c5_words32_ncu.txt)
 constexpr int kWordsVox = PCFE_WORDS_VOX;
 template <int C>
 __global__ void __launch_bounds__(kExpThreads)

@@ -1,6 +1,6 @@
 """DRAM traffic per kernel of one step from an `ncu --set full` report -> profiles/<tag>_traffic_<workload>.json,
 the file bench.py's roofline.traffic is read from.  Launches of the same kernel are averaged.
-    python tests/native/ncu_traffic.py REP WORKLOAD TAG "<the command the report was captured with>" """
+    python tests/native/ncu_traffic.py REP WORKLOAD TAG "<the command the report was captured with>" FRAMES_PER_STEP """
 import collections
 import csv
 import json
@@ -10,6 +10,7 @@ import subprocess
 import sys
 
 rep, workload, tag, cmd = sys.argv[1:5]
+frames = int(sys.argv[5]) if len(sys.argv) > 5 else 64
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -24,7 +25,7 @@ for r in rows[2:]:
     a[1] += float(r[ix["dram__bytes_write.sum"]]) * scale[units[ix["dram__bytes_write.sum"]]]
     a[2] += float(r[ix["gpu__time_duration.sum"]])
     a[3] += 1
-d = {"workload": workload, "source": os.path.basename(rep) + " (" + cmd + ")",
+d = {"workload": workload, "frames_per_step": frames, "source": os.path.basename(rep) + " (" + cmd + ")",
      "kernels": {k: {"dram_read": int(v[0] / v[3]), "dram_write": int(v[1] / v[3]), "us": round(v[2] / v[3], 2), "launches": v[3]}
                  for k, v in acc.items()}}
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "profiles",
