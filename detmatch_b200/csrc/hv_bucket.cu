@@ -56,6 +56,7 @@ Knob g_opt_expand_variant{0};  // 1: un-pipelined fixed-P expansion kernel
 Knob g_opt_expand_prefetch{1};  // frames of L2 prefetch distance in the expansion (0 = off)
 Knob g_opt_pdl{1};              // programmatic dependent launch between the record path's kernels
 Knob g_opt_expand_ctas{0};      // > 0: persistent expansion with this many CTAs per SM
+Knob g_opt_expand_tiles{0};     // > 0: 32-voxel tiles per warp of the record expansion (default 3)
 Knob g_opt_warp_dedup{0};       // 1: warp-level key de-duplication (__match_any_sync) in front of the bucket table
 Knob g_opt_bin_small{2};        // partition tile: 0 = 4096 points, 1 = 1024 points, 2 = by batch size
 Knob g_opt_overlap{1};          // 0: waves of a multi-wave batch run one after the other on the caller's stream
@@ -1356,7 +1357,8 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
                       const int coors_vec /* every coors buffer is 16-byte aligned */,
                       const int tiles_x /* CTA-tiles per frame; the 1-D grid strides over tiles_x * frames */,
                       const int32_t* __restrict__ vn_all /* PACK: voxel_num of the batch's frame 0 */,
-                      const int f_first /* PACK: batch index of this launch's frame 0 */) {
+                      const int f_first /* PACK: batch index of this launch's frame 0 */,
+                      const int pipe_tiles /* 32-voxel tiles per warp */) {
   constexpr int PT = 5;
   constexpr int W = PT * C;  // output words per voxel
   // source word (point index * C + feature) of every output word of a warp's tile, kEmpty = zero
@@ -1386,7 +1388,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   const uint32_t* __restrict__ firsts = w.firsts(f);
   const uint4* __restrict__ rec = w.rec(f);
   const float* __restrict__ pts = fr.pts;
-  const int vbase = (bx * kExpWarps + wid) * (kPipeTiles * 32);
+  const int vbase = (bx * kExpWarps + wid) * (pipe_tiles * 32);
   if (vbase >= m) continue;  // warp-uniform
   size_t off = 0;  // PACK: rows of the earlier frames
   if (PACK) {
@@ -1408,7 +1410,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   uint4 ra_cur = load_rec(fi_cur);
 
 #pragma unroll 1
-  for (int it = 0; it < kPipeTiles; ++it) {
+  for (int it = 0; it < pipe_tiles; ++it) {
     const int v0 = vbase + it * 32;
     if (v0 >= m) break;  // warp-uniform
     const int nvox = min(32, m - v0);
@@ -1971,7 +1973,10 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
         ProfScope ps("hvb_expand", st);
         const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
         const int64_t vmax = std::max<int64_t>(std::min<int64_t>(max_voxels, wn_max), 1);
-        const int pper = kExpWarps * kPipeTiles * 32;
+        // tiles per warp: 3 (B = 4 / 8 / 16 / 64 frames: 0.0350 / 0.0602 / 0.1063 / 0.354 ms; 4 tiles: 0.0377 /
+        // 0.0613 / 0.1072 / 0.355; `hv_expand_tiles` overrides)
+        const int pipe_tiles = g_opt_expand_tiles > 0 ? (int)g_opt_expand_tiles : 3;
+        const int pper = kExpWarps * pipe_tiles * 32;
         const dim3 pgrid((unsigned)((vmax + pper - 1) / pper), (unsigned)wv);
         const int32_t* vn = voxel_num + f0;
         const int tiles_x = (int)pgrid.x;
@@ -1980,7 +1985,7 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
         const bool pdl = g_opt_pdl != 0;
 #define PCFE_LAUNCH_EXPAND_REC(CC, MM, PP)                                                                      \
   PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<CC, MM, PP>, dim3(egrid), dim3(kExpThreads), 0, st, pdl, b, w, p.g, \
-                           fdiv, vn, wv, (int)g_opt_expand_prefetch, coors_vec, tiles_x, (const int32_t*)voxel_num, f0))
+                           fdiv, vn, wv, (int)g_opt_expand_prefetch, coors_vec, tiles_x, (const int32_t*)voxel_num, f0, pipe_tiles))
 #define PCFE_LAUNCH_EXPAND_REC_C(CC)                                \
   do {                                                              \
     if (mean && pack) PCFE_LAUNCH_EXPAND_REC(CC, true, true);       \

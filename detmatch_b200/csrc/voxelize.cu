@@ -53,6 +53,7 @@ extern Knob g_opt_cluster;
 extern Knob g_opt_overlap;
 extern Knob g_opt_bin_small;
 extern Knob g_opt_warp_dedup;
+extern Knob g_opt_expand_tiles;
 extern Knob g_opt_pdl;
 extern Knob g_opt_pib_grid;
 extern Knob g_opt_no_fast_div;
@@ -490,6 +491,7 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_overlap")) g_opt_overlap = value;
   else if (!strcmp(name, "hv_bin_small")) g_opt_bin_small = value;
   else if (!strcmp(name, "hv_warp_dedup")) g_opt_warp_dedup = value;
+  else if (!strcmp(name, "hv_expand_tiles")) g_opt_expand_tiles = value;
   else return PCFE_ERR_SHAPE;
   return PCFE_OK;
 }
