@@ -118,6 +118,9 @@ constexpr int kBinTileSmall = kBinThreads * kBinPerThreadSmall;  // 1024 points
 constexpr int kMaxBuckets = 1024;
 
 __global__ void hvb_zero_kernel(uint4* __restrict__ p, const size_t n16) {
+  // the partition kernel may start right away: its row loads and key computation need nothing from
+  // here, and it waits (griddepcontrol.wait) for this grid's completion before its first counter atomic
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
     p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
