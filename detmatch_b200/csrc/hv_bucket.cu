@@ -60,11 +60,6 @@ Knob g_opt_expand_tiles{0};     // > 0: 32-voxel tiles per warp of the record ex
 Knob g_opt_warp_dedup{0};       // 1: warp-level key de-duplication (__match_any_sync) in front of the bucket table
 Knob g_opt_bin_small{2};        // partition tile: 0 = 4096 points, 1 = 1024 points, 2 = by batch size
 Knob g_opt_overlap{1};          // 0: waves of a multi-wave batch run one after the other on the caller's stream
-Knob g_opt_walk2{0};            // 1: bucket kernel walks cells of one / two points in a light first pass, the rest in a second
-Knob g_opt_scan_fold{0};        // 1: voxel numbering (hvb_scan_firsts) done by the last bucket CTAs of every frame, no scan launch
-Knob g_opt_expand_rev{0};       // 1: expansion takes the frames in descending order
-Knob g_opt_ent_evict{0};        // 1: the bucket kernel's entry copies carry an L2 evict-first hint
-Knob g_opt_carveout{0};         // 1: expansion / scan kernels ask for the maximum shared-memory carve-out (co-residency with the bucket kernel)
 Knob g_opt_cluster{0};          // 1: record path with one thread-block cluster per frame (hv_cluster.cuh) -- measured slower, see profiles/r02_cluster_*
 
 namespace {
@@ -101,7 +96,7 @@ struct HvbWork {
   __device__ __forceinline__ uint32_t* prefix(int f) const { return wordprefix + (size_t)f * word_stride; }
 };
 // ctl word indices after the nb bucket counters
-constexpr int kCtlList = 0, kCtlCell = 1, kCtlOverflow = 2, kCtlDone = 3;
+constexpr int kCtlList = 0, kCtlCell = 1, kCtlOverflow = 2;
 
 // ------------------------------------------------------------------------------------------
 // A: partition points into hash buckets
@@ -288,57 +283,6 @@ constexpr int kBucketThreads = PCFE_BUCKET_THREADS;
 #endif
 constexpr int kMaxCap = 2048;  // entries per bucket (list offsets are packed into 16 bits)
 
-// ---- voxel ids -> first points (record path) ---------------------------------------------------------
-// firsts[v] = index of the first point of voxel v = position of the v-th set bit of the frame's
-// bitmask.  A CTA of 256 threads owns slice `slice` = W consecutive 64-bit mask words (thread t < W:
-// word slice W + t).  It re-counts the bits before its slice (<= 22 KB of L2-resident words) instead of
-// waiting for a prefix, expands its own set bits into shared memory (`stage`, 32 W words) and writes them
-// out as one contiguous, coalesced run (scattered 4-byte stores would be partial-sector L2 writes:
-// measured 7x slower).  CG: the mask was written by OTHER CTAs of the running grid (loads bypass L1).
-constexpr int kFirstsThreads = 256;
-template <int W, bool CG>
-__device__ __forceinline__ void scan_firsts_slice(const HvbWork& w, const int f, const int slice, const int nslices,
-                                                  const int words, const int max_voxels, int32_t* __restrict__ voxel_num,
-                                                  uint32_t* stage, uint32_t* warp_sums) {
-  const int tid = threadIdx.x;
-  // 64-bit mask words: low half = "first point of a voxel", high half = "that voxel has more points"
-  const uint2* __restrict__ bm = reinterpret_cast<const uint2*>(w.bitmask(f));
-  uint32_t* __restrict__ firsts = w.firsts(f);
-  const int lo = slice * W;
-  const int wd = lo + tid;
-  uint2 mine = make_uint2(0u, 0u);
-  if (tid < W && wd < words) mine = CG ? __ldcg(&bm[wd]) : bm[wd];
-  uint32_t bits = mine.x;
-  uint32_t sum = 0;
-  // every load of the re-count is issued before the first popcount (one L2 round trip, not lo / 256)
-  for (int i0 = tid; i0 < lo; i0 += 8 * kFirstsThreads) {
-    uint32_t t[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = i0 + k * kFirstsThreads;
-      t[k] = i < lo ? (CG ? __ldcg(&bm[i].x) : __ldg(&bm[i].x)) : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sum += __popc(t[k]);
-  }
-  uint32_t before;
-  block_exscan(sum, warp_sums, &before);
-  __syncthreads();  // warp_sums is reused below
-  uint32_t total;
-  uint32_t pos = block_exscan((uint32_t)__popc(bits), warp_sums, &total);
-  while (bits) {
-    const int bit = __ffs(bits) - 1;
-    bits &= bits - 1u;
-    // firsts[v] = first point of voxel v | "has a record" << 31
-    stage[pos++] = ((uint32_t)wd * 32u + (uint32_t)bit) | (((mine.y >> bit) & 1u) << 31);
-  }
-  __syncthreads();
-  for (uint32_t i = tid; i < total; i += kFirstsThreads)
-    if (before + i < (uint32_t)max_voxels) firsts[before + i] = stage[i];  // voxelization_cpu.cpp:78
-  if (slice == nslices - 1 && tid == 0)
-    voxel_num[f] = (int32_t)min(before + total, (uint32_t)max_voxels);
-}
-
 // ------------------------------------------------------------------------------------------
 // B': the same job for P <= PT (PT = 5 or 8): cells keep their points in a linked list built with
 // one shared-memory atomicExch per entry; then one thread per cell walks the chain and keeps the
@@ -502,30 +446,20 @@ hvb_bucket_small_kernel(const HvbWork w, const int pe /* 1 <= pe <= PT */) {
 // (sweep-ordered) frames: 46 % of the points of a 4096-point tile repeat a cell of the tile, and a tile's
 // entries of one bucket sit next to each other -- and costs a few instructions per entry when they do not
 // (PointShuffle'd frames: 0.03 % in-warp repeats); `hv_warp_dedup`, measured in profiles/r02_summary.md.
-// WALK2: the cells are walked in two passes -- cells of one or two points (three quarters of a LiDAR frame's
-// cells) are finished by a pass that looks at two chain links at most, the others are put on a list and
-// walked by dense warps afterwards (a warp's walk lasts as long as its longest chain: 9.6 entries on
-// average over 32 random cells whose mean is 1.9).
-// FOLD: the frame's voxel numbering (scan_firsts_slice, otherwise the hvb_scan_firsts launch) is done by
-// the last K bucket CTAs of the frame to finish, K = number of 128-word mask slices: every CTA takes a
-// ticket when its mask bits are out; ticket holders nb - K .. nb - 1 wait for the counter to reach nb
-// (only CTAs that are already running are waited for) and number one slice each.
-template <bool DEDUP, bool WALK2, bool FOLD>
+template <bool DEDUP>
 __global__ void __launch_bounds__(kBucketThreads)
-hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const int spec /* entries copied before ne is known */,
-                      const int evict_hint, const int words, const int max_voxels, int32_t* __restrict__ voxel_num) {
+hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const int spec /* entries copied before ne is known */) {
   constexpr int PT = 5;
   constexpr uint32_t kNil = 0xFFFFFFFFu;
   extern __shared__ __align__(16) uint32_t smem[];
   __shared__ __align__(8) uint64_t bar[2];
-  __shared__ uint32_t s_nclaimed, s_ndefer, s_ticket;
-  __shared__ uint32_t warp_sums[FOLD ? 33 : 1];
+  __shared__ uint32_t s_nclaimed;
 
   // frames in REVERSE launch order: the bin kernel wrote the entries of the last frames most
   // recently (still in L2), and the records this kernel writes last (first frames) are the ones
   // the expansion reads first
   const int f = (int)(gridDim.y - 1u - blockIdx.y), b = blockIdx.x, tid = threadIdx.x;
-  uint32_t* ctl = w.ctl(f);
+  const uint32_t* ctl = w.ctl(f);
   const int cap = w.cap;
   uint2* ents = reinterpret_cast<uint2*>(smem);  // {key, point}; .x becomes the chain link once inserted
   uint32_t* hkey = smem + 2 * cap;
@@ -539,14 +473,10 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
   __syncthreads();  // barrier objects initialised before any use (also keeps racecheck quiet)
   pdl_wait();       // everything below reads what the bin kernel wrote
   pdl_trigger();
-  uint64_t pol = 0;
-  if (evict_hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   if (tid == 0) {
     mbar_expect_tx(&bar[0], (uint32_t)spec * 8u);
-    if (evict_hint) bulk_g2s_hint(ents, gent, (uint32_t)spec * 8u, &bar[0], pol);
-    else bulk_g2s(ents, gent, (uint32_t)spec * 8u, &bar[0]);
+    bulk_g2s(ents, gent, (uint32_t)spec * 8u, &bar[0]);
     s_nclaimed = 0u;
-    s_ndefer = 0u;
   }
   const uint32_t overflow = ctl[w.nb + kCtlOverflow];
   const int ne = (int)min(ctl[b], (uint32_t)cap);
@@ -558,8 +488,7 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
   if (tid == 0 && ne > spec) {
     const uint32_t bytes = (uint32_t)(((ne - spec) + 1) & ~1) * 8u;  // 16-byte granules; cap and spec are even
     mbar_expect_tx(&bar[1], bytes);
-    if (evict_hint) bulk_g2s_hint(ents + spec, gent + spec, bytes, &bar[1], pol);
-    else bulk_g2s(ents + spec, gent + spec, bytes, &bar[1]);
+    bulk_g2s(ents + spec, gent + spec, bytes, &bar[1]);
   }
   {
     uint4* k4 = reinterpret_cast<uint4*>(hkey);  // hkey and head are contiguous: 2 * S words
@@ -567,9 +496,8 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
   }
   __syncthreads();  // table and barriers initialised
   mbar_wait(&bar[0], 0);  // always: the copy must not outlive the CTA's shared memory
-  if (overflow) return;   // (the frame takes the fallback: nothing of it is numbered here)
-  if (!FOLD && ne == 0) return;
-  if (ne > spec) mbar_wait(&bar[1], 0);  // (FOLD: an empty bucket falls through to its ticket)
+  if (overflow || ne == 0) return;
+  if (ne > spec) mbar_wait(&bar[1], 0);
 
   const uint32_t smask = (uint32_t)S - 1u;
   const int sshift = 32 - w.log2_nb - w.log2_slots;
@@ -622,14 +550,16 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
   const int nv = (int)s_nclaimed;
   unsigned long long* __restrict__ bm64 = reinterpret_cast<unsigned long long*>(w.bitmask(f));
   uint4* __restrict__ rec = w.rec(f);
-  // One cell, all of its chain: the 5 smallest point indices stay in registers, ascending.  The first 5
-  // steps are peeled: step k inserts into a sorted prefix of k entries (k compare-exchanges instead of 5).
-  auto walk_cell = [&](const int s) {
+#pragma unroll 1
+  for (int j = tid; j < nv; j += kBucketThreads) {
     uint32_t sorted[PT];
 #pragma unroll
     for (int t = 0; t < PT; ++t) sorted[t] = kEmpty;
+    const int s = slotlist[j];
     uint32_t cnt = 0;
     uint32_t e = head[s];
+    // chain walk; the 5 smallest point indices stay in registers, ascending.  The first 5 steps are
+    // peeled: step k inserts into a sorted prefix of k entries (k compare-exchanges instead of 5).
 #pragma unroll
     for (int step = 0; step < PT; ++step) {
       if (e != kNil) {
@@ -673,80 +603,6 @@ hvb_bucket_rec_kernel(const HvbWork w, const int pe /* 1 <= pe <= 5 */, const in
       if (PCFE_REC_STRIDE == 2) rec[2 * (size_t)first + 1] = make_uint4(0u, 0u, 0u, 0u);
     }
     atomicOr(&bm64[first >> 5], (1ull << (first & 31)) | (more ? (1ull << (32 + (first & 31))) : 0ull));
-  };
-  if (!WALK2) {
-#pragma unroll 1
-    for (int j = tid; j < nv; j += kBucketThreads) walk_cell(slotlist[j]);
-  } else {
-    // pass A: one or two points -- two chain links decide; everything longer goes on the deferred list, which
-    // lives behind the cell list (nv + #deferred <= ne <= cap: a deferred cell owns three entries at least)
-#pragma unroll 1
-    for (int j0 = 0; j0 < nv; j0 += kBucketThreads) {  // warp-uniform trip count (ballot below)
-      const int j = j0 + tid;
-      bool defer = false;
-      int s = 0;
-      if (j < nv) {
-        s = slotlist[j];
-        const uint2 e1 = ents[head[s]];
-        if (e1.x == kNil) {
-          atomicOr(&bm64[e1.y >> 5], 1ull << (e1.y & 31));
-        } else {
-          const uint2 e2 = ents[e1.x];
-          if (e2.x == kNil) {
-            const uint32_t first = min(e1.y, e2.y), second = max(e1.y, e2.y);
-            const bool more = pe > 1;
-            if (more) {
-              rec[PCFE_REC_STRIDE * (size_t)first] = make_uint4(second, kEmpty, kEmpty, kEmpty);
-              if (PCFE_REC_STRIDE == 2) rec[2 * (size_t)first + 1] = make_uint4(0u, 0u, 0u, 0u);
-            }
-            atomicOr(&bm64[first >> 5], (1ull << (first & 31)) | (more ? (1ull << (32 + (first & 31))) : 0ull));
-          } else {
-            defer = true;
-          }
-        }
-      }
-      const uint32_t dm = __ballot_sync(0xFFFFFFFFu, defer);
-      if (dm) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&s_ndefer, (uint32_t)__popc(dm));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (defer) slotlist[nv + base + __popc(dm & lane_lt)] = (uint16_t)s;
-      }
-    }
-    __syncthreads();
-    const int nd = (int)s_ndefer;
-#pragma unroll 1
-    for (int j = tid; j < nd; j += kBucketThreads) walk_cell(slotlist[nv + j]);
-  }
-  if (FOLD) {
-    // every mask bit of this CTA is out: take a ticket; the frame's last K tickets number the voxels
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(&ctl[w.nb + kCtlDone], 1u);
-    __syncthreads();
-    constexpr int SW = 128;  // mask words per slice (a 16 KB stage: the smallest bucket plan has that much)
-    const int nslices = (words + SW - 1) / SW;
-    const int K = min(nslices, w.nb);
-    const int part = (int)s_ticket - (w.nb - K);
-    if (part < 0) return;
-    if (tid == 0) {
-      uint32_t it = 0, seen;
-      while (true) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&ctl[w.nb + kCtlDone]) : "memory");
-        if (seen >= (uint32_t)w.nb) break;
-        __nanosleep(32);
-        if (++it > (1u << 22)) {  // (never seen: CTAs are dispatched in order) the frame takes the fallback
-          ctl[w.nb + kCtlOverflow] = 1u;
-          break;
-        }
-      }
-    }
-    __syncthreads();
-    __threadfence();
-    for (int slice = part; slice < nslices; slice += K) {
-      scan_firsts_slice<SW, true>(w, f, slice, nslices, words, max_voxels, voxel_num, smem, warp_sums);
-      __syncthreads();
-    }
   }
 }
 
@@ -1420,17 +1276,56 @@ hvb_expand_pipe_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, c
 }
 
 // ---- record-at-first-point variant: voxel ids -> first points, then a pipelined expansion -----------
-// (scan_firsts_slice, the numbering itself, sits in front of the bucket kernel, which can run it in its tail)
+// firsts[v] = index of the first point of voxel v = position of the v-th set bit of the frame's
+// bitmask.  CTA (slice, frame) re-counts the bits before its slice (<= 22 KB of L2-resident words)
+// instead of waiting for a prefix, then writes the positions of its own set bits.
+constexpr int kFirstsThreads = 256;
+
+// CTA (slice, frame) owns 256 consecutive bitmask words (one per thread).  It re-counts the bits
+// before its slice (<= 22 KB of L2-resident words) instead of waiting for a prefix, expands its
+// own set bits into shared memory and writes them out as one contiguous, coalesced run (scattered
+// 4-byte stores would be partial-sector L2 writes: measured 7x slower).
 __global__ void __launch_bounds__(kFirstsThreads)
 hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
                        int32_t* __restrict__ voxel_num) {
   __shared__ uint32_t warp_sums[33];
   __shared__ uint32_t stage[kFirstsThreads * 32];
-  const int f = blockIdx.y;
+  const int f = blockIdx.y, tid = threadIdx.x;
   pdl_wait();
   pdl_trigger();
   if (w.ctl(f)[w.nb + kCtlOverflow]) return;
-  scan_firsts_slice<kFirstsThreads, false>(w, f, (int)blockIdx.x, (int)gridDim.x, words, max_voxels, voxel_num, stage, warp_sums);
+  // 64-bit mask words: low half = "first point of a voxel", high half = "that voxel has more points"
+  const uint2* __restrict__ bm = reinterpret_cast<const uint2*>(w.bitmask(f));
+  uint32_t* __restrict__ firsts = w.firsts(f);
+  const int lo = blockIdx.x * kFirstsThreads;
+  const int wd = lo + tid;
+  const uint2 mine = wd < words ? bm[wd] : make_uint2(0u, 0u);
+  uint32_t bits = mine.x;
+  uint32_t sum = 0;
+  // every load of the re-count is issued before the first popcount (one L2 round trip, not lo / 256)
+  for (int i0 = tid; i0 < lo; i0 += 8 * kFirstsThreads) {
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = i0 + k * kFirstsThreads < lo ? __ldg(&bm[i0 + k * kFirstsThreads].x) : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += __popc(t[k]);
+  }
+  uint32_t before;
+  block_exscan(sum, warp_sums, &before);
+  __syncthreads();  // warp_sums is reused below
+  uint32_t total;
+  uint32_t pos = block_exscan((uint32_t)__popc(bits), warp_sums, &total);
+  while (bits) {
+    const int bit = __ffs(bits) - 1;
+    bits &= bits - 1u;
+    // firsts[v] = first point of voxel v | "has a record" << 31
+    stage[pos++] = ((uint32_t)wd * 32u + (uint32_t)bit) | (((mine.y >> bit) & 1u) << 31);
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < total; i += kFirstsThreads)
+    if (before + i < (uint32_t)max_voxels) firsts[before + i] = stage[i];  // voxelization_cpu.cpp:78
+  if (blockIdx.x == gridDim.x - 1 && tid == 0)
+    voxel_num[f] = (int32_t)min(before + total, (uint32_t)max_voxels);
 }
 
 // Expansion.  Three dependent round trips per tile of 32 voxels (firsts -> record -> rows), one of
@@ -1466,8 +1361,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
                       const int tiles_x /* CTA-tiles per frame; the 1-D grid strides over tiles_x * frames */,
                       const int32_t* __restrict__ vn_all /* PACK: voxel_num of the batch's frame 0 */,
                       const int f_first /* PACK: batch index of this launch's frame 0 */,
-                      const int pipe_tiles /* 32-voxel tiles per warp */,
-                      const int rev /* 1: frames in descending order */) {
+                      const int pipe_tiles /* 32-voxel tiles per warp */) {
   constexpr int PT = 5;
   constexpr int W = PT * C;  // output words per voxel
   // source word (point index * C + feature) of every output word of a warp's tile, kEmpty = zero
@@ -1478,11 +1372,9 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   int32_t* cstage = coor_all + wid * 96;
 #pragma unroll 1
   for (int wi = blockIdx.x; wi < tiles_x * frames; wi += gridDim.x) {
-  const int fo = wi / tiles_x, bx = wi - fo * tiles_x;
-  const int f = rev ? frames - 1 - fo : fo;
-  const int fnext = rev ? f - pf_dist : f + pf_dist;  // the frame whose rows are pulled into L2 meanwhile
-  if (pf_dist > 0 && fnext >= 0 && fnext < frames && threadIdx.x < 32) {  // see hvb_expand_pipe_kernel
-    const HvFrame& nf = batch.f[fnext];
+  const int f = wi / tiles_x, bx = wi - f * tiles_x;
+  if (pf_dist > 0 && f + pf_dist < frames && threadIdx.x < 32) {  // see hvb_expand_pipe_kernel
+    const HvFrame& nf = batch.f[f + pf_dist];
     const size_t total = ((size_t)nf.n * C * 4) & ~(size_t)15;
     const size_t slice = ((total + tiles_x - 1) / tiles_x + 511) & ~(size_t)511;
     const size_t lo = (size_t)bx * slice + (size_t)threadIdx.x * (slice / 32);
@@ -1969,12 +1861,12 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
   {
     int rc = ensure_dyn_smem((const void*)hvb_bucket_small_kernel<5>, 0, device, p.smem_bucket);
     if (rc == PCFE_OK) rc = ensure_dyn_smem((const void*)hvb_bucket_small_kernel<8>, 1, device, p.smem_bucket);
-    const size_t rec_max = std::max<size_t>((size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2, 16384);
-    if (rc == PCFE_OK) rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel<false, false, false>, 2, device, rec_max);
-    if (rc == PCFE_OK) rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel<true, false, false>, 4, device, rec_max);
-    if (rc == PCFE_OK) rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel<false, true, false>, 5, device, rec_max);
-    if (rc == PCFE_OK) rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel<false, false, true>, 6, device, rec_max);
-    if (rc == PCFE_OK) rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel<false, true, true>, 7, device, rec_max);
+    if (rc == PCFE_OK)
+      rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel<false>, 2, device,
+                           (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2);
+    if (rc == PCFE_OK)
+      rc = ensure_dyn_smem((const void*)hvb_bucket_rec_kernel<true>, 4, device,
+                           (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)(2 * p.cap) * 2);
     if (rc != PCFE_OK) return rc;
   }
   const int pe = std::max(max_points, 1);
@@ -2055,31 +1947,20 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
     }
     int rc = PCFE_OK;
     if (use_rec) {
-      bool fold = false;
       if (!clustered) {
         ProfScope ps("hvb_bucket", st);
         const dim3 grid((unsigned)p.nb, (unsigned)wv);
+        const size_t smem_rec = (size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)p.cap * 2;
         // speculative first copy: the average bucket fill of the largest frame, rounded up to 64
         // entries, never more than the region
         const int spec = (int)std::min<int64_t>(p.cap, std::max<int64_t>((((wn_max + p.nb - 1) / p.nb) + 63) / 64 * 64, 64));
-        const bool dedup = g_opt_warp_dedup != 0, walk2 = g_opt_walk2 != 0 && !dedup;
-        fold = g_opt_scan_fold != 0 && !dedup;
-        // (folded numbering: the stage of a 128-word mask slice, 16 KB, lives in the same dynamic shared memory)
-        const size_t smem_rec = std::max<size_t>((size_t)(2 * p.slots + 2 * p.cap) * 4 + (size_t)p.cap * 2, fold ? 16384 : 0);
-        const int hint = g_opt_ent_evict != 0 ? 1 : 0;
-        const bool pdl = g_opt_pdl != 0;
-#define PCFE_LAUNCH_BUCKET(DD, WW, FF)                                                                                   \
-  PCFE_CUDA_TRY(launch_pdl(hvb_bucket_rec_kernel<DD, WW, FF>, grid, dim3(kBucketThreads), smem_rec, st, pdl, w, pe, spec, hint, \
-                           wnpad / 32, max_voxels, voxel_num + f0))
-        if (dedup) PCFE_LAUNCH_BUCKET(true, false, false);
-        else if (walk2 && fold) PCFE_LAUNCH_BUCKET(false, true, true);
-        else if (walk2) PCFE_LAUNCH_BUCKET(false, true, false);
-        else if (fold) PCFE_LAUNCH_BUCKET(false, false, true);
-        else PCFE_LAUNCH_BUCKET(false, false, false);
-#undef PCFE_LAUNCH_BUCKET
+        if (g_opt_warp_dedup)
+          PCFE_CUDA_TRY(launch_pdl(hvb_bucket_rec_kernel<true>, grid, dim3(kBucketThreads), smem_rec, st, g_opt_pdl != 0, w, pe, spec));
+        else
+          PCFE_CUDA_TRY(launch_pdl(hvb_bucket_rec_kernel<false>, grid, dim3(kBucketThreads), smem_rec, st, g_opt_pdl != 0, w, pe, spec));
         PCFE_LAUNCH_CHECK();
       }
-      if (!clustered && !fold) {
+      if (!clustered) {
         ProfScope ps("hvb_scan_firsts", st);
         PCFE_CUDA_TRY(launch_pdl(hvb_scan_firsts_kernel, dim3((unsigned)((wnpad / 32 + kFirstsThreads - 1) / kFirstsThreads), (unsigned)wv),
                                  dim3(kFirstsThreads), 0, st, g_opt_pdl != 0, w, wnpad / 32, max_voxels, voxel_num + f0));
@@ -2105,15 +1986,9 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
         unsigned egrid = pgrid.x * pgrid.y;
         if (g_opt_expand_ctas > 0) egrid = std::min<unsigned>(egrid, (unsigned)(g_opt_expand_ctas * 148));
         const bool pdl = g_opt_pdl != 0;
-        const int erev = g_opt_expand_rev != 0 ? 1 : 0;
-        if (g_opt_carveout) {  // experiment: same carve-out as the bucket kernel, so that CTAs of both can share an SM
-          const void* ek = c == 4 ? (const void*)hvb_expand_rec_kernel<4, false, false> : (const void*)hvb_expand_rec_kernel<5, false, false>;
-          PCFE_CUDA_TRY(cudaFuncSetAttribute(ek, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-          PCFE_CUDA_TRY(cudaFuncSetAttribute((const void*)hvb_scan_firsts_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        }
 #define PCFE_LAUNCH_EXPAND_REC(CC, MM, PP)                                                                      \
   PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<CC, MM, PP>, dim3(egrid), dim3(kExpThreads), 0, st, pdl, b, w, p.g, \
-                           fdiv, vn, wv, (int)g_opt_expand_prefetch, coors_vec, tiles_x, (const int32_t*)voxel_num, f0, pipe_tiles, erev))
+                           fdiv, vn, wv, (int)g_opt_expand_prefetch, coors_vec, tiles_x, (const int32_t*)voxel_num, f0, pipe_tiles))
 #define PCFE_LAUNCH_EXPAND_REC_C(CC)                                \
   do {                                                              \
     if (mean && pack) PCFE_LAUNCH_EXPAND_REC(CC, true, true);       \

@@ -58,11 +58,6 @@ extern Knob g_opt_pdl;
 extern Knob g_opt_pib_grid;
 extern Knob g_opt_no_fast_div;
 extern Knob g_opt_expand_prefetch;
-extern Knob g_opt_walk2;
-extern Knob g_opt_scan_fold;
-extern Knob g_opt_expand_rev;
-extern Knob g_opt_ent_evict;
-extern Knob g_opt_carveout;
 
 namespace {
 
@@ -497,11 +492,6 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_bin_small")) g_opt_bin_small = value;
   else if (!strcmp(name, "hv_warp_dedup")) g_opt_warp_dedup = value;
   else if (!strcmp(name, "hv_expand_tiles")) g_opt_expand_tiles = value;
-  else if (!strcmp(name, "hv_walk2")) g_opt_walk2 = value;
-  else if (!strcmp(name, "hv_scan_fold")) g_opt_scan_fold = value;
-  else if (!strcmp(name, "hv_expand_rev")) g_opt_expand_rev = value;
-  else if (!strcmp(name, "hv_ent_evict")) g_opt_ent_evict = value;
-  else if (!strcmp(name, "hv_carveout")) g_opt_carveout = value;
   else return PCFE_ERR_SHAPE;
   return PCFE_OK;
 }

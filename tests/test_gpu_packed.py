@@ -11,10 +11,9 @@ from oracle import oracle, vfe_mean
 from tests.helpers import assert_same_bits
 
 pytestmark = pytest.mark.gpu
-TAIL_KNOBS = ("hv_walk2", "hv_scan_fold", "hv_expand_rev", "hv_ent_evict")
 
 
-@pytest.fixture(params=["record", "tail", "cluster", "fallback", "general", "global", "waves"])
+@pytest.fixture(params=["record", "cluster", "fallback", "general", "global", "waves"])
 def pack_mode(request):
     """record: packed rows from the expansion kernel; cluster: the same with the frame's partition +
     grouping done by one thread-block cluster (hv_cluster.cuh); fallback: every frame through the two-stage
@@ -26,11 +25,7 @@ def pack_mode(request):
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "general" else 0)
     _cabi.debug_set("hv_wave", 2 if mode == "waves" else 0)
     _cabi.debug_set("hv_cluster", 1 if mode == "cluster" else 0)
-    for k in TAIL_KNOBS:  # round-2 tail variants of the record path (see tests/test_gpu_voxel.py)
-        _cabi.debug_set(k, 1 if mode == "tail" else 0)
     yield mode
-    for k in TAIL_KNOBS:
-        _cabi.debug_set(k, 0)
     for k in ("hv_path", "hv_force_overflow", "hv_bucket_variant", "hv_wave"):
         _cabi.debug_set(k, 0)
     _cabi.debug_set("hv_cluster", 0)

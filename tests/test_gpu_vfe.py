@@ -12,7 +12,6 @@ from oracle import oracle, vfe_mean
 from tests.helpers import assert_same_bits, golden
 
 pytestmark = pytest.mark.gpu
-TAIL_KNOBS = ("hv_walk2", "hv_scan_fold", "hv_expand_rev", "hv_ent_evict")
 
 EPS = np.float32(2.0 ** -24)
 
@@ -62,7 +61,7 @@ def test_standalone_device_side_row_limit_and_empty():
     assert e.shape == (0, 4)
 
 
-@pytest.fixture(params=["record", "tail", "cluster", "fallback", "general", "global"])
+@pytest.fixture(params=["record", "cluster", "fallback", "general", "global"])
 def mean_mode(request):
     """record: the fused epilogue of the expansion kernel; cluster: the same with the frame's partition +
     grouping done by one thread-block cluster (hv_cluster.cuh); fallback: every frame forced through the
@@ -73,11 +72,7 @@ def mean_mode(request):
     _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "general" else 0)
     _cabi.debug_set("hv_cluster", 1 if mode == "cluster" else 0)
-    for k in TAIL_KNOBS:  # round-2 tail variants of the record path (see tests/test_gpu_voxel.py)
-        _cabi.debug_set(k, 1 if mode == "tail" else 0)
     yield mode
-    for k in TAIL_KNOBS:
-        _cabi.debug_set(k, 0)
     for k in ("hv_path", "hv_force_overflow", "hv_bucket_variant"):
         _cabi.debug_set(k, 0)
     _cabi.debug_set("hv_cluster", 0)

@@ -13,15 +13,13 @@ from tests.helpers import assert_same_bits, golden, golden_names
 pytestmark = pytest.mark.gpu
 
 KITTI = [0, -40, -3, 70.4, 40, 1]
-TAIL_KNOBS = ("hv_walk2", "hv_scan_fold", "hv_expand_rev", "hv_ent_evict")
 
 
-@pytest.fixture(autouse=True, params=["launches", "tail", "dedup", "cluster", "bucket_general", "global", "fallback"])
+@pytest.fixture(autouse=True, params=["launches", "dedup", "cluster", "bucket_general", "global", "fallback"])
 def hv_mode(request):
     """Every test runs against all hard-voxelize implementations behind the one entry point: the
-    bucket path as a launch sequence (default; record kernels where P == 5 and C = 4 / 5), the same
-    with the round-2 tail variants (two-pass chain walk, voxel numbering folded into the bucket kernel's
-    last CTAs, descending expansion order, evict-first entry copies), the same with warp-level __match_any_sync key de-duplication in front of the bucket table, the record
+    bucket path as a launch sequence (default; record kernels where P == 5 and C = 4 / 5), the record
+    same with warp-level __match_any_sync key de-duplication in front of the bucket table, the record
     path with one thread-block cluster per frame (hv_cluster.cuh: measured slower, kept as the
     round-2 DSMEM experiment), the general bucket kernels (register-sorted chains for P <= 8, bitonic ranks
     otherwise), the global-memory path, and the default path with every frame forced through its
@@ -33,11 +31,7 @@ def hv_mode(request):
     _cabi.debug_set("hv_warp_dedup", 1 if mode == "dedup" else 0)
     _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "bucket_general" else 0)
-    for k in TAIL_KNOBS:
-        _cabi.debug_set(k, 1 if mode == "tail" else 0)
     yield mode
-    for k in TAIL_KNOBS:
-        _cabi.debug_set(k, 0)
     _cabi.debug_set("hv_path", 0)
     _cabi.debug_set("hv_cluster", 0)
     _cabi.debug_set("hv_warp_dedup", 0)
