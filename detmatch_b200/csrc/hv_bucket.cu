@@ -60,8 +60,6 @@ Knob g_opt_expand_tiles{0};     // > 0: 32-voxel tiles per warp of the record ex
 Knob g_opt_warp_dedup{0};       // 1: warp-level key de-duplication (__match_any_sync) in front of the bucket table
 Knob g_opt_bin_small{2};        // partition tile: 0 = 4096 points, 1 = 1024 points, 2 = by batch size
 Knob g_opt_overlap{1};          // 0: waves of a multi-wave batch run one after the other on the caller's stream
-Knob g_opt_bin_ring{1};         // 1: large batches are partitioned by the persistent TMA-ring kernel (hvb_bin_ring_kernel)
-Knob g_opt_scan_wpt{0};         // mask words per thread of the voxel numbering kernel: 0 = by batch size, 1, 2
 Knob g_opt_cluster{0};          // 1: record path with one thread-block cluster per frame (hv_cluster.cuh) -- measured slower, see profiles/r02_cluster_*
 
 namespace {
@@ -266,210 +264,6 @@ hvb_bin_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const Gri
     const uint2 e = stage[j];
     const uint32_t b = w.log2_nb ? (e.x * kGold) >> shift : 0u;
     ent[delta[b] + j] = e;
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------
-// A (large batches, C = 4 / 5, 16-byte aligned rows): the same partition as hvb_bin_kernel, run by
-// PERSISTENT CTAs whose rows arrive through a ring of TMA bulk copies.  The plain kernel's CTAs all
-// start together, load together (DRAM saturated, issue slots idle) and compute together (the reverse):
-// ncu shows DRAM 55 % / issue 54 % / L1 61 %, nothing saturated.  Here a CTA strides over the
-// 4096-point tiles of the batch; a tile's rows come as 8 chunks of 512 rows (10 KB at C = 5) through a
-// 3-slot ring (`full` mbarriers completed by the copies, `empty` mbarriers by the 8 warps), so the
-// chunks of the NEXT tile are in flight while the current one is ranked, scattered and flushed, and
-// the row words are read from shared memory (stride C words: conflict-free for C = 5, one LDS.128 per
-// row for C = 4) instead of three 20-byte-strided global loads per point.
-// dynamic shared memory: ring[3][512 C] | stage[4096] (uint2) | hist[nb] | soff[nb] | delta[nb]
-// ------------------------------------------------------------------------------------------
-constexpr int kRingRows = 512, kRingSlots = 3, kRingChunks = kBinTile / kRingRows;
-static_assert(kBinThreads == 256 && kBinPerThread == 16 && kRingChunks == 8, "ring kernel: 256 threads x 16 points");
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <int C>
-__global__ void __launch_bounds__(kBinThreads, 3)
-hvb_bin_ring_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
-                    const int use_fast_div, const int tiles_x, const int frames) {
-  extern __shared__ __align__(128) unsigned char dsm[];
-  float* ring = reinterpret_cast<float*>(dsm);
-  uint2* stage = reinterpret_cast<uint2*>(dsm + (size_t)kRingSlots * kRingRows * C * 4);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(stage + kBinTile);
-  uint32_t* soff = hist + w.nb;
-  uint32_t* delta = soff + w.nb;
-  __shared__ __align__(8) uint64_t full[kRingSlots], empty[kRingSlots];
-  __shared__ uint32_t warp_sums[33];
-  __shared__ uint32_t s_overflow;
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int total_items = tiles_x * frames;
-  if (tid == 0) {
-#pragma unroll
-    for (int k = 0; k < kRingSlots; ++k) {
-      mbar_init(&full[k], 1);
-      mbar_init(&empty[k], kBinThreads / 32);
-    }
-  }
-  __syncthreads();
-  // items of this CTA: blockIdx.x, + gridDim.x, ...; tiles past the end of a (shorter) frame are skipped
-  auto next_valid = [&](int it) {
-    while (it < total_items) {
-      const int f = it / tiles_x, tx = it - f * tiles_x;
-      if ((long long)tx * kBinTile < (long long)batch.f[f].n) break;
-      it += (int)gridDim.x;
-    }
-    return it;
-  };
-  // producer (thread 0): next chunk to request
-  int p_it = 0, p_k = 0, p_slot = 0, p_par = 0, p_q = 0;
-  auto produce = [&]() {
-    if (p_it >= total_items) return;
-    if (p_q >= kRingSlots) mbar_wait(&empty[p_slot], (uint32_t)(p_par ^ 1));  // the slot's previous chunk has been read by all warps
-    const int f = p_it / tiles_x, tx = p_it - f * tiles_x;
-    const int start = tx * kBinTile + p_k * kRingRows;
-    if (batch.f[f].n - start >= kRingRows) {
-      constexpr uint32_t bytes = (uint32_t)kRingRows * C * 4u;
-      mbar_expect_tx(&full[p_slot], bytes);
-      bulk_g2s(ring + (size_t)p_slot * kRingRows * C, batch.f[f].pts + (size_t)start * C, bytes, &full[p_slot]);
-    } else {
-      mbar_arrive(&full[p_slot]);  // ragged / empty chunk: its rows are loaded directly by the consumers
-    }
-    ++p_q;
-    if (++p_slot == kRingSlots) { p_slot = 0; p_par ^= 1; }
-    if (++p_k == kRingChunks) { p_k = 0; p_it = next_valid(p_it + (int)gridDim.x); }
-  };
-  if (tid == 0) {
-    p_it = next_valid((int)blockIdx.x);
-    produce(); produce(); produce();
-  }
-  int c_slot = 0, c_par = 0;
-  const int shift = 32 - w.log2_nb;
-  const FastAxes fa = make_fast_axes(g);
-  const float qnan = __int_as_float(0x7FC00000);  // past the end: NaN fails every range test
-
-#pragma unroll 1
-  for (int it = next_valid((int)blockIdx.x); it < total_items; it = next_valid(it + (int)gridDim.x)) {
-    const int f = it / tiles_x, tx = it - f * tiles_x;
-    const int n = batch.f[f].n;
-    const int tile0 = tx * kBinTile;
-    for (int b = tid; b < w.nb; b += kBinThreads) hist[b] = 0;
-    if (tid == 0) s_overflow = 0u;
-    uint32_t key[kBinPerThread];
-#pragma unroll
-    for (int k = 0; k < kRingChunks; ++k) {
-      const int start = tile0 + k * kRingRows;
-      float ax[2], ay[2], az[2];
-      mbar_wait(&full[c_slot], (uint32_t)c_par);
-      if (n - start >= kRingRows) {
-        const float* r = ring + (size_t)c_slot * kRingRows * C;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (C == 4) {
-            const float4 v = reinterpret_cast<const float4*>(r)[j * kBinThreads + tid];
-            ax[j] = v.x; ay[j] = v.y; az[j] = v.z;
-          } else {
-            const float* q = r + (size_t)(j * kBinThreads + tid) * C;
-            ax[j] = q[0]; ay[j] = q[1]; az[j] = q[2];
-          }
-        }
-      } else {
-        const float* __restrict__ p = batch.f[f].pts;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int i = start + j * kBinThreads + tid;
-          const bool in = i < n;
-          ax[j] = in ? __ldg(p + (size_t)i * C) : qnan;
-          ay[j] = in ? __ldg(p + (size_t)i * C + 1) : qnan;
-          az[j] = in ? __ldg(p + (size_t)i * C + 2) : qnan;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[c_slot]);
-      if (++c_slot == kRingSlots) { c_slot = 0; c_par ^= 1; }
-      if (tid == 0) produce();
-      // cell keys of the chunk's two points (same arithmetic as hvb_bin_kernel)
-      uint32_t fmask = 3u;
-      if (g.filter) fmask = (filter_pass(ax[0], ay[0], az[0], g) ? 1u : 0u) | (filter_pass(ax[1], ay[1], az[1], g) ? 2u : 0u);
-      bool guard_ok = use_fast_div != 0;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        ax[j] = __fsub_rn(ax[j], g.x0);
-        ay[j] = __fsub_rn(ay[j], g.y0);
-        az[j] = __fsub_rn(az[j], g.z0);
-        guard_ok = guard_ok & fast_div_guard(ax[j]) & fast_div_guard(ay[j]) & fast_div_guard(az[j]);
-      }
-      if (guard_ok) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float qx = fast_div(ax[j], g.vx, fa.rx), qy = fast_div(ay[j], g.vy, fa.ry), qz = fast_div(az[j], g.vz, fa.rz);
-          const uint32_t qmax = max(max(__float_as_uint(qx), __float_as_uint(qy)), __float_as_uint(qz));
-          const int cx = __float2int_rz(qx), cy = __float2int_rz(qy), cz = __float2int_rz(qz);
-          const bool ok = (qmax < 0x4F000000u) & (cx < g.gx) & (cy < g.gy) & (cz < g.gz);
-          const uint32_t lin = ((uint32_t)cz * (uint32_t)g.gy + (uint32_t)cy) * (uint32_t)g.gx + (uint32_t)cx;
-          key[2 * k + j] = (ok && ((fmask >> j) & 1u)) ? lin : kEmpty;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float qx = __fdiv_rn(ax[j], g.vx), qy = __fdiv_rn(ay[j], g.vy), qz = __fdiv_rn(az[j], g.vz);
-          const bool in = (qx >= 0.0f) & (qx < 2147483648.0f) & (qy >= 0.0f) & (qy < 2147483648.0f) &
-                          (qz >= 0.0f) & (qz < 2147483648.0f);
-          const int cx = in ? __float2int_rz(qx) : -1, cy = in ? __float2int_rz(qy) : -1, cz = in ? __float2int_rz(qz) : -1;
-          const bool ok = in & (cx < g.gx) & (cy < g.gy) & (cz < g.gz);
-          const uint32_t lin = ((uint32_t)cz * (uint32_t)g.gy + (uint32_t)cy) * (uint32_t)g.gx + (uint32_t)cx;
-          key[2 * k + j] = (ok && ((fmask >> j) & 1u)) ? lin : kEmpty;
-        }
-      }
-    }
-    __syncthreads();  // hist is zero; the previous tile's stage / delta are no longer read
-    uint32_t rb[kBinPerThread];
-#pragma unroll
-    for (int k = 0; k < kBinPerThread; ++k) {
-      rb[k] = 0;
-      if (key[k] != kEmpty) {
-        const uint32_t b = w.log2_nb ? (key[k] * kGold) >> shift : 0u;
-        rb[k] = (b << 16) | atomicAdd(&hist[b], 1u);
-      }
-    }
-    __syncthreads();
-    pdl_wait();  // the counters are zeroed by the previous kernel of the stream
-    uint32_t* ctl = w.ctl(f);
-    uint32_t total = 0;
-    for (int b0 = 0; b0 < w.nb; b0 += kBinThreads) {
-      const int b = b0 + tid;
-      const uint32_t h = b < w.nb ? hist[b] : 0u;
-      uint32_t gb = 0;
-      if (h) gb = atomicAdd(&ctl[b], h);
-      uint32_t tot;
-      const uint32_t ex = block_exscan(h, warp_sums, &tot);
-      if (b < w.nb) {
-        soff[b] = total + ex;
-        delta[b] = (uint32_t)b * (uint32_t)w.cap + gb - (total + ex);
-        if (gb + h > (uint32_t)w.cap) {
-          ctl[w.nb + kCtlOverflow] = 1u;
-          s_overflow = 1u;
-        }
-      }
-      total += tot;
-      __syncthreads();
-    }
-    if (!s_overflow) {
-#pragma unroll
-      for (int k = 0; k < kBinPerThread; ++k) {
-        if (key[k] != kEmpty)
-          stage[soff[rb[k] >> 16] + (rb[k] & 0xFFFFu)] = make_uint2(key[k], (uint32_t)(tile0 + k * kBinThreads + tid));
-      }
-      __syncthreads();
-      uint2* __restrict__ ent = w.ent(f);
-      for (uint32_t j = tid; j < total; j += kBinThreads) {
-        const uint2 e = stage[j];
-        const uint32_t b = w.log2_nb ? (e.x * kGold) >> shift : 0u;
-        ent[delta[b] + j] = e;
-      }
-    }
-    __syncthreads();  // s_overflow / stage / delta are rewritten by the next tile
   }
 }
 
@@ -1534,64 +1328,6 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
     voxel_num[f] = (int32_t)min(before + total, (uint32_t)max_voxels);
 }
 
-// The same with TWO mask words per thread (slices of 512 words, 16-bit stage entries: offset inside the slice |
-// has-record << 15) for batches whose 256-word slices would not fit the GPU in one wave (64 C4 frames: 1408
-// CTAs for 888 slots = 1.6 waves of a latency-bound kernel; here 704 CTAs).
-__global__ void __launch_bounds__(kFirstsThreads)
-hvb_scan_firsts2_kernel(const HvbWork w, const int words, const int max_voxels,
-                        int32_t* __restrict__ voxel_num) {
-  __shared__ uint32_t warp_sums[33];
-  __shared__ uint16_t stage[kFirstsThreads * 64];
-  const int f = blockIdx.y, tid = threadIdx.x;
-  pdl_wait();
-  pdl_trigger();
-  if (w.ctl(f)[w.nb + kCtlOverflow]) return;
-  const uint2* __restrict__ bm = reinterpret_cast<const uint2*>(w.bitmask(f));
-  uint32_t* __restrict__ firsts = w.firsts(f);
-  const int lo = blockIdx.x * (2 * kFirstsThreads);
-  const int wd = lo + 2 * tid;
-  uint2 m0 = make_uint2(0u, 0u), m1 = make_uint2(0u, 0u);
-  if (wd + 1 < words) {
-    const uint4 t = *reinterpret_cast<const uint4*>(bm + wd);  // (the mask is 256-byte aligned, wd is even)
-    m0 = make_uint2(t.x, t.y);
-    m1 = make_uint2(t.z, t.w);
-  } else if (wd < words) {
-    m0 = bm[wd];
-  }
-  uint32_t sum = 0;
-  for (int i0 = tid; i0 < lo; i0 += 8 * kFirstsThreads) {
-    uint32_t t[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t[k] = i0 + k * kFirstsThreads < lo ? __ldg(&bm[i0 + k * kFirstsThreads].x) : 0u;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sum += __popc(t[k]);
-  }
-  uint32_t before;
-  block_exscan(sum, warp_sums, &before);
-  __syncthreads();  // warp_sums is reused below
-  uint32_t total;
-  uint32_t pos = block_exscan((uint32_t)(__popc(m0.x) + __popc(m1.x)), warp_sums, &total);
-  uint32_t bits = m0.x;
-  while (bits) {
-    const int bit = __ffs(bits) - 1;
-    bits &= bits - 1u;
-    stage[pos++] = (uint16_t)(((uint32_t)(2 * tid) * 32u + (uint32_t)bit) | (((m0.y >> bit) & 1u) << 15));
-  }
-  bits = m1.x;
-  while (bits) {
-    const int bit = __ffs(bits) - 1;
-    bits &= bits - 1u;
-    stage[pos++] = (uint16_t)(((uint32_t)(2 * tid + 1) * 32u + (uint32_t)bit) | (((m1.y >> bit) & 1u) << 15));
-  }
-  __syncthreads();
-  for (uint32_t i = tid; i < total; i += kFirstsThreads) {
-    const uint32_t e = stage[i];
-    if (before + i < (uint32_t)max_voxels) firsts[before + i] = ((uint32_t)lo * 32u + (e & 0x3FFFu)) | ((e >> 15) << 31);
-  }
-  if (blockIdx.x == gridDim.x - 1 && tid == 0)
-    voxel_num[f] = (int32_t)min(before + total, (uint32_t)max_voxels);
-}
-
 // Expansion.  Three dependent round trips per tile of 32 voxels (firsts -> record -> rows), one of
 // each kind in flight: rows of tile t, records of tile t + 1, first-point indices of tile t + 2.
 // Records are fetched with lane = voxel; the rows are fetched with lane = OUTPUT WORD: word
@@ -2139,8 +1875,6 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
     vec_ok = !((!mean && ((uintptr_t)frames[k].voxels & 15)) || ((uintptr_t)frames[k].points & 15));
   int coors_vec = 1;
   for (int k = 0; k < num_frames && coors_vec; ++k) coors_vec = !((uintptr_t)frames[k].coors & 15);
-  bool pts_vec = true;  // TMA bulk copies of the rows need 16-byte aligned frames
-  for (int k = 0; k < num_frames && pts_vec; ++k) pts_vec = !((uintptr_t)frames[k].points & 15);
 
   int wave_idx = 0;
   for (int f0 = 0; f0 < num_frames; f0 += wave, ++wave_idx) {
@@ -2200,20 +1934,6 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
       const dim3 grid((unsigned)std::max<int64_t>((wn_max + tile - 1) / tile, 1), (unsigned)wv);
       const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
       const bool pdl = g_opt_pdl != 0;
-      // large batches of 16-byte aligned C = 4 / 5 rows: persistent CTAs fed by a TMA ring
-      const size_t ring_smem = (size_t)kRingSlots * kRingRows * c * 4 + (size_t)kBinTile * sizeof(uint2) + (size_t)3 * p.nb * 4;
-      bool ring = g_opt_bin_ring != 0 && !small && (c == 4 || c == 5) && pts_vec && ring_smem <= 100 * 1024 && wn_max < (1ll << 30);
-      if (ring) {
-        const void* rk = c == 4 ? (const void*)hvb_bin_ring_kernel<4> : (const void*)hvb_bin_ring_kernel<5>;
-        int rcs = ensure_dyn_smem(rk, c == 4 ? 5 : 6, device, ring_smem);
-        if (rcs != PCFE_OK) return rcs;
-        const int items = (int)big_tiles * wv;
-        const int slots = 148 * std::max(1, std::min(3, (int)((227 * 1024) / (ring_smem + 1280))));
-        const int per = (items + slots - 1) / slots;       // tiles per CTA
-        const unsigned rgrid = (unsigned)((items + per - 1) / per);
-        if (c == 4) PCFE_CUDA_TRY(launch_pdl(hvb_bin_ring_kernel<4>, dim3(rgrid), dim3(kBinThreads), ring_smem, st, pdl, b, w, p.g, fdiv, (int)big_tiles, wv));
-        else PCFE_CUDA_TRY(launch_pdl(hvb_bin_ring_kernel<5>, dim3(rgrid), dim3(kBinThreads), ring_smem, st, pdl, b, w, p.g, fdiv, (int)big_tiles, wv));
-      } else {
 #define PCFE_LAUNCH_BIN(CC)                                                                                              \
   do {                                                                                                                   \
     if (small) PCFE_CUDA_TRY(launch_pdl(hvb_bin_kernel<CC, kBinPerThreadSmall>, grid, dim3(kBinThreads), 0, st, pdl, b, w, p.g, c, fdiv)); \
@@ -2223,7 +1943,6 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
       else if (c == 5) PCFE_LAUNCH_BIN(5);
       else PCFE_LAUNCH_BIN(0);
 #undef PCFE_LAUNCH_BIN
-      }
       PCFE_LAUNCH_CHECK();
     }
     int rc = PCFE_OK;
@@ -2243,15 +1962,8 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
       }
       if (!clustered) {
         ProfScope ps("hvb_scan_firsts", st);
-        const int sl1 = (wnpad / 32 + kFirstsThreads - 1) / kFirstsThreads, sl2 = (wnpad / 32 + 2 * kFirstsThreads - 1) / (2 * kFirstsThreads);
-        // two words per thread when the one-word slices would need more than one wave (6 CTAs per SM)
-        const int wpt = g_opt_scan_wpt > 0 ? (int)g_opt_scan_wpt : ((int64_t)sl1 * wv > 6 * 148 ? 2 : 1);
-        if (wpt == 2)
-          PCFE_CUDA_TRY(launch_pdl(hvb_scan_firsts2_kernel, dim3((unsigned)sl2, (unsigned)wv), dim3(kFirstsThreads), 0, st, g_opt_pdl != 0,
-                                   w, wnpad / 32, max_voxels, voxel_num + f0));
-        else
-          PCFE_CUDA_TRY(launch_pdl(hvb_scan_firsts_kernel, dim3((unsigned)sl1, (unsigned)wv), dim3(kFirstsThreads), 0, st, g_opt_pdl != 0,
-                                   w, wnpad / 32, max_voxels, voxel_num + f0));
+        PCFE_CUDA_TRY(launch_pdl(hvb_scan_firsts_kernel, dim3((unsigned)((wnpad / 32 + kFirstsThreads - 1) / kFirstsThreads), (unsigned)wv),
+                                 dim3(kFirstsThreads), 0, st, g_opt_pdl != 0, w, wnpad / 32, max_voxels, voxel_num + f0));
         PCFE_LAUNCH_CHECK();
       }
       if (pack) {  // every frame's voxel count has to be known before the first row is placed

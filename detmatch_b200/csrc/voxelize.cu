@@ -58,8 +58,6 @@ extern Knob g_opt_pdl;
 extern Knob g_opt_pib_grid;
 extern Knob g_opt_no_fast_div;
 extern Knob g_opt_expand_prefetch;
-extern Knob g_opt_bin_ring;
-extern Knob g_opt_scan_wpt;
 
 namespace {
 
@@ -494,8 +492,6 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_bin_small")) g_opt_bin_small = value;
   else if (!strcmp(name, "hv_warp_dedup")) g_opt_warp_dedup = value;
   else if (!strcmp(name, "hv_expand_tiles")) g_opt_expand_tiles = value;
-  else if (!strcmp(name, "hv_bin_ring")) g_opt_bin_ring = value;
-  else if (!strcmp(name, "hv_scan_wpt")) g_opt_scan_wpt = value;
   else return PCFE_ERR_SHAPE;
   return PCFE_OK;
 }

@@ -13,7 +13,7 @@ from tests.helpers import assert_same_bits
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["record", "ring", "cluster", "fallback", "general", "global", "waves"])
+@pytest.fixture(params=["record", "cluster", "fallback", "general", "global", "waves"])
 def pack_mode(request):
     """record: packed rows from the expansion kernel; cluster: the same with the frame's partition +
     grouping done by one thread-block cluster (hv_cluster.cuh); fallback: every frame through the two-stage
@@ -25,11 +25,7 @@ def pack_mode(request):
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "general" else 0)
     _cabi.debug_set("hv_wave", 2 if mode == "waves" else 0)
     _cabi.debug_set("hv_cluster", 1 if mode == "cluster" else 0)
-    _cabi.debug_set("hv_bin_small", 0 if mode == "ring" else 2)  # ring: the persistent TMA-ring partition kernel for every batch size
-    _cabi.debug_set("hv_scan_wpt", 2 if mode == "ring" else 0)  # ... and the two-words-per-thread numbering kernel
     yield mode
-    _cabi.debug_set("hv_bin_small", 2)
-    _cabi.debug_set("hv_scan_wpt", 0)
     for k in ("hv_path", "hv_force_overflow", "hv_bucket_variant", "hv_wave"):
         _cabi.debug_set(k, 0)
     _cabi.debug_set("hv_cluster", 0)

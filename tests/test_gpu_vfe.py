@@ -61,7 +61,7 @@ def test_standalone_device_side_row_limit_and_empty():
     assert e.shape == (0, 4)
 
 
-@pytest.fixture(params=["record", "ring", "cluster", "fallback", "general", "global"])
+@pytest.fixture(params=["record", "cluster", "fallback", "general", "global"])
 def mean_mode(request):
     """record: the fused epilogue of the expansion kernel; cluster: the same with the frame's partition +
     grouping done by one thread-block cluster (hv_cluster.cuh); fallback: every frame forced through the
@@ -72,11 +72,7 @@ def mean_mode(request):
     _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "general" else 0)
     _cabi.debug_set("hv_cluster", 1 if mode == "cluster" else 0)
-    _cabi.debug_set("hv_bin_small", 0 if mode == "ring" else 2)  # ring: the persistent TMA-ring partition kernel for every batch size
-    _cabi.debug_set("hv_scan_wpt", 2 if mode == "ring" else 0)  # ... and the two-words-per-thread numbering kernel
     yield mode
-    _cabi.debug_set("hv_bin_small", 2)
-    _cabi.debug_set("hv_scan_wpt", 0)
     for k in ("hv_path", "hv_force_overflow", "hv_bucket_variant"):
         _cabi.debug_set(k, 0)
     _cabi.debug_set("hv_cluster", 0)

@@ -15,11 +15,10 @@ pytestmark = pytest.mark.gpu
 KITTI = [0, -40, -3, 70.4, 40, 1]
 
 
-@pytest.fixture(autouse=True, params=["launches", "ring", "dedup", "cluster", "bucket_general", "global", "fallback"])
+@pytest.fixture(autouse=True, params=["launches", "dedup", "cluster", "bucket_general", "global", "fallback"])
 def hv_mode(request):
     """Every test runs against all hard-voxelize implementations behind the one entry point: the
-    bucket path as a launch sequence (default; record kernels where P == 5 and C = 4 / 5), the same with
-    the persistent TMA-ring partition kernel forced on (by default only large batches take it), the
+    bucket path as a launch sequence (default; record kernels where P == 5 and C = 4 / 5), the record
     same with warp-level __match_any_sync key de-duplication in front of the bucket table, the record
     path with one thread-block cluster per frame (hv_cluster.cuh: measured slower, kept as the
     round-2 DSMEM experiment), the general bucket kernels (register-sorted chains for P <= 8, bitonic ranks
@@ -32,12 +31,7 @@ def hv_mode(request):
     _cabi.debug_set("hv_warp_dedup", 1 if mode == "dedup" else 0)
     _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "bucket_general" else 0)
-    _cabi.debug_set("hv_bin_small", 0 if mode == "ring" else 2)  # 0: 4096-point tiles whatever the batch size
-    _cabi.debug_set("hv_bin_ring", 1)
-    _cabi.debug_set("hv_scan_wpt", 2 if mode == "ring" else 0)  # ... and the two-words-per-thread numbering kernel
     yield mode
-    _cabi.debug_set("hv_bin_small", 2)
-    _cabi.debug_set("hv_scan_wpt", 0)
     _cabi.debug_set("hv_path", 0)
     _cabi.debug_set("hv_cluster", 0)
     _cabi.debug_set("hv_warp_dedup", 0)
