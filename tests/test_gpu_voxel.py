@@ -471,3 +471,32 @@ def test_workspace_query_covers_three_feature_rows():
     rng = np.random.default_rng(5)
     pts = rng.uniform([0, -4, -3], [8, 4, 1], size=(5000, 3)).astype(np.float32)
     _check_hard(pts, [0.5, 0.5, 0.5], KITTI, 300, 50, "C=3 P=300")
+
+
+@pytest.mark.parametrize("P,C", [(64, 5), (32, 4), (20, 4)])
+def test_long_voxels_into_dirty_output_buffers(P, C):
+    """Pillar shapes (the hvb_expand_words path) through a pre-allocated plan whose outputs start out as NaN
+    bit patterns and are reused by a second run: every word of a row < voxel_num must have been written --
+    short pillars, a pillar longer than P, frames with fewer points than max_voxels, an empty frame."""
+    from detmatch_b200.ops.voxel import HardVoxelizeBatchPlan
+    cfg = synth.CONFIGS["C5"]
+    vs, rg, V = cfg["voxel_size"], cfg["point_cloud_range"], 3000
+    frames = [synth.lidar_frame(n, C, 8800 + 13 * k + P, cfg["r_max"]).numpy() for k, n in enumerate((40000, 2500, 0, 9000))]
+    rng = np.random.default_rng(5 + P)
+    for fr, (lo, cnt) in zip((frames[0], frames[3]), ((100, 200), (5, 37))):  # one very dense and one medium pillar
+        fr[lo:lo + cnt, 0] = 10.3 + 0.2 * rng.random(cnt).astype(np.float32)
+        fr[lo:lo + cnt, 1] = -7.1 + 0.2 * rng.random(cnt).astype(np.float32)
+    plan = HardVoxelizeBatchPlan([len(f) for f in frames], C, vs, rg, P, V, "cuda:0")
+    for t in (plan.voxels, plan.coors, plan.num_points):
+        t.view(torch.int32).fill_(-1)  # NaN bit pattern / -1
+    plan.bind([torch.from_numpy(f).cuda() for f in frames])
+    for _ in range(2):  # the second run sees the first one's leftovers
+        vox, coors, num, vnum = plan.run()
+    counts = vnum.cpu().tolist()
+    for k, fr in enumerate(frames):
+        ev, ec, en = oracle.hard_voxelize(fr, vs, rg, P, V)
+        assert counts[k] == len(en)
+        assert_same_bits(num[k, :counts[k]].cpu().numpy(), en, f"frame {k} num")
+        assert_same_bits(coors[k, :counts[k]].cpu().numpy(), ec, f"frame {k} coors")
+        assert_same_bits(vox[k, :counts[k]].cpu().numpy(), ev, f"frame {k} voxels")
+    assert int(num[0, :counts[0]].max()) == P
