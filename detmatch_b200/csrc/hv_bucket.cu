@@ -1352,6 +1352,24 @@ hvb_scan_firsts_kernel(const HvbWork w, const int words, const int max_voxels,
 // openpcdet.py:69-76 / voxelnet.py:60-67): every frame's buffers are the SAME arrays, frame f writes
 // its rows at offset sum(voxel_num of the batch's earlier frames) and its coordinates as
 // (batch index, z, y, x) rows of 16 bytes.
+#ifndef PCFE_EXP_POLICY
+#define PCFE_EXP_POLICY 2  // (measured: 2 = -0.45 % of the C4 step, 1 and 4 slower) bit 0: row gathers L2 evict_last, bit 1: row prefetch evict_last, bit 2: firsts / records evict_first
+#endif
+__device__ __forceinline__ float ldg_hint(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_hint(const uint32_t* p, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_hint(const uint4* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
 template <int C, bool MEAN, bool PACK>
 __global__ void __launch_bounds__(kExpThreads, MEAN ? PCFE_EXP_MEAN_MINB : PCFE_EXP_REC_MINB)
 hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const GridParams g,
@@ -1370,6 +1388,11 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t* eff = eff_all + (MEAN ? 0 : wid * (32 * W));
   int32_t* cstage = coor_all + wid * 96;
+  uint64_t pol_last = 0, pol_first = 0;
+  if (PCFE_EXP_POLICY) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+  }
 #pragma unroll 1
   for (int wi = blockIdx.x; wi < tiles_x * frames; wi += gridDim.x) {
   const int f = wi / tiles_x, bx = wi - f * tiles_x;
@@ -1380,6 +1403,9 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     const size_t lo = (size_t)bx * slice + (size_t)threadIdx.x * (slice / 32);
     if (lo < total) {
       const uint32_t bytes = (uint32_t)min(slice / 32, total - lo);
+      if (PCFE_EXP_POLICY & 2)
+        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(reinterpret_cast<const char*>(nf.pts) + lo), "r"(bytes), "l"(pol_last) : "memory");
+      else
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(nf.pts) + lo), "r"(bytes) : "memory");
     }
   }
@@ -1401,10 +1427,11 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   }
 
   // firsts[v] = first point of voxel v | (the voxel has more points: see rec[first]) << 31
-  auto load_first = [&](int v0) { return v0 + lane < m ? __ldg(firsts + v0 + lane) : kEmpty; };
+  auto load_first = [&](int v0) { return v0 + lane < m ? ((PCFE_EXP_POLICY & 4) ? ldg_hint(firsts + v0 + lane, pol_first) : __ldg(firsts + v0 + lane)) : kEmpty; };
   auto load_rec = [&](uint32_t fi) {
     uint4 r = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);  // no points besides the first
-    if (fi != kEmpty && (fi >> 31)) r = __ldg(rec + PCFE_REC_STRIDE * (size_t)(fi & 0x7FFFFFFFu));
+    if (fi != kEmpty && (fi >> 31))
+      r = (PCFE_EXP_POLICY & 4) ? ldg_hint(rec + PCFE_REC_STRIDE * (size_t)(fi & 0x7FFFFFFFu), pol_first) : __ldg(rec + PCFE_REC_STRIDE * (size_t)(fi & 0x7FFFFFFFu));
     return r;
   };
   const FastAxes fa = make_fast_axes(g);
@@ -1433,7 +1460,8 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     float px = 0.f, py = 0.f, pz = 0.f;
     if (have) {
       const float* __restrict__ fp = pts + (size_t)first * C;
-      px = __ldg(fp); py = __ldg(fp + 1); pz = __ldg(fp + 2);
+      if (PCFE_EXP_POLICY & 1) { px = ldg_hint(fp, pol_last); py = ldg_hint(fp + 1, pol_last); pz = ldg_hint(fp + 2, pol_last); }
+      else { px = __ldg(fp); py = __ldg(fp + 1); pz = __ldg(fp + 2); }
       fr.num[off + v0 + lane] = (int32_t)len;
     }
     __syncwarp();
@@ -1468,7 +1496,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     for (int k = 0; k < HW; ++k) {
       const uint32_t src = eff[lane + 32 * k];  // word lane + 32 k of the tile
       val[k] = 0.0f;
-      if (src != kEmpty) val[k] = __ldg(pts + src);
+      if (src != kEmpty) val[k] = (PCFE_EXP_POLICY & 1) ? ldg_hint(pts + src, pol_last) : __ldg(pts + src);
     }
     }
     // records of the next tile, first-point indices of the one after
