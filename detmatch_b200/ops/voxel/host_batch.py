@@ -5,7 +5,7 @@ concatenated ``(voxels, num_points, coors_batch)``.  ``voxelize_batch_host`` doe
 HOST frames with the results in (pinned) HOST memory: every frame is uploaded, voxelized on the GPU --
 there is no CPU code path -- and the concatenated rows are read back.
 
-The batch is cut into chunks of ``chunk`` frames on three streams: the upload of chunk i + 1, the
+The batch is cut into chunks of ``chunk`` frames (the first one shorter) on three streams: the upload of chunk i + 1, the
 kernels of chunk i and the read-back of chunk i - 1 overlap.  A chunk runs the packed C-ABI call
 (``pcfe_hard_voxelize_packed_batch_f32``: concatenated rows written by the expansion kernel itself, no
 ``torch.cat`` staging), so one chunk leaves the device with three copies that land directly at their
@@ -36,7 +36,11 @@ class HostVoxelizePipeline:
         self.voxel_size, self.coors_range = list(voxel_size), list(coors_range)
         self.vs, self.rg = _cabi.f3(voxel_size), _cabi.f6(coors_range)
         F = len(self.sizes)
-        self.chunks = [list(range(i, min(i + chunk, F))) for i in range(0, F, chunk)]
+        # a short first chunk: nothing overlaps its upload, so the pipeline fills in a quarter of the time
+        # (64 C4 frames, chunk 8: chunks of 2, 6, 8, 8, ...)
+        first = max(1, chunk // 4) if F > chunk else chunk
+        cuts = sorted({0, min(first, F), *range(chunk, F, chunk), F})
+        self.chunks = [list(range(a, b)) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
         self.packed = self.p == 5 and self.c in (4, 5)
         self.dpts = [torch.empty((n, self.c), dtype=torch.float32, device=dev) for n in self.sizes]
         caps = [sum(min(self.sizes[k], self.v) for k in ch) for ch in self.chunks]
