@@ -1570,29 +1570,31 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
 }
 
 // ---- expansion for long voxels (pillars: P * C = 320 words, a multiple of 4) -----------------------
-// A warp owns kWordsVox consecutive voxels.  Lane = voxel for the cell records (one coalesced load),
-// the key decoding (host-computed reciprocals, all lanes busy) and the coordinate / count stores; then
-// the voxels are written one after the other with lane = output word: the len * C real words of a
-// voxel -- word w belongs to slot w / C, feature w % C -- are gathered through the voxel's list and
-// leave as coalesced streaming stores, everything behind them is stored as float4 zeros directly: no
-// shared memory, no zero-fill pass.  The two dependent loads of a voxel's first 32 words (list entry
-// -> row word) are software-pipelined over the voxels: the list entries of voxel j + 2 and the row
-// words of voxel j + 1 are in flight while voxel j is stored (a pillar holds 6 points on average, so
-// those 32 words are usually all it has).  C == 0: features per point at run time.  Needs 16-byte
-// aligned voxel buffers.  (First version -- one voxel per lane-0 decode, four voxels per warp, idx and
-// row fetched per float4 element: 211 warp-instructions per voxel, 0.191 ms per 16-frame C5 step at 64 %
-// issue-active and 57 % DRAM, profiles/r02_c5_ncu_summary.txt.)
+// A warp owns kWordsVox consecutive voxels, which are contiguous in memory: ONE run of nvox * W / 4 float4s.
+// Lane = voxel for the cell records (one coalesced load), the key decoding (host-computed reciprocals)
+// and the coordinate / count stores; then
+//   phase 1  every float4 behind its voxel's data is a zero store (depends on the cell records only);
+//   phase 2  the data float4s of all voxels, numbered through a prefix over the voxels' lengths: list
+//            entries and row words are fetched by the lane that stores them -- two dependent loads, all
+//            lanes busy whatever the lengths are.
+// The zero stores are in flight while phase 2 waits for its lists and rows.  No shared memory.  C == 0:
+// features per point at run time.  Needs 16-byte aligned voxel buffers.
+// History (profiles/r02_summary.md): a first version decoded one voxel at a time (211 warp-instructions
+// per voxel, 0.191 ms per 16-frame C5 step); the second walked the voxels one after the other with lane =
+// output word and the lists two voxels ahead (123 per voxel, 0.183 ms, issue-active 64 %, DRAM 57 %); this
+// one needs ~50 per voxel and is no faster at 8 voxels per warp (0.187 ms): the kernel is bound by how its
+// writes reach DRAM -- a variant with the data phase cut out still takes 0.154 ms for 700 MB of zeros where a
+// grid-stride fill of the same bytes runs at 7.1 TB/s.  What helps is a SMALLER contiguous region per CTA
+// (the chip then writes a narrower window at any moment): 4 voxels per warp 0.176 ms, 2: 0.179, 1: 0.220, 16: 0.200.
 #ifndef PCFE_WORDS_VOX
-#define PCFE_WORDS_VOX 8
+#define PCFE_WORDS_VOX 4
 #endif
-// voxels per warp: short warp tasks keep the voxels in flight on the chip within about one frame, whose
-// rows then stay in L2 between the two touches every 32-byte sector of a shuffled frame gets on average
-// (32 voxels per warp: 0.298 ms and 2.4 x the DRAM reads, profiles/r02_c5_words32_ncu.txt)
 constexpr int kWordsVox = PCFE_WORDS_VOX;
 template <int C>
 __global__ void __launch_bounds__(kExpThreads)
 hvb_expand_words_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, const KeyDecode kd,
-                        const int c_rt, const int max_points, const int32_t* __restrict__ voxel_num) {
+                             const int c_rt, const int max_points, const int32_t* __restrict__ voxel_num,
+                             const uint32_t m_w4 /* ceil(2^16 / (W / 4)) when i / (W / 4) = (i * m_w4) >> 16 holds for all i < kWordsVox * W / 4, else 0 */) {
   const int f = blockIdx.y;
   pdl_wait();
   if (w.ctl(f)[w.nb + kCtlOverflow]) return;
@@ -1608,8 +1610,22 @@ hvb_expand_words_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, 
   if (v0 >= m) return;
   const int nvox = min(kWordsVox, m - v0);
   uint4 cl = make_uint4(0u, 0u, 0u, 0u);  // key, len, list_off, first
+  if (lane < nvox) cl = __ldg(vcell + v0 + lane);
+  const uint32_t len = min(cl.y, (uint32_t)max_points);
+  const uint32_t nreal = len * (uint32_t)c;          // 0 for lanes >= nvox
+  const uint32_t nreal4 = (nreal + 3u) >> 2;          // data float4s of the lane's voxel (the last one zero-padded)
+  float4* __restrict__ dst4 = reinterpret_cast<float4*>(fr.voxels + (size_t)v0 * W);
+  // phase 1: zero padding
+  const int total4 = nvox * W4;
+#pragma unroll 2
+  for (int i4 = lane; i4 < ((total4 + 31) & ~31); i4 += 32) {
+    const uint32_t v = m_w4 ? ((uint32_t)i4 * m_w4) >> 16 : (uint32_t)i4 / (uint32_t)W4;
+    const uint32_t r4 = (uint32_t)i4 - v * (uint32_t)W4;
+    const uint32_t nr4 = __shfl_sync(0xFFFFFFFFu, nreal4, (int)(v & 31u));
+    if (i4 < total4 && r4 >= nr4) __stcs(dst4 + i4, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+  // coordinates and counts
   if (lane < nvox) {
-    cl = __ldg(vcell + v0 + lane);
     const uint32_t cz = div_small_err(cl.x, kd.plane, kd.m_plane);
     const uint32_t rem = cl.x - cz * kd.plane;
     const uint32_t cy = div_small_err(rem, kd.gx, kd.m_gx);
@@ -1617,72 +1633,42 @@ hvb_expand_words_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, 
     co[0] = (int32_t)cz;
     co[1] = (int32_t)cy;
     co[2] = (int32_t)(rem - cy * kd.gx);
-    fr.num[v0 + lane] = (int32_t)min(cl.y, (uint32_t)max_points);
+    fr.num[v0 + lane] = (int32_t)len;
   }
-  const int sl0 = lane / c, q0 = lane - sl0 * c;  // slot and feature of word `lane`
-  // The list of voxel j (its first 64 entries) lives in two registers per lane, fetched two voxels
-  // ahead; every row word of the voxel is then addressed through shuffles, so all of a voxel's row
-  // loads are independent of each other (a full pillar is 10 loads per lane in flight at once).
-  auto len_of = [&](int j) { return (int)min(__shfl_sync(0xFFFFFFFFu, cl.y, j & 31), (uint32_t)max_points); };
-  auto load_list = [&](int j, int len, uint32_t& a, uint32_t& b) {
-    const uint32_t off = __shfl_sync(0xFFFFFFFFu, cl.z, j & 31);
-    a = (j < nvox && lane < len) ? __ldg(lst + off + lane) : kEmpty;
-    b = (j < nvox && lane + 32 < len) ? __ldg(lst + off + 32 + lane) : kEmpty;
-  };
-  auto first_val = [&](uint32_t a) {  // word `lane` of a voxel: slot sl0 <= 10
-    const uint32_t idx = __shfl_sync(0xFFFFFFFFu, a, sl0);
-    return idx != kEmpty ? __ldg(pts + (size_t)idx * c + q0) : 0.0f;
-  };
-  int len_c = len_of(0), len_n = len_of(1), len_nn = 0;
-  uint32_t la_c, lb_c, la_n, lb_n, la_nn = kEmpty, lb_nn = kEmpty;
-  load_list(0, len_c, la_c, lb_c);
-  load_list(1, len_n, la_n, lb_n);
-  float val_c = first_val(la_c);
-  constexpr int kTail = 4;  // 32-word groups fetched together behind the first one
-#pragma unroll 1
-  for (int j = 0; j < nvox; ++j) {
-    // lists of voxel j + 2, first row words of voxel j + 1
-    len_nn = len_of(j + 2);
-    load_list(j + 2, len_nn, la_nn, lb_nn);
-    const float val_n = first_val(la_n);
-    const int nreal = len_c * c;
-    const int nreal4 = (nreal + 3) & ~3;  // <= W
-    const uint32_t off = __shfl_sync(0xFFFFFFFFu, cl.z, j);
-    float* __restrict__ dst = fr.voxels + (size_t)(v0 + j) * W;
-    float o[kTail];
-    auto tail_load = [&](const int w0) {  // row words w0 .. w0 + 32 kTail - 1, all loads independent
+  // phase 2: data float4s, numbered d = 0 .. D - 1 through the voxels
+  uint32_t incl = nreal4;
 #pragma unroll
-      for (int k = 0; k < kTail; ++k) {
-        const int wd = w0 + 32 * k + lane;
-        const int sl = wd / c;
-        const uint32_t xa = __shfl_sync(0xFFFFFFFFu, la_c, sl & 31), xb = __shfl_sync(0xFFFFFFFFu, lb_c, sl & 31);
+  for (int d = 1; d < kWordsVox; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const uint32_t D = __shfl_sync(0xFFFFFFFFu, incl, kWordsVox - 1);
+  uint32_t bound[kWordsVox];  // inclusive prefix of every voxel, in every lane
+#pragma unroll
+  for (int j = 0; j < kWordsVox; ++j) bound[j] = __shfl_sync(0xFFFFFFFFu, incl, j);
+  for (uint32_t d0 = 0; d0 < D; d0 += 32) {  // warp-uniform trip count
+    const uint32_t d = d0 + (uint32_t)lane;
+    uint32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < kWordsVox - 1; ++j) v += d >= bound[j] ? 1u : 0u;
+    const uint32_t inc_v = __shfl_sync(0xFFFFFFFFu, incl, (int)v), n4_v = __shfl_sync(0xFFFFFFFFu, nreal4, (int)v);
+    const uint32_t nr_v = __shfl_sync(0xFFFFFFFFu, nreal, (int)v), off_v = __shfl_sync(0xFFFFFFFFu, cl.z, (int)v);
+    if (d < D) {
+      const uint32_t r4 = d - (inc_v - n4_v);
+      const uint32_t w0 = 4u * r4;
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t wd = w0 + (uint32_t)k;
         o[k] = 0.0f;
-        if (wd < nreal) {
-          const uint32_t idx = sl < 32 ? xa : sl < 64 ? xb : __ldg(lst + off + sl);
-          o[k] = __ldg(pts + (size_t)idx * c + (wd - sl * c));
+        if (wd < nr_v) {
+          const uint32_t sl = wd / (uint32_t)c;
+          const uint32_t idx = __ldg(lst + off_v + sl);
+          o[k] = __ldg(pts + (size_t)idx * c + (wd - sl * (uint32_t)c));
         }
       }
-    };
-    auto tail_store = [&](const int w0) {
-#pragma unroll
-      for (int k = 0; k < kTail; ++k) {
-        const int wd = w0 + 32 * k + lane;
-        if (wd < nreal4) __stcs(dst + wd, o[k]);
-      }
-    };
-    // loads first, then the stores that depend on nothing (the zero padding), then the data
-    if (32 < nreal4) tail_load(32);  // voxels with more than 32 real words (warp-uniform)
-    float4* __restrict__ dst4 = reinterpret_cast<float4*>(dst);
-    for (int i4 = (nreal4 >> 2) + lane; i4 < W4; i4 += 32) __stcs(dst4 + i4, make_float4(0.f, 0.f, 0.f, 0.f));
-    if (lane < nreal4) __stcs(dst + lane, val_c);  // words nreal .. nreal4 - 1 are zero padding
-    if (32 < nreal4) tail_store(32);
-#pragma unroll 1
-    for (int w0 = 32 + 32 * kTail; w0 < nreal4; w0 += 32 * kTail) {
-      tail_load(w0);
-      tail_store(w0);
+      __stcs(dst4 + (size_t)v * W4 + r4, make_float4(o[0], o[1], o[2], o[3]));
     }
-    len_c = len_n; la_c = la_n; lb_c = lb_n; val_c = val_n;
-    len_n = len_nn; la_n = la_nn; lb_n = lb_nn;
   }
 }
 
@@ -2088,9 +2074,13 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
         // long voxels: lane = output word, 32 voxels per warp, one after the other
         const KeyDecode kd = make_key_decode(p.g);
         const dim3 wgrid((unsigned)((vmax + kExpWarps * kWordsVox - 1) / (kExpWarps * kWordsVox)), (unsigned)wv);
-        if (c == 4) hvb_expand_words_kernel<4><<<wgrid, kExpThreads, 0, st>>>(b, w, kd, c, max_points, vn);
-        else if (c == 5) hvb_expand_words_kernel<5><<<wgrid, kExpThreads, 0, st>>>(b, w, kd, c, max_points, vn);
-        else hvb_expand_words_kernel<0><<<wgrid, kExpThreads, 0, st>>>(b, w, kd, c, max_points, vn);
+        const int w4 = max_points * c / 4;
+        uint32_t m_w4 = (int64_t)kWordsVox * w4 < 65536 ? (uint32_t)((65536 + w4 - 1) / w4) : 0u;
+        for (int i = 0; m_w4 && i < kWordsVox * w4 + 32; ++i)
+          if ((int)(((uint32_t)i * m_w4) >> 16) != i / w4) m_w4 = 0u;  // (the reciprocal must be exact on the range used)
+        if (c == 4) hvb_expand_words_kernel<4><<<wgrid, kExpThreads, 0, st>>>(b, w, kd, c, max_points, vn, m_w4);
+        else if (c == 5) hvb_expand_words_kernel<5><<<wgrid, kExpThreads, 0, st>>>(b, w, kd, c, max_points, vn, m_w4);
+        else hvb_expand_words_kernel<0><<<wgrid, kExpThreads, 0, st>>>(b, w, kd, c, max_points, vn, m_w4);
         PCFE_LAUNCH_CHECK();
       } else if (c == 4) rc = launch_expand<4>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
       else if (c == 5) rc = launch_expand<5>(grid, st, b, w, p.g, c, max_points, p.exp_vt, vn, vec_ok);
