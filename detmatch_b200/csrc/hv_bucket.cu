@@ -60,6 +60,7 @@ Knob g_opt_expand_tiles{0};     // > 0: 32-voxel tiles per warp of the record ex
 Knob g_opt_warp_dedup{0};       // 1: warp-level key de-duplication (__match_any_sync) in front of the bucket table
 Knob g_opt_bin_small{2};        // partition tile: 0 = 4096 points, 1 = 1024 points, 2 = by batch size
 Knob g_opt_overlap{1};          // 0: waves of a multi-wave batch run one after the other on the caller's stream
+Knob g_opt_expand_map{2};       // record expansion, tiles of a warp: 0 consecutive, 1 round-robin inside the CTA, 2 round-robin over the frame (default: measured best)
 Knob g_opt_cluster{0};          // 1: record path with one thread-block cluster per frame (hv_cluster.cuh) -- measured slower, see profiles/r02_cluster_*
 
 namespace {
@@ -1379,7 +1380,8 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
                       const int tiles_x /* CTA-tiles per frame; the 1-D grid strides over tiles_x * frames */,
                       const int32_t* __restrict__ vn_all /* PACK: voxel_num of the batch's frame 0 */,
                       const int f_first /* PACK: batch index of this launch's frame 0 */,
-                      const int pipe_tiles /* 32-voxel tiles per warp */) {
+                      const int pipe_tiles /* 32-voxel tiles per warp */,
+                      const int map /* which tiles a warp takes, see below */) {
   constexpr int PT = 5;
   constexpr int W = PT * C;  // output words per voxel
   // source word (point index * C + feature) of every output word of a warp's tile, kEmpty = zero
@@ -1417,7 +1419,20 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   const uint32_t* __restrict__ firsts = w.firsts(f);
   const uint4* __restrict__ rec = w.rec(f);
   const float* __restrict__ pts = fr.pts;
-  const int vbase = (bx * kExpWarps + wid) * (pipe_tiles * 32);
+  // tile of the warp's step `it`: base + it * tstride.  map 0: a warp's tiles are consecutive; 1: the CTA's
+  // tiles are dealt to its warps round-robin (the CTA writes one contiguous run per step); 2: the frame's
+  // tiles are dealt to all its warps round-robin (the frame is written as one moving window)
+  int tbase = (bx * kExpWarps + wid) * pipe_tiles, tstride = 1;
+  if (map == 1) {
+    tbase = bx * kExpWarps * pipe_tiles + wid;
+    tstride = kExpWarps;
+  } else if (map == 2) {
+    const int nct = (m + 32 * kExpWarps * pipe_tiles - 1) / (32 * kExpWarps * pipe_tiles);  // CTAs the frame needs
+    if (bx >= nct) continue;
+    tbase = bx * kExpWarps + wid;
+    tstride = kExpWarps * nct;
+  }
+  const int vbase = tbase * 32, vstride = tstride * 32;
   if (vbase >= m) continue;  // warp-uniform
   size_t off = 0;  // PACK: rows of the earlier frames
   if (PACK) {
@@ -1436,12 +1451,12 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   };
   const FastAxes fa = make_fast_axes(g);
   uint32_t fi_cur = load_first(vbase);
-  uint32_t fi_nxt = load_first(vbase + 32);
+  uint32_t fi_nxt = load_first(vbase + vstride);
   uint4 ra_cur = load_rec(fi_cur);
 
 #pragma unroll 1
   for (int it = 0; it < pipe_tiles; ++it) {
-    const int v0 = vbase + it * 32;
+    const int v0 = vbase + it * vstride;
     if (v0 >= m) break;  // warp-uniform
     const int nvox = min(32, m - v0);
     const bool have = fi_cur != kEmpty;  // false for lanes past the end
@@ -1501,7 +1516,7 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
     }
     // records of the next tile, first-point indices of the one after
     const uint4 ra_nxt = load_rec(fi_nxt);
-    const uint32_t fi_nn = load_first(v0 + 64);
+    const uint32_t fi_nn = load_first(v0 + 2 * vstride);
     if (have) {  // voxelization_cpu.cpp:23-29 (the point is in range: it produced a cell key)
       const float ax = __fsub_rn(px, g.x0), ay = __fsub_rn(py, g.y0), az = __fsub_rn(pz, g.z0);
       float qx, qy, qz;
@@ -1990,9 +2005,12 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
         ProfScope ps("hvb_expand", st);
         const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
         const int64_t vmax = std::max<int64_t>(std::min<int64_t>(max_voxels, wn_max), 1);
-        // tiles per warp: 3 (B = 4 / 8 / 16 / 64 frames: 0.0350 / 0.0602 / 0.1063 / 0.354 ms; 4 tiles: 0.0377 /
-        // 0.0613 / 0.1072 / 0.355; `hv_expand_tiles` overrides)
-        const int pipe_tiles = g_opt_expand_tiles > 0 ? (int)g_opt_expand_tiles : 3;
+        // tiles per warp, dealt round-robin over the frame's warps (hv_expand_map = 2: the frame is written as a
+        // moving window instead of 38 KB regions per CTA -- DRAM takes a narrow write window much better,
+        // profiles/r02_summary.md): 4 for batches of 16 frames and more (64 frames: 3 / 4 / 5 tiles = 0.3508 /
+        // 0.3452 / 0.3481 ms, consecutive tiles: 0.3553; 32 frames 0.1868 / 0.1850 / 0.1867), 3 below (4 frames:
+        // 0.0350 / 0.0388); `hv_expand_tiles` overrides
+        const int pipe_tiles = g_opt_expand_tiles > 0 ? (int)g_opt_expand_tiles : (wv >= 16 ? 4 : 3);
         const int pper = kExpWarps * pipe_tiles * 32;
         const dim3 pgrid((unsigned)((vmax + pper - 1) / pper), (unsigned)wv);
         const int32_t* vn = voxel_num + f0;
@@ -2002,7 +2020,7 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
         const bool pdl = g_opt_pdl != 0;
 #define PCFE_LAUNCH_EXPAND_REC(CC, MM, PP)                                                                      \
   PCFE_CUDA_TRY(launch_pdl(hvb_expand_rec_kernel<CC, MM, PP>, dim3(egrid), dim3(kExpThreads), 0, st, pdl, b, w, p.g, \
-                           fdiv, vn, wv, (int)g_opt_expand_prefetch, coors_vec, tiles_x, (const int32_t*)voxel_num, f0, pipe_tiles))
+                           fdiv, vn, wv, (int)g_opt_expand_prefetch, coors_vec, tiles_x, (const int32_t*)voxel_num, f0, pipe_tiles, (int)g_opt_expand_map))
 #define PCFE_LAUNCH_EXPAND_REC_C(CC)                                \
   do {                                                              \
     if (mean && pack) PCFE_LAUNCH_EXPAND_REC(CC, true, true);       \

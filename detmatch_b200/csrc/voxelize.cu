@@ -58,6 +58,7 @@ extern Knob g_opt_pdl;
 extern Knob g_opt_pib_grid;
 extern Knob g_opt_no_fast_div;
 extern Knob g_opt_expand_prefetch;
+extern Knob g_opt_expand_map;
 
 namespace {
 
@@ -492,6 +493,7 @@ extern "C" int pcfe_debug_set(const char* name, int value) {
   else if (!strcmp(name, "hv_bin_small")) g_opt_bin_small = value;
   else if (!strcmp(name, "hv_warp_dedup")) g_opt_warp_dedup = value;
   else if (!strcmp(name, "hv_expand_tiles")) g_opt_expand_tiles = value;
+  else if (!strcmp(name, "hv_expand_map")) g_opt_expand_map = value;
   else return PCFE_ERR_SHAPE;
   return PCFE_OK;
 }

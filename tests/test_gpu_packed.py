@@ -13,7 +13,7 @@ from tests.helpers import assert_same_bits
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["record", "cluster", "fallback", "general", "global", "waves"])
+@pytest.fixture(params=["record", "map0", "map1", "cluster", "fallback", "general", "global", "waves"])
 def pack_mode(request):
     """record: packed rows from the expansion kernel; cluster: the same with the frame's partition +
     grouping done by one thread-block cluster (hv_cluster.cuh); fallback: every frame through the two-stage
@@ -25,7 +25,9 @@ def pack_mode(request):
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "general" else 0)
     _cabi.debug_set("hv_wave", 2 if mode == "waves" else 0)
     _cabi.debug_set("hv_cluster", 1 if mode == "cluster" else 0)
+    _cabi.debug_set("hv_expand_map", {"map0": 0, "map1": 1}.get(mode, 2))  # record expansion: which tiles a warp takes
     yield mode
+    _cabi.debug_set("hv_expand_map", 2)
     for k in ("hv_path", "hv_force_overflow", "hv_bucket_variant", "hv_wave"):
         _cabi.debug_set(k, 0)
     _cabi.debug_set("hv_cluster", 0)

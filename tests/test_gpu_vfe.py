@@ -61,7 +61,7 @@ def test_standalone_device_side_row_limit_and_empty():
     assert e.shape == (0, 4)
 
 
-@pytest.fixture(params=["record", "cluster", "fallback", "general", "global"])
+@pytest.fixture(params=["record", "map0", "map1", "cluster", "fallback", "general", "global"])
 def mean_mode(request):
     """record: the fused epilogue of the expansion kernel; cluster: the same with the frame's partition +
     grouping done by one thread-block cluster (hv_cluster.cuh); fallback: every frame forced through the
@@ -72,7 +72,9 @@ def mean_mode(request):
     _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "general" else 0)
     _cabi.debug_set("hv_cluster", 1 if mode == "cluster" else 0)
+    _cabi.debug_set("hv_expand_map", {"map0": 0, "map1": 1}.get(mode, 2))  # record expansion: which tiles a warp takes
     yield mode
+    _cabi.debug_set("hv_expand_map", 2)
     for k in ("hv_path", "hv_force_overflow", "hv_bucket_variant"):
         _cabi.debug_set(k, 0)
     _cabi.debug_set("hv_cluster", 0)

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 KITTI = [0, -40, -3, 70.4, 40, 1]
 
 
-@pytest.fixture(autouse=True, params=["launches", "dedup", "cluster", "bucket_general", "global", "fallback"])
+@pytest.fixture(autouse=True, params=["launches", "map0", "map1", "dedup", "cluster", "bucket_general", "global", "fallback"])
 def hv_mode(request):
     """Every test runs against all hard-voxelize implementations behind the one entry point: the
     bucket path as a launch sequence (default; record kernels where P == 5 and C = 4 / 5), the record
@@ -31,7 +31,9 @@ def hv_mode(request):
     _cabi.debug_set("hv_warp_dedup", 1 if mode == "dedup" else 0)
     _cabi.debug_set("hv_force_overflow", 1 if mode == "fallback" else 0)
     _cabi.debug_set("hv_bucket_variant", 1 if mode == "bucket_general" else 0)
+    _cabi.debug_set("hv_expand_map", {"map0": 0, "map1": 1}.get(mode, 2))  # record expansion: which tiles a warp takes
     yield mode
+    _cabi.debug_set("hv_expand_map", 2)
     _cabi.debug_set("hv_path", 0)
     _cabi.debug_set("hv_cluster", 0)
     _cabi.debug_set("hv_warp_dedup", 0)
