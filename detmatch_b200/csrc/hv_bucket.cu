@@ -2009,8 +2009,9 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
         // moving window instead of 38 KB regions per CTA -- DRAM takes a narrow write window much better,
         // profiles/r02_summary.md): 4 for batches of 16 frames and more (64 frames: 3 / 4 / 5 tiles = 0.3508 /
         // 0.3452 / 0.3481 ms, consecutive tiles: 0.3553; 32 frames 0.1868 / 0.1850 / 0.1867), 3 below (4 frames:
-        // 0.0350 / 0.0388); `hv_expand_tiles` overrides
-        const int pipe_tiles = g_opt_expand_tiles > 0 ? (int)g_opt_expand_tiles : (wv >= 16 ? 4 : 3);
+        // 0.0350 / 0.0388; C1, 16 frames of 16 000 voxels: 3); `hv_expand_tiles` overrides
+        // (the rule: 4 when the voxel capacity of the wave fills the GPU's 1184 CTA slots twice over with 4-tile warps)
+        const int pipe_tiles = g_opt_expand_tiles > 0 ? (int)g_opt_expand_tiles : (vmax * wv >= 2ll * 1184 * kExpWarps * 4 * 32 ? 4 : 3);
         const int pper = kExpWarps * pipe_tiles * 32;
         const dim3 pgrid((unsigned)((vmax + pper - 1) / pper), (unsigned)wv);
         const int32_t* vn = voxel_num + f0;
