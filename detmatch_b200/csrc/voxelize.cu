@@ -469,7 +469,8 @@ extern "C" int pcfe_debug_axis_sweep(float lo, float vs, float hi, uint64_t* out
 // (target points per bucket), "hv_wave" (frames per launch sequence), "hv_bucket_variant" (1: general
 // kernels instead of the record path), "hv_expand_variant" (1: un-pipelined expansion kernels),
 // "hv_expand_prefetch" (frames of L2 prefetch distance), "hv_no_fast_div", "hv_pdl",
-// "hv_expand_ctas" (persistent expansion), "pib_grid" (0: brute-force first-hit point-in-box assignment).  Returns
+// "hv_expand_ctas" (persistent expansion), "hv_expand_map" (record expansion, tiles of a warp: 0 consecutive, 1 round-robin
+// inside the CTA, 2 round-robin over the frame = default), "pib_grid" (0: brute-force first-hit point-in-box assignment).  Returns
 // PCFE_ERR_SHAPE for an unknown name.
 extern "C" int pcfe_debug_set(const char* name, int value) {
   if (!name) return PCFE_ERR_NULL;
