@@ -1421,7 +1421,8 @@ hvb_expand_rec_kernel(const __grid_constant__ HvBatch batch, const HvbWork w, co
   const float* __restrict__ pts = fr.pts;
   // tile of the warp's step `it`: base + it * tstride.  map 0: a warp's tiles are consecutive; 1: the CTA's
   // tiles are dealt to its warps round-robin (the CTA writes one contiguous run per step); 2: the frame's
-  // tiles are dealt to all its warps round-robin (the frame is written as one moving window)
+  // tiles are dealt to all its warps round-robin (the frame's CTAs sweep it together: what they gather at any moment
+  // comes from one narrow band of the frame)
   int tbase = (bx * kExpWarps + wid) * pipe_tiles, tstride = 1;
   if (map == 1) {
     tbase = bx * kExpWarps * pipe_tiles + wid;
@@ -2005,9 +2006,9 @@ static int hvb_run_waves(const pcfe_frame_t* frames, int num_frames, int c, cons
         ProfScope ps("hvb_expand", st);
         const int fdiv = fast_div_sizes_ok(p.g) && !g_opt_no_fast_div ? 1 : 0;
         const int64_t vmax = std::max<int64_t>(std::min<int64_t>(max_voxels, wn_max), 1);
-        // tiles per warp, dealt round-robin over the frame's warps (hv_expand_map = 2: the frame is written as a
-        // moving window instead of 38 KB regions per CTA -- DRAM takes a narrow write window much better,
-        // profiles/r02_summary.md): 4 for batches of 16 frames and more (64 frames: 3 / 4 / 5 tiles = 0.3508 /
+        // tiles per warp, dealt round-robin over the frame's warps (hv_expand_map = 2: the frame's CTAs sweep it
+        // together, so the rows / records gathered at any moment come from one narrow band of the frame instead of
+        // one 38 KB region per CTA -- the read side's locality, not the stores', profiles/r02_summary.md): 4 for batches of 16 frames and more (64 frames: 3 / 4 / 5 tiles = 0.3508 /
         // 0.3452 / 0.3481 ms, consecutive tiles: 0.3553; 32 frames 0.1868 / 0.1850 / 0.1867), 3 below (4 frames:
         // 0.0350 / 0.0388; C1, 16 frames of 16 000 voxels: 3); `hv_expand_tiles` overrides
         // (the rule: 4 when the voxel capacity of the wave fills the GPU's 1184 CTA slots twice over with 4-tile warps)
